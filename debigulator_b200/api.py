@@ -1,0 +1,198 @@
+"""ctypes binding of libdebigulator_b200.so (include/debigulator_b200.h)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdebigulator_b200.so")
+_lib = None
+
+STATUS_NAMES = {
+    0: "ok", 1: "cap_lt_input", 2: "input_too_small", 3: "too_large", 4: "stored_len", 5: "bad_table",
+    6: "bad_code", 7: "bad_symbol", 8: "bad_distance", 9: "out_overflow", 10: "truncated", 11: "bad_repeat",
+    12: "container", 13: "crc", 14: "filter", 15: "short_stream",
+}
+KIND_INFLATE, KIND_GZ, KIND_PNG = 0, 1, 2
+
+
+class DebigulatorError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """Loads the CUDA library. There is deliberately no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise DebigulatorError(
+            f"{_LIB_PATH} is missing: build it with `python -m debigulator_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(_LIB_PATH, mode=C.RTLD_LOCAL)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.dbg_version.restype = i32
+    L.dbg_device_count.restype = i32
+    L.dbg_create.argtypes = [i32]
+    L.dbg_create.restype = vp
+    L.dbg_destroy.argtypes = [vp]
+    L.dbg_destroy.restype = None
+    L.dbg_last_error.argtypes = [vp]
+    L.dbg_last_error.restype = C.c_char_p
+    L.dbg_ctx_device.argtypes = [vp]
+    L.dbg_ctx_device.restype = i32
+    L.dbg_kernel_launches.argtypes = [vp]
+    L.dbg_kernel_launches.restype = u64
+    L.dbg_profile_enable.argtypes = [vp, i32]
+    L.dbg_profile_enable.restype = i32
+    L.dbg_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.dbg_profile_read.restype = i32
+    L.dbg_synchronize.argtypes = [vp]
+    L.dbg_synchronize.restype = i32
+    for name in ("dbg_inflate_batch", "dbg_decode_gz_batch"):
+        f = getattr(L, name)
+        f.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
+        f.restype = i32
+    L.dbg_decode_png_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.dbg_decode_png_batch.restype = i32
+    L.dbg_decode_batch_packed.argtypes = [vp, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dbg_decode_batch_packed.restype = i32
+    for name in ("dbg_inflate_batch_device", "dbg_decode_gz_batch_device"):
+        f = getattr(L, name)
+        f.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        f.restype = i32
+    L.dbg_png_scratch_bytes.argtypes = [u64, u64, u64]
+    L.dbg_png_scratch_bytes.restype = u64
+    L.dbg_decode_png_batch_device.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, u64, u64, vp]
+    L.dbg_decode_png_batch_device.restype = i32
+    L.decode_png_get_width_height.argtypes = [vp, u64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                              C.POINTER(C.c_uint8)]
+    L.decode_png_get_width_height.restype = None
+    _lib = L
+    return L
+
+
+def png_get_width_height(data: bytes):
+    """decode_png_get_width_height (decode_png.h:69-75): returns (good, w, h). Host only."""
+    L = load_library()
+    w, h, g = C.c_uint32(0), C.c_uint32(0), C.c_uint8(0)
+    buf = C.create_string_buffer(bytes(data), len(data))
+    L.decode_png_get_width_height(buf, len(data), C.byref(w), C.byref(h), C.byref(g))
+    return int(g.value), int(w.value), int(h.value)
+
+
+def _ptr(t):
+    """Device / host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class Context:
+    """One decode context per GPU (dbg_create). Raises if no CUDA device is usable."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = self.L.dbg_create(int(device))
+        if not self.h:
+            raise DebigulatorError("dbg_create failed: " + self.L.dbg_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dbg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DebigulatorError(f"{what} failed ({rc}): " + self.L.dbg_last_error(self.h).decode())
+
+    @property
+    def kernel_launches(self):
+        return int(self.L.dbg_kernel_launches(self.h))
+
+    def profile_enable(self, on=True):
+        self._check(self.L.dbg_profile_enable(self.h, 1 if on else 0), "dbg_profile_enable")
+
+    def profile_read(self):
+        """(total inflate-kernel ms, launches) since profile_enable."""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        self._check(self.L.dbg_profile_read(self.h, C.byref(ms), C.byref(n)), "dbg_profile_read")
+        return float(ms.value), int(n.value)
+
+    def synchronize(self):
+        self._check(self.L.dbg_synchronize(self.h), "dbg_synchronize")
+
+    # ---- host-buffer batches (lists of bytes in, lists of bytes out) ----------
+    def _pointer_batch(self, fn, items, caps):
+        n = len(items)
+        bufs = [C.create_string_buffer(bytes(d), max(len(d), 1)) for d in items]
+        outs = [C.create_string_buffer(max(int(c), 1)) for c in caps]
+        in_p = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        out_p = (C.c_void_p * n)(*[C.addressof(b) for b in outs])
+        in_sz = (C.c_uint64 * n)(*[len(d) for d in items])
+        cap = (C.c_uint64 * n)(*[int(c) for c in caps])
+        out_sz = (C.c_uint64 * n)()
+        return n, bufs, outs, in_p, out_p, in_sz, cap, out_sz
+
+    def inflate_batch(self, streams, caps):
+        """dbg_inflate_batch: returns [(good, bytes)]."""
+        n, bufs, outs, in_p, out_p, in_sz, cap, out_sz = self._pointer_batch(None, streams, caps)
+        good = (C.c_uint32 * n)()
+        self._check(self.L.dbg_inflate_batch(self.h, n, in_p, in_sz, out_p, cap, out_sz, good), "dbg_inflate_batch")
+        return [(int(good[i]), outs[i].raw[: out_sz[i]] if good[i] else b"") for i in range(n)]
+
+    def decode_gz_batch(self, members, caps):
+        n, bufs, outs, in_p, out_p, in_sz, cap, out_sz = self._pointer_batch(None, members, caps)
+        good = (C.c_uint32 * n)()
+        self._check(self.L.dbg_decode_gz_batch(self.h, n, in_p, in_sz, out_p, cap, out_sz, good), "dbg_decode_gz_batch")
+        return [(int(good[i]), outs[i].raw[: out_sz[i]] if good[i] else b"") for i in range(n)]
+
+    def decode_png_batch(self, files):
+        """dbg_decode_png_batch: returns [(good, w, h, rgba bytes)]."""
+        dims = [png_get_width_height(f) for f in files]
+        caps = [(w * h * 4 if g else 0) for g, w, h in dims]
+        n, bufs, outs, in_p, out_p, in_sz, cap, _ = self._pointer_batch(None, files, caps)
+        good = (C.c_uint8 * n)()
+        self._check(self.L.dbg_decode_png_batch(self.h, n, in_p, in_sz, out_p, cap, good), "dbg_decode_png_batch")
+        return [(int(good[i]), dims[i][1], dims[i][2], outs[i].raw[: caps[i]] if good[i] else b"") for i in range(n)]
+
+    # ---- packed host arenas (numpy uint8 arrays, ideally pinned) --------------
+    def decode_packed(self, kind, h_in, in_off, in_size, h_out, out_off, out_cap):
+        n = len(in_off)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        in_size = np.ascontiguousarray(in_size, dtype=np.uint64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+        out_cap = np.ascontiguousarray(out_cap, dtype=np.uint64)
+        out_size = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.uint32)
+        self._check(self.L.dbg_decode_batch_packed(self.h, int(kind), n, _ptr(h_in), _ptr(in_off), _ptr(in_size),
+                                                   _ptr(h_out), _ptr(out_off), _ptr(out_cap), _ptr(out_size),
+                                                   _ptr(status)), "dbg_decode_batch_packed")
+        return out_size, status
+
+    # ---- device-resident batches (torch CUDA tensors; offsets as int64) -------
+    def inflate_device(self, d_in, in_off, in_size, d_out, out_off, out_cap, out_size, status, order=None,
+                       stream=None, gz=False):
+        fn = self.L.dbg_decode_gz_batch_device if gz else self.L.dbg_inflate_batch_device
+        self._check(fn(self.h, in_off.numel(), _ptr(d_in), _ptr(in_off), _ptr(in_size), _ptr(d_out), _ptr(out_off),
+                       _ptr(out_cap), _ptr(out_size), _ptr(status), _ptr(order), stream),
+                    "dbg_decode_gz_batch_device" if gz else "dbg_inflate_batch_device")
+
+    def png_device(self, d_in, in_off, in_size, d_out, out_off, out_cap, status, total_in, total_rgba, stream=None):
+        self._check(self.L.dbg_decode_png_batch_device(self.h, in_off.numel(), _ptr(d_in), _ptr(in_off), _ptr(in_size),
+                                                       _ptr(d_out), _ptr(out_off), _ptr(out_cap), _ptr(status),
+                                                       int(total_in), int(total_rgba), stream),
+                    "dbg_decode_png_batch_device")

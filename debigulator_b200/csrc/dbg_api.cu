@@ -1,0 +1,441 @@
+// dbg_api.cu -- host side of libdebigulator_b200.so: context, batched C-ABI
+// (include/debigulator_b200.h) and kernel launches. No CPU decode path exists
+// in this library: every entry point needs a CUDA device and reports
+// DBG_ERR_NO_DEVICE / DBG_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <utility>
+#include <vector>
+
+#include "../../include/debigulator_b200.h"
+#include "kernels.cuh"
+#include "png_kernels.cuh"
+
+static thread_local char g_err[512] = "";
+
+static void set_err(dbg_ctx *ctx, const char *fmt, ...);
+
+// Grow-only buffer (device or pinned host).
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned_host = false;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        release();
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            return e;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p) {
+            if (pinned_host) cudaFreeHost(p);
+            else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct dbg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    char err[512] = "";
+    // optional per-launch timing of the dominant (inflate) kernel, for roofline reports
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    // device-side scratch
+    Buf d_counter;                 // work-queue heads
+    Buf d_meta;                    // derived descriptors (gzip payloads, PNG streams)
+    Buf d_png_scratch;             // compacted IDAT + filtered scanlines
+    // host-API staging
+    Buf d_in, d_out, d_desc;       // arenas + descriptor tables
+    Buf h_in, h_out, h_desc;       // pinned mirrors
+    dbg_ctx()
+    {
+        h_in.pinned_host = h_out.pinned_host = h_desc.pinned_host = true;
+    }
+};
+
+static void set_err(dbg_ctx *ctx, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (ctx) memcpy(ctx->err, g_err, sizeof(g_err));
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return DBG_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+extern "C" int dbg_version(void) { return 100; }
+
+extern "C" int dbg_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_err(nullptr, "cudaGetDeviceCount: %s -- this library has no CPU path", cudaGetErrorString(e));
+        return DBG_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+extern "C" const char *dbg_last_error(const dbg_ctx *ctx) { return ctx ? ctx->err : g_err; }
+extern "C" int dbg_ctx_device(const dbg_ctx *ctx) { return ctx ? ctx->device : -1; }
+extern "C" uint64_t dbg_kernel_launches(const dbg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" dbg_ctx *dbg_create(int device)
+{
+    int n = dbg_device_count();
+    if (n <= 0) {
+        if (n == 0) set_err(nullptr, "no CUDA device visible -- this library has no CPU path");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        set_err(nullptr, "device %d out of range (0..%d)", device, n - 1);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        set_err(nullptr, "cannot select device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    if (prop.major < 10) {
+        set_err(nullptr, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    dbg_ctx *ctx = new dbg_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_err(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return nullptr;
+    }
+    size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
+    cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+    dbg::png_configure_kernels();
+    return ctx;
+}
+
+extern "C" void dbg_destroy(dbg_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    Buf *all[] = {&ctx->d_counter, &ctx->d_meta, &ctx->d_png_scratch, &ctx->d_in, &ctx->d_out,
+                  &ctx->d_desc,    &ctx->h_in,   &ctx->h_out,         &ctx->h_desc};
+    for (Buf *b : all) b->release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int dbg_profile_enable(dbg_ctx *ctx, int on)
+{
+    if (!ctx) return DBG_ERR_ARG;
+    ctx->profiling = on != 0;
+    ctx->prof_used = 0;
+    return DBG_OK;
+}
+
+// Sum of the device durations (ms) of the inflate kernels launched since
+// dbg_profile_enable(ctx, 1), and how many there were. Waits for them.
+extern "C" int dbg_profile_read(dbg_ctx *ctx, double *total_ms, uint64_t *launches)
+{
+    if (!ctx || !total_ms || !launches) return DBG_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    double sum = 0;
+    for (size_t i = 0; i < ctx->prof_used; i++) {
+        float ms = 0;
+        CU(cudaEventSynchronize(ctx->prof_events[i].second));
+        CU(cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = ctx->prof_used;
+    ctx->prof_used = 0;
+    return DBG_OK;
+}
+
+extern "C" int dbg_synchronize(dbg_ctx *ctx)
+{
+    if (!ctx) return DBG_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DBG_OK;
+}
+
+// ------------------------------------------------------------------ launches --
+static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s)
+{
+    a.counter = d_counter;
+    CU(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), s));
+    uint32_t ctas_needed = (a.n + dbg::INFLATE_WARPS_PER_CTA - 1) / dbg::INFLATE_WARPS_PER_CTA;
+    uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);
+    size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->profiling) {
+        if (ctx->prof_used == ctx->prof_events.size()) {
+            CU(cudaEventCreate(&e0));
+            CU(cudaEventCreate(&e1));
+            ctx->prof_events.push_back({e0, e1});
+        }
+        e0 = ctx->prof_events[ctx->prof_used].first;
+        e1 = ctx->prof_events[ctx->prof_used].second;
+        ctx->prof_used++;
+        CU(cudaEventRecord(e0, s));
+    }
+    dbg::inflate_batch_kernel<<<grid, dbg::INFLATE_THREADS, smem, s>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (e1) CU(cudaEventRecord(e1, s));
+    return DBG_OK;
+}
+
+extern "C" int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                        const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                                        const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
+                                        const uint32_t *d_order, void *stream)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!d_in || !d_in_off || !d_in_size || !d_out || !d_out_off || !d_out_cap || !d_out_size || !d_status ||
+        n > 0x7fffffffull) {
+        set_err(ctx, "dbg_inflate_batch_device: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    CU(ctx->d_counter.reserve(64));
+    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, d_order, nullptr, (uint32_t)n};
+    return launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
+}
+
+extern "C" int dbg_decode_gz_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                          const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                                          const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
+                                          const uint32_t *d_order, void *stream)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!d_in || !d_in_off || !d_in_size || !d_out || !d_out_off || !d_out_cap || !d_out_size || !d_status ||
+        n > 0x7fffffffull) {
+        set_err(ctx, "dbg_decode_gz_batch_device: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    CU(ctx->d_counter.reserve(64));
+    CU(ctx->d_meta.reserve(n * 20 + 64));
+    uint64_t *p_off = (uint64_t *)ctx->d_meta.p;
+    uint64_t *p_size = p_off + n;
+    uint32_t *pre = (uint32_t *)(p_size + n);
+    dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, p_off, p_size, pre);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    dbg::InflateBatch a{d_in, p_off, p_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, pre, d_order, nullptr, (uint32_t)n};
+    return launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
+}
+
+extern "C" uint64_t dbg_png_scratch_bytes(uint64_t n, uint64_t total_in_bytes, uint64_t total_rgba_bytes)
+{
+    return dbg::png_scratch_bytes(n, total_in_bytes, total_rgba_bytes);
+}
+
+extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                           const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                                           const uint64_t *d_out_cap, uint32_t *d_status, uint64_t total_in_bytes,
+                                           uint64_t total_rgba_bytes, void *stream)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!d_in || !d_in_off || !d_in_size || !d_out || !d_out_off || !d_out_cap || !d_status || n > 0x7fffffffull) {
+        set_err(ctx, "dbg_decode_png_batch_device: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    CU(ctx->d_counter.reserve(64));
+    CU(ctx->d_png_scratch.reserve(dbg::png_scratch_bytes(n, total_in_bytes, total_rgba_bytes)));
+    dbg::PngLayout lay = dbg::png_layout((uint8_t *)ctx->d_png_scratch.p, n, total_in_bytes, total_rgba_bytes);
+
+    // 1. container walk + CRC-32 + IDAT gather (one warp per image)
+    dbg::PngBatch pb{d_in, d_in_off, d_in_size, d_out_cap, (uint32_t)n, lay};
+    int rc = dbg::png_launch_scan(pb, ctx->sm_count, s);
+    ctx->launches += 2;
+    if (rc) CU((cudaError_t)rc);
+    // 2. inflate the compacted zlib payloads into the filtered-scanline buffers
+    dbg::InflateBatch a{lay.idat, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
+                        lay.pre_status, nullptr, nullptr, (uint32_t)n};
+    rc = launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
+    if (rc) return rc;
+    // 3. un-filter (+ palette / RGB expansion) straight into the caller's RGBA
+    rc = dbg::png_launch_unfilter(pb, d_out, d_out_off, d_status, ctx->sm_count, s);
+    ctx->launches++;
+    if (rc) CU((cudaError_t)rc);
+    return DBG_OK;
+}
+
+// -------------------------------------------------------------- host batches --
+static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
+                                       const uint64_t *in_size, uint8_t *h_out, const uint64_t *out_off,
+                                       const uint64_t *out_cap, uint64_t *out_size, uint32_t *status)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!h_in || !in_off || !in_size || !h_out || !out_off || !out_cap || !out_size || !status || kind < 0 || kind > 2 ||
+        n > 0x7fffffffull) {
+        set_err(ctx, "dbg_decode_batch_packed: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    uint64_t in_span = 0, out_span = 0, tot_in = 0, tot_out = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        in_span = std::max(in_span, in_off[i] + in_size[i]);
+        out_span = std::max(out_span, out_off[i] + out_cap[i]);
+        tot_in += in_size[i];
+        tot_out += out_cap[i];
+    }
+    // descriptor block: in_off, in_size, out_off, out_cap, out_size (u64 x n each), status + order (u32 x n each)
+    size_t desc_bytes = n * (5 * 8 + 2 * 4);
+    CU(ctx->h_desc.reserve(desc_bytes));
+    CU(ctx->d_desc.reserve(desc_bytes));
+    CU(ctx->d_in.reserve(in_span + 64));
+    CU(ctx->d_out.reserve(out_span + 64));
+    uint64_t *hd = (uint64_t *)ctx->h_desc.p;
+    memcpy(hd, in_off, n * 8);
+    memcpy(hd + n, in_size, n * 8);
+    memcpy(hd + 2 * n, out_off, n * 8);
+    memcpy(hd + 3 * n, out_cap, n * 8);
+    uint32_t *h_status = (uint32_t *)(hd + 5 * n);
+    uint32_t *h_order = h_status + n;
+    std::iota(h_order, h_order + n, 0u);
+    std::stable_sort(h_order, h_order + n, [&](uint32_t a, uint32_t b) { return in_size[a] > in_size[b]; });
+    uint64_t *dd = (uint64_t *)ctx->d_desc.p;
+    uint32_t *d_status = (uint32_t *)(dd + 5 * n);
+    uint32_t *d_order = d_status + n;
+    CU(cudaMemcpyAsync(ctx->d_in.p, h_in, in_span, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
+    CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
+    int rc;
+    if (kind == 0)
+        rc = dbg_inflate_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p, dd + 2 * n,
+                                      dd + 3 * n, dd + 4 * n, d_status, d_order, s);
+    else if (kind == 1)
+        rc = dbg_decode_gz_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p,
+                                        dd + 2 * n, dd + 3 * n, dd + 4 * n, d_status, d_order, s);
+    else
+        rc = dbg_decode_png_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p,
+                                         dd + 2 * n, dd + 3 * n, d_status, tot_in, tot_out, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_out, ctx->d_out.p, out_span, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hd + 4 * n, dd + 4 * n, n * 8 + n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(status, h_status, n * 4);
+    if (kind == 2) {
+        for (uint64_t i = 0; i < n; i++) out_size[i] = status[i] == 0 ? out_cap[i] : 0;
+    } else {
+        memcpy(out_size, hd + 4 * n, n * 8);
+    }
+    return DBG_OK;
+}
+
+// pointer-array front ends: pack into the pinned staging arenas, run the packed
+// path, scatter the results.
+static int run_pointer_batch(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                             uint8_t *const *out, const uint64_t *out_cap, uint64_t *out_size, uint32_t *status)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!in || !in_size || !out || !out_cap || !status) {
+        set_err(ctx, "batch call: NULL argument");
+        return DBG_ERR_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> in_off(n), out_off(n), sizes(n);
+    uint64_t ti = 0, to = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        in_off[i] = ti;
+        ti += align_up(in_size[i] + 16, 16);
+        out_off[i] = to;
+        to += align_up(out_cap[i], 16);
+    }
+    CU(ctx->h_in.reserve(ti + 64));
+    CU(ctx->h_out.reserve(to + 64));
+    uint8_t *hi = (uint8_t *)ctx->h_in.p;
+    for (uint64_t i = 0; i < n; i++) {
+        if (in_size[i] && !in[i]) {
+            set_err(ctx, "batch call: item %llu has a NULL input", (unsigned long long)i);
+            return DBG_ERR_ARG;
+        }
+        memcpy(hi + in_off[i], in[i], in_size[i]);
+        memset(hi + in_off[i] + in_size[i], 0, align_up(in_size[i] + 16, 16) - in_size[i]);
+    }
+    int rc = dbg_decode_batch_packed(ctx, kind, n, hi, in_off.data(), in_size, (uint8_t *)ctx->h_out.p, out_off.data(),
+                                     out_cap, sizes.data(), status);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; i++) {
+        if (status[i] == 0 && out[i]) memcpy(out[i], (uint8_t *)ctx->h_out.p + out_off[i], sizes[i]);
+        if (out_size) out_size[i] = sizes[i];
+    }
+    return DBG_OK;
+}
+
+extern "C" int dbg_inflate_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                                 uint8_t *const *out, const uint64_t *out_cap, uint64_t *out_size, uint32_t *good)
+{
+    int rc = run_pointer_batch(ctx, 0, n, in, in_size, out, out_cap, out_size, good);
+    if (rc == DBG_OK)
+        for (uint64_t i = 0; i < n; i++) good[i] = good[i] == 0 ? 1u : 0u;
+    return rc;
+}
+
+extern "C" int dbg_decode_gz_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                                   uint8_t *const *out, const uint64_t *out_cap, uint64_t *out_size, uint32_t *good)
+{
+    int rc = run_pointer_batch(ctx, 1, n, in, in_size, out, out_cap, out_size, good);
+    if (rc == DBG_OK)
+        for (uint64_t i = 0; i < n; i++) good[i] = good[i] == 0 ? 1u : 0u;
+    return rc;
+}
+
+extern "C" int dbg_decode_png_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                                    uint8_t *const *out_rgba, const uint64_t *rgba_size, uint8_t *good)
+{
+    if (!good) return DBG_ERR_ARG;
+    std::vector<uint32_t> st(n);
+    int rc = run_pointer_batch(ctx, 2, n, in, in_size, out_rgba, rgba_size, nullptr, st.data());
+    if (rc == DBG_OK)
+        for (uint64_t i = 0; i < n; i++) good[i] = st[i] == 0 ? 1 : 0;
+    return rc;
+}

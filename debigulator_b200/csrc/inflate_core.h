@@ -1,0 +1,483 @@
+// inflate_core.h -- warp-per-stream DEFLATE decoder (device code, sm_100a).
+//
+// Replaces the whole of the reference's inflate() (inflate.c:786-1965): bit
+// reader (:225-278, :367-413), stored / fixed / dynamic block parsing
+// (:919-989, :1018-1181, :1182-1667), canonical Huffman build (unpack_huffman
+// :565-706 + huffman_to_hashmap :494-557), symbol decode (:421-474) and the
+// LZ77 copy (:1861-1897). It is a new design, not a translation:
+//
+//   * one warp owns one stream. Symbol decode is executed redundantly and
+//     uniformly by all 32 lanes (same registers, broadcast shared-memory LUT
+//     reads), so there is no divergence and no shuffle on the serial path;
+//     the lanes fan out only where there is parallel work: Huffman table
+//     construction (match_any/ballot ranking, warp scans) and LZ77 / stored
+//     copies (one byte per lane, pattern replication for short distances).
+//   * compressed bytes are staged global -> shared with 16-byte cp.async
+//     (LDGSTS) into a 2 x 512 B per-warp ring, requested one chunk ahead.
+//   * decode tables are two-level: a 9-bit (litlen) / 7-bit (distance) primary
+//     LUT with pre-baked base/extra-bit fields, and a canonical first-code
+//     walk for the rare longer codes -- 4.7 KB of shared memory per warp
+//     instead of the reference's 3 x 792 KB hash maps (inflate.c:112-118).
+//
+// Behavioural parity with the reference's silent, no-assert build is kept where
+// the reference has defined behaviour: the premature
+// end-of-stream rule Q2 (inflate.c:1702-1717), the "code length >= alphabet
+// size" rejection Q3 (:599-602), the min/max code-length bookkeeping Q5
+// (:528-539), BTYPE 3 skipped as an empty block (:990-998), repeat codes
+// running across the litlen/dist boundary (:1412-1416), and the argument checks
+// (:826-844). Where the reference has undefined behaviour (output overflow,
+// reads past the input, symbols 286/287, distance symbols 30/31 handled at
+// :1809) this decoder fails the stream instead.
+#pragma once
+#include "simt.h"
+
+namespace dbg {
+
+// Per-stream status; `good` in the reference's sense is (status == ST_OK).
+enum InflateStatus : uint32_t {
+    ST_OK = 0,
+    ST_CAP_LT_INPUT = 1,    // inflate.c:826 recipient_size < compressed_input_size
+    ST_INPUT_TOO_SMALL = 2, // inflate.c:836 compressed_input_size < 5
+    ST_TOO_LARGE = 3,       // beyond this implementation's 31/32-bit stream limits
+    ST_STORED_LEN = 4,      // inflate.c:949 LEN != ~NLEN
+    ST_BAD_TABLE = 5,       // unpack_huffman failure (:599) or over-subscribed code
+    ST_BAD_CODE = 6,        // hashed_huffman_decode failure (:465-473)
+    ST_BAD_SYMBOL = 7,      // litlen 286/287, distance > 29 (:1809)
+    ST_BAD_DISTANCE = 8,    // inflate.c:1843 distance reaches before the output start
+    ST_OUT_OVERFLOW = 9,    // output capacity exceeded (UB in the reference)
+    ST_TRUNCATED = 10,      // input exhausted at a block boundary / inside a stored block
+    ST_BAD_REPEAT = 11,     // code-length repeat with no previous length
+    ST_CONTAINER = 12,      // set by container parsers (PNG / gzip), not by inflate
+};
+
+struct InflateSmem {
+    uint32_t ring[256];      // 2 x 512 B input ring
+    uint32_t lit_lut[512];   // 9-bit primary litlen table
+    uint32_t dist_lut[128];  // 7-bit primary distance table (also: code-length code table)
+    uint16_t lit_sorted[288];
+    uint16_t lit_first[16], lit_offs[16], lit_cnt[16];
+    uint16_t dist_first[16], dist_offs[16], dist_cnt[16];
+    uint8_t dist_sorted[32];
+    uint8_t lens[320];       // HLIT (<=288) + HDIST (<=32) code lengths
+};
+
+// LUT entry: [3:0] code length (0 = not in the primary table), bit4 literal /
+// plain value, bit5 end-of-block, bit6 length-or-distance with base in [31:16]
+// and extra-bit count in [12:8], bit7 undecodable symbol.
+enum { E_LIT = 0x10, E_EOB = 0x20, E_BASE = 0x40, E_BAD = 0x80 };
+enum { K_CLEN = 0, K_LITLEN = 1, K_DIST = 2 };
+enum { LIT_ROOT = 9, DIST_ROOT = 7 };
+
+template <int KIND>
+DBG_DEV uint32_t make_entry(uint32_t sym, uint32_t l)
+{
+    if (KIND == K_CLEN) return (sym << 16) | E_LIT | l;
+    if (KIND == K_LITLEN) {
+        if (sym < 256) return (sym << 16) | E_LIT | l;
+        if (sym == 256) return E_EOB | l;
+        if (sym > 285) return E_BAD | l;
+        uint32_t i = sym - 257, xb, base;  // inflate.c:716-746
+        if (i < 8) { xb = 0; base = 3 + i; }
+        else if (i == 28) { xb = 0; base = 258; }
+        else { xb = (i >> 2) - 1; base = 3 + ((4 + (i & 3)) << xb); }
+        return (base << 16) | (xb << 8) | E_BASE | l;
+    }
+    if (sym > 29) return E_BAD | l;        // inflate.c:1809
+    uint32_t xb = sym < 4 ? 0 : (sym >> 1) - 1;  // inflate.c:748-779
+    uint32_t base = sym < 4 ? sym + 1 : 1 + ((2 + (sym & 1)) << xb);
+    return (base << 16) | (xb << 8) | E_BASE | l;
+}
+
+// ---------------------------------------------------------------- bit reader --
+struct BitReader {
+    const uint8_t *base;  // 16-byte aligned global address at or below the stream start
+    uint32_t *ring;
+    uint64_t buf;
+    uint32_t bitcnt;
+    uint32_t wpos;   // ring-coordinate index of the word held in `nw`
+    uint32_t nw;     // prefetched next word
+    uint32_t end16;  // ring-coordinate byte offset past which input reads as zero
+
+    DBG_DEVM void load_chunk(uint32_t c)
+    {
+        uint32_t off = (c << 9) + ((uint32_t)simt::lane() << 4);
+        bool in = off < end16;
+        simt::cp_async16(&ring[((c & 1) << 7) + ((uint32_t)simt::lane() << 2)], base + (in ? off : 0), in ? 16 : 0);
+    }
+    DBG_DEVM void maintain()
+    {
+        if (wpos & 64) {  // half way through a chunk: the next one has landed
+            simt::cp_async_wait_all();
+            simt::syncwarp();
+        } else {          // entered a new chunk: recycle the slot behind us
+            simt::syncwarp();
+            load_chunk((wpos >> 7) + 1);
+            simt::cp_async_commit();
+        }
+    }
+    DBG_DEVM uint32_t take()
+    {
+        uint32_t w = nw;
+        wpos++;
+        if ((wpos & 63) == 0) maintain();
+        nw = ring[wpos & 255];
+        return w;
+    }
+    DBG_DEVM void refill()
+    {
+        if (bitcnt < 32) {
+            buf |= (uint64_t)take() << bitcnt;
+            bitcnt += 32;
+        }
+    }
+    DBG_DEVM void consume(uint32_t n)
+    {
+        buf >>= n;
+        bitcnt -= n;
+    }
+    DBG_DEVM uint64_t abs_bits() const { return ((uint64_t)wpos << 5) - bitcnt; }
+    DBG_DEVM void seek(uint64_t bytepos)
+    {
+        uint32_t c = (uint32_t)(bytepos >> 9);
+        simt::cp_async_wait_all();  // nothing from an earlier position may land after this
+        simt::syncwarp();
+        load_chunk(c);
+        load_chunk(c + 1);
+        simt::cp_async_commit();
+        simt::cp_async_wait_all();
+        simt::syncwarp();
+        wpos = (uint32_t)(bytepos >> 2);
+        nw = ring[wpos & 255];
+        uint32_t skip = ((uint32_t)bytepos & 3) << 3;
+        buf = (uint64_t)(take() >> skip);
+        bitcnt = 32 - skip;
+    }
+};
+
+// ------------------------------------------------------------ table builder --
+// Canonical Huffman construction for `n` code lengths (RFC 1951 3.2.2 as in
+// unpack_huffman inflate.c:565-706), executed by the whole warp:
+//   pass 1  per-length histogram via match_any, reference validity rule
+//           (any length >= n fails, :599-602) and the reference's effective
+//           maximum code length (Q5, :528-539) via a warp prefix-min;
+//   scan    first code and sorted-order offset of every length (lane l owns
+//           length l);
+//   pass 2  stable counting sort of the symbols by (length, symbol);
+//   pass 3  primary LUT fill from the sorted order (bit-reversed replication).
+template <int KIND, typename SORTED_T>
+DBG_DEV bool build_table(const uint8_t *lens, int n, int root, uint32_t *lut, SORTED_T *sorted, uint16_t *first,
+                         uint16_t *offs, uint16_t *cnt, uint32_t *eff_max_out)
+{
+    const int ln = simt::lane();
+    if (ln < 16) cnt[ln] = 0;
+    for (int i = ln; i < (1 << root); i += 32) lut[i] = 0;
+    simt::syncwarp();
+
+    uint32_t run_min = 99, emax = 1;
+    bool bad = false;
+    for (int base = 0; base < n; base += 32) {
+        int s = base + ln;
+        uint32_t l = (s < n) ? lens[s] : 0;
+        bad |= (l >= (uint32_t)n);
+        uint32_t m = simt::match_any(l);
+        if (l && ln == 31 - simt::clz(m)) cnt[l] = (uint16_t)(cnt[l] + simt::popc(m));
+        uint32_t pm = l ? l : 99;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = simt::shfl_up(pm, d);
+            if (ln >= d && t < pm) pm = t;
+        }
+        uint32_t excl = simt::shfl_up(pm, 1);
+        if (ln == 0) excl = 99;
+        if (run_min < excl) excl = run_min;
+        uint32_t cand = (l && excl <= l) ? l : 0;
+        for (int d = 16; d; d >>= 1) {
+            uint32_t t = simt::shfl_xor(cand, d);
+            if (t > cand) cand = t;
+        }
+        if (cand > emax) emax = cand;
+        uint32_t last = simt::shfl(pm, 31);
+        if (last < run_min) run_min = last;
+        simt::syncwarp();
+    }
+    if (simt::any(bad)) return false;
+
+    uint32_t c_l = (ln >= 1 && ln < 16) ? cnt[ln] : 0;
+    uint32_t incl = c_l;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = simt::shfl_up(incl, d);
+        if (ln >= d) incl += t;
+    }
+    uint32_t code = 0;
+    for (int j = 1; j < 16; j++) {
+        uint32_t cj = simt::shfl(c_l, j);
+        if (j < ln && ln < 16) code += cj << (ln - j);
+    }
+    bool over = (ln >= 1 && ln < 16 && c_l && code + c_l > (1u << ln));
+    if (ln < 16) {
+        first[ln] = (uint16_t)code;
+        offs[ln] = (uint16_t)(incl - c_l);
+    }
+    uint32_t total = simt::shfl(incl, 15);
+    if (simt::any(over)) return false;
+    simt::syncwarp();
+
+    for (int base = 0; base < n; base += 32) {
+        int s = base + ln;
+        uint32_t l = (s < n) ? lens[s] : 0;
+        uint32_t m = simt::match_any(l);
+        uint32_t b = l ? offs[l] : 0;
+        simt::syncwarp();
+        if (l) {
+            if (ln == 31 - simt::clz(m)) offs[l] = (uint16_t)(b + simt::popc(m));
+            sorted[b + simt::popc(m & ((1u << ln) - 1))] = (SORTED_T)s;
+        }
+        simt::syncwarp();
+    }
+    if (ln >= 1 && ln < 16) offs[ln] = (uint16_t)(offs[ln] - cnt[ln]);
+    simt::syncwarp();
+
+    for (uint32_t base = 0; base < total; base += 32) {
+        uint32_t k = base + ln;
+        if (k < total) {
+            uint32_t s = sorted[k];
+            uint32_t l = lens[s];
+            if (l <= (uint32_t)root && l <= emax) {
+                uint32_t c = first[l] + (k - offs[l]);
+                uint32_t rev = simt::brev(c) >> (32 - l);
+                uint32_t e = make_entry<KIND>(s, l);
+                for (uint32_t j = rev; j < (1u << root); j += (1u << l)) lut[j] = e;
+            }
+        }
+    }
+    simt::syncwarp();
+    *eff_max_out = emax;
+    return true;
+}
+
+// Codes longer than the primary index: canonical walk, shortest length first,
+// which is the order the reference probes in (inflate.c:437-463).
+template <int KIND, typename SORTED_T>
+DBG_DEV_NOINLINE uint32_t slow_decode(uint32_t bits, int root, uint32_t maxlen, const SORTED_T *sorted,
+                                      const uint16_t *first, const uint16_t *offs, const uint16_t *cnt)
+{
+    uint32_t v = simt::brev(bits);
+    for (uint32_t l = (uint32_t)root + 1; l <= maxlen; l++) {
+        uint32_t idx = (v >> (32 - l)) - first[l];
+        if (idx < cnt[l]) return make_entry<KIND>(sorted[offs[l] + idx], l);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------- copies --
+// LZ77 match (inflate.c:1861-1897). The caller guarantees dist <= pos and
+// pos + len <= cap. All lanes participate.
+DBG_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    uint8_t *dst = out + pos;
+    const uint8_t *src = dst - dist;
+    simt::syncwarp();  // earlier stores by other lanes are visible from here on
+    if (dist >= len) {
+        for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
+    } else if (dist >= 32) {
+        for (uint32_t b = 0; b < len; b += 32) {
+            uint32_t i = b + ln;
+            if (i < len) dst[i] = src[i];
+            simt::syncwarp();
+        }
+    } else {
+        // overlapping short distance: replicate the dist-byte pattern from registers
+        uint32_t idx = ln % dist;
+        uint32_t v = src[idx];
+        uint32_t step = 32 % dist;
+        for (uint32_t b = 0; b < len; b += 32) {
+            uint32_t x = simt::shfl(v, (int)idx);
+            if (b + ln < len) dst[b + ln] = (uint8_t)x;
+            idx += step;
+            if (idx >= dist) idx -= dist;
+        }
+    }
+}
+
+DBG_DEV uint32_t swizzle_at(uint32_t i)
+{
+    // code-length alphabet order 16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15 (inflate.c:25-26)
+    const uint64_t lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) |
+                        (9ull << 30) | (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
+    const uint64_t hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
+    return (uint32_t)((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31);
+}
+
+// ---------------------------------------------------------------- the stream --
+// Decodes one raw DEFLATE stream of `in_size` bytes at `in` into out[0..cap).
+// Every lane of the warp must call it with identical arguments; the return
+// value and *final_size are uniform. `in` may have any alignment; bytes from
+// (in & ~15) up to the 16-byte boundary at or after in + in_size must be readable.
+DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap,
+                              uint64_t *final_size)
+{
+    *final_size = 0;
+    if (cap < in_size) return ST_CAP_LT_INPUT;
+    if (in_size < 5) return ST_INPUT_TOO_SMALL;
+    if (in_size >= (1ull << 31) || cap >= (1ull << 32)) return ST_TOO_LARGE;
+
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint32_t mis = (uint32_t)((uintptr_t)in & 15);
+    const uint64_t end_byte = (uint64_t)mis + in_size;  // ring coordinates
+    BitReader br;
+    br.base = in - mis;
+    br.ring = sm->ring;
+    br.end16 = (uint32_t)((end_byte + 15) & ~15ull);
+    br.seek(mis);
+
+    // Q2 (inflate.c:1702-1717): the stream ends, successfully, as soon as the
+    // byte cursor ceil(P/8) has reached in_size, i.e. P >= 8*in_size - 7.
+    const uint64_t q2_limit = 8 * end_byte - 7;
+    const uint32_t q2_w = (uint32_t)(q2_limit >> 5);
+
+    uint32_t pos = 0;
+    const uint32_t cap32 = (uint32_t)cap;
+    uint32_t lit_max = 0, dist_max = 0;
+    bool more = true;
+    while (more) {
+        if (br.abs_bits() >= 8 * end_byte) return ST_TRUNCATED;
+        br.refill();
+        uint32_t hdr = (uint32_t)br.buf & 7;
+        br.consume(3);
+        if (hdr & 1) more = false;
+        uint32_t btype = hdr >> 1;
+        if (btype == 0) {
+            br.consume(br.bitcnt & 7);
+            br.refill();
+            uint32_t len = (uint32_t)br.buf & 0xffff;
+            uint32_t nlen = ((uint32_t)br.buf >> 16) & 0xffff;
+            br.consume(32);
+            if (len != (~nlen & 0xffff)) return ST_STORED_LEN;
+            if (len) {
+                uint64_t bytepos = br.abs_bits() >> 3;
+                if (bytepos + len > end_byte) return ST_TRUNCATED;
+                if ((uint64_t)pos + len > cap32) return ST_OUT_OVERFLOW;
+                const uint8_t *src = br.base + bytepos;
+                uint8_t *dst = out + pos;
+                for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
+                pos += len;
+                br.seek(bytepos + len);
+            }
+            continue;
+        }
+        if (btype == 3) continue;  // inflate.c:990-998: ignored in the no-assert build
+
+        uint32_t hlit = 288, hdist = 32;
+        if (btype == 1) {
+            // fixed code (inflate.c:1035-1084); distances are 5-bit codes (:1783-1788)
+            for (uint32_t i = ln; i < 320; i += 32)
+                sm->lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
+            simt::syncwarp();
+        } else {
+            br.refill();
+            hlit = ((uint32_t)br.buf & 31) + 257;
+            hdist = (((uint32_t)br.buf >> 5) & 31) + 1;
+            uint32_t hclen = (((uint32_t)br.buf >> 10) & 15) + 4;
+            br.consume(14);
+            if (ln < 19) sm->lens[ln] = 0;
+            simt::syncwarp();
+            for (uint32_t i = 0; i < hclen; i++) {
+                br.refill();
+                if (ln == 0) sm->lens[swizzle_at(i)] = (uint8_t)((uint32_t)br.buf & 7);
+                br.consume(3);
+            }
+            simt::syncwarp();
+            uint32_t cl_max;
+            if (!build_table<K_CLEN, uint8_t>(sm->lens, 19, DIST_ROOT, sm->dist_lut, sm->dist_sorted, sm->dist_first,
+                                              sm->dist_offs, sm->dist_cnt, &cl_max))
+                return ST_BAD_TABLE;
+            const uint32_t n = hlit + hdist;
+            uint32_t i = 0, prev = 0;
+            while (i < n) {
+                br.refill();
+                uint32_t e = sm->dist_lut[(uint32_t)br.buf & 127];
+                if ((e & 15) == 0) return ST_BAD_CODE;
+                br.consume(e & 15);
+                uint32_t sym = e >> 16;
+                if (sym < 16) {
+                    if (ln == 0) sm->lens[i] = (uint8_t)sym;
+                    prev = sym;
+                    i++;
+                    continue;
+                }
+                uint32_t rep, val;
+                if (sym == 16) {  // inflate.c:1439-1469
+                    if (i == 0) return ST_BAD_REPEAT;
+                    rep = 3 + ((uint32_t)br.buf & 3);
+                    br.consume(2);
+                    val = prev;
+                } else if (sym == 17) {  // :1471-1488
+                    rep = 3 + ((uint32_t)br.buf & 7);
+                    br.consume(3);
+                    val = 0;
+                } else {  // :1490-1509
+                    rep = 11 + ((uint32_t)br.buf & 127);
+                    br.consume(7);
+                    val = 0;
+                }
+                for (uint32_t k = ln; k < rep; k += 32)
+                    if (i + k < n) sm->lens[i + k] = (uint8_t)val;
+                prev = val;
+                i += rep;
+            }
+            simt::syncwarp();
+        }
+        if (!build_table<K_LITLEN, uint16_t>(sm->lens, (int)hlit, LIT_ROOT, sm->lit_lut, sm->lit_sorted, sm->lit_first,
+                                             sm->lit_offs, sm->lit_cnt, &lit_max))
+            return ST_BAD_TABLE;
+        if (!build_table<K_DIST, uint8_t>(sm->lens + hlit, (int)hdist, DIST_ROOT, sm->dist_lut, sm->dist_sorted,
+                                          sm->dist_first, sm->dist_offs, sm->dist_cnt, &dist_max))
+            return ST_BAD_TABLE;
+
+        for (;;) {
+            if (br.wpos >= q2_w && br.abs_bits() >= q2_limit) {
+                more = false;
+                break;
+            }
+            br.refill();
+            uint32_t e = sm->lit_lut[(uint32_t)br.buf & ((1u << LIT_ROOT) - 1)];
+            if ((e & 15) == 0) {
+                e = slow_decode<K_LITLEN, uint16_t>((uint32_t)br.buf, LIT_ROOT, lit_max, sm->lit_sorted, sm->lit_first,
+                                                    sm->lit_offs, sm->lit_cnt);
+                if (!e) return ST_BAD_CODE;
+            }
+            br.consume(e & 15);
+            if (e & E_LIT) {
+                if (pos >= cap32) return ST_OUT_OVERFLOW;
+                if (ln == 0) out[pos] = (uint8_t)(e >> 16);
+                pos++;
+                continue;
+            }
+            if (e & E_EOB) break;
+            if (e & E_BAD) return ST_BAD_SYMBOL;
+            uint32_t xb = (e >> 8) & 31;
+            uint32_t len = (e >> 16) + ((uint32_t)br.buf & ((1u << xb) - 1));
+            br.consume(xb);
+            br.refill();
+            e = sm->dist_lut[(uint32_t)br.buf & ((1u << DIST_ROOT) - 1)];
+            if ((e & 15) == 0) {
+                e = slow_decode<K_DIST, uint8_t>((uint32_t)br.buf, DIST_ROOT, dist_max, sm->dist_sorted, sm->dist_first,
+                                                 sm->dist_offs, sm->dist_cnt);
+                if (!e) return ST_BAD_CODE;
+            }
+            br.consume(e & 15);
+            if (e & E_BAD) return ST_BAD_SYMBOL;
+            xb = (e >> 8) & 31;
+            uint32_t dist = (e >> 16) + ((uint32_t)br.buf & ((1u << xb) - 1));
+            br.consume(xb);
+            if (dist > pos) return ST_BAD_DISTANCE;
+            if ((uint64_t)pos + len > cap32) return ST_OUT_OVERFLOW;
+            copy_match(out, pos, len, dist);
+            pos += len;
+        }
+    }
+    *final_size = pos;
+    return ST_OK;
+}
+
+}  // namespace dbg

@@ -1,0 +1,93 @@
+// kernels.cuh -- __global__ entry points of the decode path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "inflate_core.h"
+
+namespace dbg {
+
+constexpr int INFLATE_WARPS_PER_CTA = 4;
+constexpr int INFLATE_THREADS = INFLATE_WARPS_PER_CTA * 32;
+constexpr int INFLATE_CTAS_PER_SM = 8;  // 32 resident warps per SM, 64 registers per thread
+
+struct InflateBatch {
+    const uint8_t *in_base;
+    const uint64_t *in_off;
+    const uint64_t *in_size;
+    uint8_t *out_base;
+    const uint64_t *out_off;
+    const uint64_t *out_cap;
+    uint64_t *out_size;
+    uint32_t *status;
+    const uint32_t *pre_status;  // optional: non-zero entries are reported as-is and skipped
+    const uint32_t *order;       // optional scheduling permutation
+    uint32_t *counter;           // work-queue head, zeroed before launch
+    uint32_t n;
+};
+
+// Persistent warps pulling streams from a global queue: one warp decodes one
+// stream start to finish (inflate_core.h), then fetches the next index.
+__global__ void __launch_bounds__(INFLATE_THREADS, INFLATE_CTAS_PER_SM) inflate_batch_kernel(InflateBatch a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
+    const int ln = simt::lane();
+    for (;;) {
+        uint32_t idx = 0;
+        if (ln == 0) idx = atomicAdd(a.counter, 1u);
+        idx = simt::shfl(idx, 0);
+        if (idx >= a.n) break;
+        const uint32_t s = a.order ? a.order[idx] : idx;
+        uint32_t st = a.pre_status ? a.pre_status[s] : 0u;
+        uint64_t fs = 0;
+        if (st == 0)
+            st = inflate_warp(sm, a.in_base + a.in_off[s], a.in_size[s], a.out_base + a.out_off[s], a.out_cap[s], &fs);
+        if (ln == 0) {
+            a.out_size[s] = fs;
+            a.status[s] = st;
+        }
+        simt::syncwarp();
+    }
+}
+
+// gzip member framing, one thread per member: the header walk of
+// decode_gz.c:123-233 (silent build: FNAME skipped, FCOMMENT not) and the
+// payload size rule of decode_gz.c:270 (everything but the 8-byte trailer).
+__global__ void gz_scan_kernel(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_size, uint32_t n,
+                               uint64_t *payload_off, uint64_t *payload_size, uint32_t *pre_status)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *p = in_base + in_off[i];
+    uint64_t size = in_size[i];
+    payload_off[i] = in_off[i];
+    payload_size[i] = 0;
+    uint32_t st = ST_OK;
+    if (size < 10 || p[0] != 31 || p[1] != 139 || p[2] != 8) {
+        st = ST_CONTAINER;
+    } else {
+        uint64_t at = 10, left = size - 10;
+        if ((p[3] >> 3) & 1) {
+            uint64_t k = 0;
+            while (k < left && p[at + k] != 0) k++;
+            if (k + 1 > left) {
+                st = ST_CONTAINER;  // unterminated FNAME: the reference's size underflows and inflate rejects it
+            } else {
+                at += k + 1;
+                left -= k + 1;
+            }
+        }
+        if (st == ST_OK) {
+            if (left < 8) {
+                st = ST_CONTAINER;
+            } else {
+                payload_off[i] = in_off[i] + at;
+                payload_size[i] = left - 8;
+            }
+        }
+    }
+    pre_status[i] = st;
+}
+
+}  // namespace dbg

@@ -1,0 +1,406 @@
+// png_core.h -- device code for the PNG container path (sm_100a), one warp per
+// image. Replaces the data-touching parts of the reference's decode_png()
+// (decode_png.c:683-1567):
+//
+//   png_scan_warp      signature + chunk walk (:730-1355) with the reference's
+//                      own bookkeeping, per-chunk CRC-32 (update_crc :313-333,
+//                      table :29-286) computed by 32 lanes over 8 KiB tiles and
+//                      recombined in GF(2), IHDR / PLTE / zlib-header
+//                      validation (:900-1277) and the IDAT concatenation
+//                      (:1285-1291) into a compact per-image zlib stream.
+//   png_unfilter_warp  scanline reconstruction (:1381-1507, undo_PNG_filter
+//                      :497-541, Paeth :441-487) as a 32-row skewed wavefront:
+//                      lane j owns row r0+j and runs j pixels behind lane j-1,
+//                      taking `b`/`c` from its neighbour by shuffle; tiles are
+//                      staged through shared memory so global loads and stores
+//                      stay row-contiguous. Palette expansion (:1538-1564) and
+//                      RGB->RGBA are fused into the tile write-out.
+//
+// The reference's bookkeeping quirks are kept (Q11: IHDR/PLTE/zlib-header bytes
+// are not subtracted from the remaining-size counter; ancillary test is a
+// signed `char > 'Z'`), with real bounds checks added so nothing is read
+// outside the file. Known, documented divergences: D1 (the reference corrupts
+// the last <=771 stream bytes when a late deflate block starts),
+// D3 (the reference's RGB expansion is broken; this one is correct).
+#pragma once
+#include "inflate_core.h"
+#include "simt.h"
+
+namespace dbg {
+
+enum : uint32_t {
+    ST_PNG_CRC = 13,
+    ST_PNG_FILTER = 14,
+    ST_PNG_SHORT = 15,
+};
+
+struct PngInfo {
+    uint32_t w, h;
+    uint32_t bpp;        // bytes per pixel in the filtered stream: 4 (ct 6), 3 (ct 2), 1 (ct 3)
+    uint32_t plte_off;   // file offset of the PLTE payload (ct 3)
+    uint32_t plte_size;  // entries
+    uint32_t pad[3];
+};
+
+// ------------------------------------------------------------------ CRC-32 ----
+constexpr uint32_t CRC_POLY = 0xedb88320u;  // decode_png.c:289-304
+constexpr uint32_t CRC_SLICE = 256;         // bytes per lane per tile
+constexpr uint32_t CRC_TILE = 32 * CRC_SLICE;
+
+struct CrcTables {
+    uint32_t t[4][256];  // slicing-by-4: t[k][b] = CRC state of byte b followed by k zero bytes
+};
+
+// a(x) * b(x) mod P in the reflected representation (bit 31 = x^0).
+DBG_DEV uint32_t gf2_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+    for (int i = 31; i >= 0; i--) {
+        p ^= (0u - ((a >> i) & 1u)) & b;
+        b = (b >> 1) ^ (CRC_POLY & (0u - (b & 1u)));
+    }
+    return p;
+}
+// x^(8*nbytes) mod P
+DBG_DEV uint32_t gf2_xpow_bytes(uint32_t nbytes)
+{
+    uint32_t sq = 0x00800000u;  // x^8
+    uint32_t r = 0x80000000u;   // x^0
+    while (nbytes) {
+        if (nbytes & 1) r = gf2_mulmod(sq, r);
+        sq = gf2_mulmod(sq, sq);
+        nbytes >>= 1;
+    }
+    return r;
+}
+
+// Fill the slicing tables; `tid`/`nthreads` enumerate the cooperating threads.
+DBG_DEV void crc_tables_init(CrcTables *T, int tid, int nthreads)
+{
+    for (int i = tid; i < 256; i += nthreads) {
+        uint32_t c = (uint32_t)i;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (CRC_POLY & (0u - (c & 1u)));
+        uint32_t c1 = c, c2, c3;
+        // appending one zero byte to state s: (s >> 8) ^ t0[s & 255]; t0 itself
+        // is still being written by other threads, so recompute it locally.
+        uint32_t lo = c1 & 255, z = lo;
+        for (int k = 0; k < 8; k++) z = (z >> 1) ^ (CRC_POLY & (0u - (z & 1u)));
+        c2 = (c1 >> 8) ^ z;
+        lo = c2 & 255, z = lo;
+        for (int k = 0; k < 8; k++) z = (z >> 1) ^ (CRC_POLY & (0u - (z & 1u)));
+        c3 = (c2 >> 8) ^ z;
+        lo = c3 & 255, z = lo;
+        for (int k = 0; k < 8; k++) z = (z >> 1) ^ (CRC_POLY & (0u - (z & 1u)));
+        uint32_t c4 = (c3 >> 8) ^ z;
+        T->t[0][i] = c1;
+        T->t[1][i] = c2;
+        T->t[2][i] = c3;
+        T->t[3][i] = c4;
+    }
+}
+
+DBG_DEV uint32_t crc_slice(const CrcTables *T, uint32_t c, const uint8_t *p, uint32_t len)
+{
+    while (len && ((uintptr_t)p & 3)) {
+        c = T->t[0][(c ^ *p) & 255] ^ (c >> 8);
+        p++;
+        len--;
+    }
+    while (len >= 4) {
+        c ^= *(const uint32_t *)p;
+        c = T->t[3][c & 255] ^ T->t[2][(c >> 8) & 255] ^ T->t[1][(c >> 16) & 255] ^ T->t[0][c >> 24];
+        p += 4;
+        len -= 4;
+    }
+    while (len) {
+        c = T->t[0][(c ^ *p) & 255] ^ (c >> 8);
+        p++;
+        len--;
+    }
+    return c;
+}
+
+// CRC-32 (init and final xor 0xFFFFFFFF, decode_png.c:766,873) of p[0..n), n >= 1,
+// computed by the whole warp. `lane_k` must hold x^(8*CRC_SLICE*(31-lane)).
+// The region is cut into 8 KiB tiles counted from its END, so only the first
+// tile is partial and every lane's "bytes after my slice" count is a constant.
+DBG_DEV uint32_t crc32_warp(const CrcTables *T, uint32_t lane_k, const uint8_t *p, uint64_t n)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    uint32_t head = (uint32_t)(n % CRC_TILE);
+    uint32_t running = 0;
+    bool first = true;
+    uint64_t done = 0;
+    while (done < n) {
+        uint32_t tlen = (first && head) ? head : CRC_TILE;  // real bytes in this tile
+        uint32_t vstart = CRC_TILE - tlen;                  // virtual offset of the first real byte
+        uint32_t s0 = ln * CRC_SLICE, s1 = s0 + CRC_SLICE;  // my virtual slice
+        uint32_t c = 0;
+        if (s1 > vstart) {
+            uint32_t b0 = s0 > vstart ? s0 : vstart;
+            bool has_first = (b0 == vstart);
+            if (has_first) c = first ? 0xffffffffu : running;
+            c = crc_slice(T, c, p + done + (b0 - vstart), s1 - b0);
+            c = gf2_mulmod(lane_k, c);
+        }
+        for (int d = 16; d; d >>= 1) c ^= simt::shfl_xor(c, d);
+        running = c;
+        done += tlen;
+        first = false;
+    }
+    return running ^ 0xffffffffu;
+}
+
+// --------------------------------------------------------------- chunk walk ----
+DBG_DEV uint32_t be32(const uint8_t *p)
+{
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+DBG_DEV bool tag_is(const uint8_t *p, char a, char b, char c, char d)
+{
+    return p[0] == (uint8_t)a && p[1] == (uint8_t)b && p[2] == (uint8_t)c && p[3] == (uint8_t)d;
+}
+
+// Walks one PNG file. Uniform across the warp. On success returns ST_OK, fills
+// `info`, and has copied the concatenated IDAT payload (minus the 2-byte zlib
+// header) to `zdst`; *z_size is the deflate size handed to inflate
+// (payload - 4, decode_png.c:816).
+DBG_DEV uint32_t png_scan_warp(const CrcTables *T, uint32_t lane_k, const uint8_t *file, uint64_t size,
+                               uint64_t rgba_size, uint8_t *zdst, uint64_t zcap, PngInfo *info, uint64_t *z_size)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    *z_size = 0;
+    if (size < 8 || size >= (1ull << 32)) return ST_CONTAINER;
+    if (!(file[1] == 'P' && file[2] == 'N' && file[3] == 'G')) return ST_CONTAINER;  // decode_png.c:730-753
+    uint64_t pos = 8;
+    uint64_t left = size - 8;
+    bool found_idat = false, ran_inflate = false, found_ihdr = false, found_iend = false;
+    uint64_t zlen = 0, zlen_at_run = 0;
+    uint32_t w = 0, h = 0, ct = 0;
+    info->plte_off = 0;
+    info->plte_size = 0;
+    while (left >= 8 && !found_iend) {  // decode_png.c:755-758
+        if (pos + 8 > size) return ST_CONTAINER;
+        const uint8_t *hdr = file + pos;
+        uint64_t length = be32(hdr);
+        const uint8_t *type = hdr + 4;
+        pos += 8;
+        left -= 8;
+        bool is_idat = tag_is(type, 'I', 'D', 'A', 'T');
+        if (!is_idat && found_idat) {  // decode_png.c:775-860: the point where the reference inflates
+            ran_inflate = true;
+            zlen_at_run = zlen;
+        }
+        if (length >= left) return ST_CONTAINER;            // decode_png.c:886
+        if (pos + length + 4 > size) return ST_CONTAINER;   // real bounds (Q11 makes `left` optimistic)
+        uint32_t crc = crc32_warp(T, lane_k, type, 4 + length);  // decode_png.c:862-874
+        if (tag_is(type, 'P', 'L', 'T', 'E')) {             // decode_png.c:900-950
+            if (!found_ihdr) return ST_CONTAINER;
+            if (length % 3 != 0) return ST_CONTAINER;
+            info->plte_off = (uint32_t)pos;
+            info->plte_size = (uint32_t)(length / 3);
+            pos += length;
+        } else if (tag_is(type, 'I', 'H', 'D', 'R')) {      // decode_png.c:951-1138
+            found_ihdr = true;
+            if (pos + 13 > size) return ST_CONTAINER;
+            const uint8_t *b = file + pos;
+            pos += 13;
+            w = be32(b);
+            h = be32(b + 4);
+            uint32_t depth = b[8];
+            ct = b[9];
+            uint32_t filter_method = b[11];
+            if ((uint64_t)w * h * 4 != rgba_size) return ST_CONTAINER;       // :970
+            if ((uint64_t)w * h * 4 + h + 1 >= (1ull << 32)) return ST_TOO_LARGE;
+            if (!(ct == 2 || ct == 3 || ct == 6)) return ST_CONTAINER;       // :987-1038
+            if (w < 1 || h < 1) return ST_CONTAINER;                         // :1044
+            if (depth != 8) return ST_CONTAINER;                             // :1088
+            if (filter_method != 0) return ST_CONTAINER;                     // :1118
+            if (left < 4) return ST_CONTAINER;                               // :1127
+        } else if (is_idat) {                               // decode_png.c:1140-1292
+            if (!found_ihdr) return ST_CONTAINER;
+            uint64_t data_len = length;
+            if (!found_idat) {
+                found_idat = true;
+                if (length < 2) return ST_CONTAINER;
+                uint32_t cmf = file[pos], flg = file[pos + 1];
+                pos += 2;
+                data_len -= 2;
+                if ((cmf & 15) != 8) return ST_CONTAINER;                    // :1186
+                uint32_t chk = (cmf << 8) | flg;
+                if (chk == 0 || chk % 31 != 0) return ST_CONTAINER;          // :1214-1220
+                if ((flg >> 5) & 1) return ST_CONTAINER;                     // FDICT :1262-1265
+            }
+            if (zlen + data_len > zcap) return ST_CONTAINER;
+            const uint8_t *src = file + pos;
+            uint8_t *dst = zdst + zlen;
+            for (uint64_t i = ln; i < data_len; i += 32) dst[i] = src[i];    // :1285-1291
+            zlen += data_len;
+            pos += data_len;
+            left -= data_len;
+        } else if (tag_is(type, 'I', 'E', 'N', 'D')) {      // :1293-1302
+            found_iend = true;
+        } else if ((int8_t)type[0] > (int8_t)'Z') {         // :1303-1308 ancillary (signed char compare)
+            pos += length;
+            left -= length;
+        } else {
+            return ST_CONTAINER;                            // :1309-1319 unknown critical chunk
+        }
+        if (left < 4) return ST_CONTAINER;                  // :1321
+        if (pos + 4 > size) return ST_CONTAINER;
+        uint32_t stored = be32(file + pos);
+        pos += 4;
+        left -= 4;
+        if (stored != crc) return ST_PNG_CRC;               // :1341-1348
+    }
+    if (!ran_inflate) return ST_CONTAINER;                  // :1357
+    if (zlen_at_run < 4 + 5) {
+        // the reference hands (payload - 4) to inflate, which rejects < 5 bytes
+        // (and the subtraction wraps below 4) -- inflate.c:836
+        return zlen_at_run < 4 ? ST_CONTAINER : ST_INPUT_TOO_SMALL;
+    }
+    info->w = w;
+    info->h = h;
+    info->bpp = ct == 6 ? 4 : ct == 2 ? 3 : 1;              // :1401-1414
+    *z_size = zlen_at_run - 4;
+    return ST_OK;
+}
+
+// ---------------------------------------------------------------- un-filter ----
+struct UnfilterSmem {
+    uint32_t tile[32][33];
+};
+
+DBG_DEV uint32_t swar_add4(uint32_t a, uint32_t b)
+{
+    return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
+}
+DBG_DEV uint32_t swar_havg4(uint32_t a, uint32_t b)  // per-byte floor((a+b)/2), decode_png.c:512-515
+{
+    return (a & b) + (((a ^ b) & 0xfefefefeu) >> 1);
+}
+DBG_DEV uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c)  // decode_png.c:441-487, ties a -> b -> c
+{
+    uint32_t r = 0;
+    for (int k = 0; k < 32; k += 8) {
+        int ia = (int)((a >> k) & 255), ib = (int)((b >> k) & 255), ic = (int)((c >> k) & 255);
+        int pa = ib - ic, pb = ia - ic, pc = ia + ib - 2 * ic;
+        pa = pa < 0 ? -pa : pa;
+        pb = pb < 0 ? -pb : pb;
+        pc = pc < 0 ? -pc : pc;
+        int pr = (pa <= pb && pa <= pc) ? ia : (pb <= pc ? ib : ic);
+        r |= (uint32_t)pr << k;
+    }
+    return r;
+}
+
+template <int BPP>
+DBG_DEV uint32_t load_px(const uint8_t *p)
+{
+    if (BPP == 4) {
+        uintptr_t a = (uintptr_t)p;
+        const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+        uint32_t sh = (uint32_t)(a & 3) * 8;
+        uint32_t lo = q[0];
+        if (sh == 0) return lo;
+        return simt::funnel_r(lo, q[1], sh);
+    }
+    uint32_t v = 0;
+    for (int k = 0; k < BPP; k++) v |= (uint32_t)p[k] << (8 * k);
+    return v;
+}
+
+// Reconstructs one image. `scan` holds h rows of (1 filter byte + w*BPP bytes);
+// it is overwritten in place with reconstructed bytes when BPP != 4 (those rows
+// are the "previous scanline" of the next band). RGBA pixels go to `out`.
+template <int BPP>
+DBG_DEV void png_unfilter_warp(UnfilterSmem *sm, uint8_t *scan, uint32_t w, uint32_t h, uint8_t *out,
+                               const uint8_t *plte, uint32_t plte_size)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint64_t stride = (uint64_t)w * BPP + 1;
+    const uint32_t mask = BPP == 4 ? 0xffffffffu : ((1u << (8 * (BPP & 3))) - 1);
+    const uint32_t ntiles = (w + 31 + 31) / 32;
+    uint32_t *out32 = (uint32_t *)out;
+    for (uint32_t r0 = 0; r0 < h; r0 += 32) {
+        const uint32_t r = r0 + ln;
+        const bool row_ok = r < h;
+        const uint32_t ft = row_ok ? scan[(uint64_t)r * stride] : 0;
+        uint32_t prev_out = 0, prev_b = 0;
+        for (uint32_t k = 0; k < ntiles; k++) {
+            // stage the skewed tile: row jj holds pixels [32k - jj, 32k - jj + 32)
+            for (uint32_t jj = 0; jj < 32; jj++) {
+                int64_t x = (int64_t)32 * k - jj + ln;
+                uint32_t v = 0;
+                if (r0 + jj < h && x >= 0 && x < (int64_t)w)
+                    v = load_px<BPP>(scan + (uint64_t)(r0 + jj) * stride + 1 + (uint64_t)x * BPP);
+                sm->tile[jj][ln] = v;
+            }
+            // previous band's last row, pixels [32k, 32k+32), already reconstructed
+            uint32_t up_px = 0;
+            {
+                uint32_t x = 32 * k + ln;
+                if (r0 > 0 && x < w) {
+                    if (BPP == 4) up_px = out32[(uint64_t)(r0 - 1) * w + x];
+                    else up_px = load_px<BPP>(scan + (uint64_t)(r0 - 1) * stride + 1 + (uint64_t)x * BPP);
+                }
+            }
+            simt::syncwarp();
+            for (uint32_t i = 0; i < 32; i++) {
+                int64_t x = (int64_t)32 * k + i - ln;
+                uint32_t b_in = simt::shfl_up(prev_out, 1);
+                uint32_t b0 = simt::shfl(up_px, (int)i);
+                if (ln == 0) b_in = b0;
+                bool px_ok = row_ok && x >= 0 && x < (int64_t)w;
+                uint32_t cur = sm->tile[ln][i];
+                uint32_t a = x > 0 ? prev_out : 0;
+                uint32_t c = x > 0 ? prev_b : 0;
+                uint32_t b = b_in;
+                uint32_t o;
+                switch (ft) {  // undo_PNG_filter decode_png.c:497-541
+                    case 0: o = cur; break;
+                    case 1: o = swar_add4(cur, a); break;
+                    case 2: o = swar_add4(cur, b); break;
+                    case 3: o = swar_add4(cur, swar_havg4(a, b)); break;
+                    case 4: o = swar_add4(cur, paeth4(a, b, c)); break;
+                    default: o = 0; break;  // :528-540 unknown filter -> 0 in the no-assert build
+                }
+                o &= mask;
+                if (px_ok) {
+                    sm->tile[ln][i] = o;
+                    prev_out = o;
+                } else {
+                    prev_out = 0;
+                }
+                prev_b = b_in;
+            }
+            simt::syncwarp();
+            for (uint32_t jj = 0; jj < 32; jj++) {
+                int64_t x = (int64_t)32 * k - jj + ln;
+                if (r0 + jj < h && x >= 0 && x < (int64_t)w) {
+                    uint32_t v = sm->tile[jj][ln];
+                    uint64_t pix = (uint64_t)(r0 + jj) * w + (uint64_t)x;
+                    if (BPP == 4) {
+                        out32[pix] = v;
+                    } else {
+                        uint8_t *q = scan + (uint64_t)(r0 + jj) * stride + 1 + (uint64_t)x * BPP;
+                        for (int kk = 0; kk < BPP; kk++) q[kk] = (uint8_t)(v >> (8 * kk));
+                        if (BPP == 3) {
+                            out32[pix] = v | 0xff000000u;
+                        } else {  // palette, alpha forced to 255 (decode_png.c:1552-1560)
+                            uint32_t rgb = 0;
+                            if (v < plte_size) {
+                                const uint8_t *e = plte + 3 * v;
+                                rgb = (uint32_t)e[0] | ((uint32_t)e[1] << 8) | ((uint32_t)e[2] << 16);
+                            }
+                            out32[pix] = rgb | 0xff000000u;
+                        }
+                    }
+                }
+            }
+            simt::syncwarp();
+        }
+    }
+}
+
+}  // namespace dbg

@@ -1,0 +1,202 @@
+// png_kernels.cuh -- __global__ wrappers and launch helpers for the PNG path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "png_core.h"
+
+namespace dbg {
+
+// Scratch carved out of one device allocation (dbg_ctx::d_png_scratch).
+struct PngLayout {
+    uint64_t *z_off, *z_size;          // per image: compacted deflate stream (offset into idat, size)
+    uint64_t *s_off, *s_cap, *s_size;  // per image: filtered scanline buffer (offset into scan, capacity, inflated size)
+    uint32_t *inf_status, *pre_status;
+    PngInfo *info;
+    uint8_t *idat;  // compacted IDAT payloads
+    uint8_t *scan;  // inflated, still filtered scanlines
+    uint64_t idat_bytes, scan_bytes;
+};
+
+struct PngBatch {
+    const uint8_t *in_base;
+    const uint64_t *in_off;
+    const uint64_t *in_size;
+    const uint64_t *rgba_size;
+    uint32_t n;
+    PngLayout lay;
+};
+
+__host__ __device__ static inline uint64_t png_align(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// est = w*h*4 + h + 1 <= rgba + rgba/4 + 1 (decode_png.c:965-968); 32 bytes of
+// slack per image cover alignment and the word-granular reads of load_px<4>.
+static inline uint64_t png_idat_bytes(uint64_t n, uint64_t total_in) { return png_align(total_in + 32 * n + 64, 256); }
+static inline uint64_t png_scan_bytes(uint64_t n, uint64_t total_rgba)
+{
+    return png_align(total_rgba + total_rgba / 4 + 48 * n + 64, 256);
+}
+static inline uint64_t png_meta_bytes(uint64_t n) { return png_align(n * (5 * 8 + 2 * 4 + sizeof(PngInfo)) + 64, 256); }
+static inline uint64_t png_scratch_bytes(uint64_t n, uint64_t total_in, uint64_t total_rgba)
+{
+    return png_meta_bytes(n) + png_idat_bytes(n, total_in) + png_scan_bytes(n, total_rgba);
+}
+static inline PngLayout png_layout(uint8_t *base, uint64_t n, uint64_t total_in, uint64_t total_rgba)
+{
+    PngLayout l;
+    uint64_t *u = (uint64_t *)base;
+    l.z_off = u;
+    l.z_size = u + n;
+    l.s_off = u + 2 * n;
+    l.s_cap = u + 3 * n;
+    l.s_size = u + 4 * n;
+    l.info = (PngInfo *)(u + 5 * n);
+    l.inf_status = (uint32_t *)(l.info + n);
+    l.pre_status = l.inf_status + n;
+    l.idat = base + png_meta_bytes(n);
+    l.idat_bytes = png_idat_bytes(n, total_in);
+    l.scan = l.idat + l.idat_bytes;
+    l.scan_bytes = png_scan_bytes(n, total_rgba);
+    return l;
+}
+
+// Pass A (one CTA): per-image buffer sizes from IHDR (the same fixed-offset read
+// as decode_png_get_width_height, decode_png.c:662-671) and their exclusive
+// prefix sums. An image whose IHDR disagrees with the caller's rgba size gets
+// no scan buffer; png_scan_warp fails it with the reference's own check.
+constexpr int PLAN_THREADS = 1024;
+__global__ void __launch_bounds__(PLAN_THREADS) png_plan_kernel(PngBatch b)
+{
+    __shared__ uint64_t sh_z[PLAN_THREADS], sh_s[PLAN_THREADS];
+    __shared__ uint64_t carry_z, carry_s;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        carry_z = 0;
+        carry_s = 0;
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < b.n; base += PLAN_THREADS) {
+        uint32_t i = base + t;
+        uint64_t zc = 0, sc = 0, est = 0;
+        if (i < b.n) {
+            uint64_t size = b.in_size[i];
+            zc = png_align(size + 16, 16);
+            if (size >= 33) {
+                const uint8_t *f = b.in_base + b.in_off[i];
+                uint64_t w = be32(f + 16), h = be32(f + 20);
+                uint64_t rgba = w * h * 4;
+                if (rgba == b.rgba_size[i] && rgba + h + 1 < (1ull << 32) && w >= 1 && h >= 1) {
+                    est = rgba + h + 1;  // decode_png.c:965-968
+                    sc = png_align(est + 16, 16);
+                }
+            }
+        }
+        sh_z[t] = zc;
+        sh_s[t] = sc;
+        __syncthreads();
+        for (int d = 1; d < PLAN_THREADS; d <<= 1) {
+            uint64_t vz = t >= d ? sh_z[t - d] : 0, vs = t >= d ? sh_s[t - d] : 0;
+            __syncthreads();
+            sh_z[t] += vz;
+            sh_s[t] += vs;
+            __syncthreads();
+        }
+        if (i < b.n) {
+            b.lay.z_off[i] = carry_z + sh_z[t] - zc;
+            b.lay.s_off[i] = carry_s + sh_s[t] - sc;
+            b.lay.s_cap[i] = est;  // inflate's recipient_size, decode_png.c:803-804
+            b.lay.z_size[i] = 0;
+            b.lay.s_size[i] = 0;
+            b.lay.inf_status[i] = 0;
+        }
+        __syncthreads();
+        if (t == PLAN_THREADS - 1) {
+            carry_z += sh_z[t];
+            carry_s += sh_s[t];
+        }
+        __syncthreads();
+    }
+}
+
+// Pass B: one warp per image -- chunk walk, CRC-32, IDAT gather.
+constexpr int SCAN_WARPS = 8;
+__global__ void __launch_bounds__(SCAN_WARPS * 32) png_scan_kernel(PngBatch b)
+{
+    __shared__ CrcTables tables;
+    crc_tables_init(&tables, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint32_t lane_k = gf2_xpow_bytes(CRC_SLICE * (31 - ln));
+    const uint32_t warps = gridDim.x * SCAN_WARPS;
+    for (uint32_t i = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5); i < b.n; i += warps) {
+        uint64_t zoff = b.lay.z_off[i];
+        uint64_t zcap = png_align(b.in_size[i] + 16, 16);
+        uint64_t zs = 0;
+        PngInfo info;
+        info.w = info.h = info.bpp = 0;
+        uint32_t st = png_scan_warp(&tables, lane_k, b.in_base + b.in_off[i], b.in_size[i], b.rgba_size[i],
+                                    b.lay.idat + zoff, zcap, &info, &zs);
+        if (ln == 0) {
+            b.lay.z_size[i] = zs;
+            b.lay.pre_status[i] = st;
+            b.lay.info[i] = info;
+        }
+        simt::syncwarp();
+    }
+}
+
+// Pass D: one warp per image -- scanline reconstruction into RGBA.
+constexpr int UNF_WARPS = 4;
+__global__ void __launch_bounds__(UNF_WARPS * 32) png_unfilter_kernel(PngBatch b, uint8_t *out_base, const uint64_t *out_off,
+                                                                     uint32_t *status)
+{
+    __shared__ UnfilterSmem sm_all[UNF_WARPS];
+    UnfilterSmem *sm = &sm_all[threadIdx.x >> 5];
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint32_t warps = gridDim.x * UNF_WARPS;
+    for (uint32_t i = blockIdx.x * UNF_WARPS + (threadIdx.x >> 5); i < b.n; i += warps) {
+        uint32_t st = b.lay.pre_status[i];
+        if (st == ST_OK) st = b.lay.inf_status[i];
+        if (st == ST_OK) {
+            PngInfo info = b.lay.info[i];
+            uint8_t *scan = b.lay.scan + b.lay.s_off[i];
+            uint64_t need = (uint64_t)info.h * ((uint64_t)info.w * info.bpp + 1);
+            if (scan[0] > 4) st = ST_PNG_FILTER;                      // decode_png.c:847-858
+            else if (b.lay.s_size[i] < need) st = ST_PNG_SHORT;       // Q13: the reference reads stale memory here
+            else {
+                uint8_t *out = out_base + out_off[i];
+                const uint8_t *file = b.in_base + b.in_off[i];
+                if (info.bpp == 4) png_unfilter_warp<4>(sm, scan, info.w, info.h, out, nullptr, 0);
+                else if (info.bpp == 3) png_unfilter_warp<3>(sm, scan, info.w, info.h, out, nullptr, 0);
+                else png_unfilter_warp<1>(sm, scan, info.w, info.h, out, file + info.plte_off, info.plte_size);
+            }
+        }
+        if (ln == 0) status[i] = st;
+        simt::syncwarp();
+    }
+}
+
+static inline void png_configure_kernels() {}
+
+// returns 0 or a cudaError_t value
+static inline int png_launch_scan(const PngBatch &b, int sm_count, cudaStream_t s)
+{
+    png_plan_kernel<<<1, PLAN_THREADS, 0, s>>>(b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    uint32_t ctas = (b.n + SCAN_WARPS - 1) / SCAN_WARPS;
+    uint32_t cap = (uint32_t)sm_count * 8;
+    png_scan_kernel<<<ctas < cap ? ctas : cap, SCAN_WARPS * 32, 0, s>>>(b);
+    return (int)cudaGetLastError();
+}
+
+static inline int png_launch_unfilter(const PngBatch &b, uint8_t *out_base, const uint64_t *out_off, uint32_t *status,
+                                      int sm_count, cudaStream_t s)
+{
+    uint32_t ctas = (b.n + UNF_WARPS - 1) / UNF_WARPS;
+    uint32_t cap = (uint32_t)sm_count * 16;
+    png_unfilter_kernel<<<ctas < cap ? ctas : cap, UNF_WARPS * 32, 0, s>>>(b, out_base, out_off, status);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dbg

@@ -1,0 +1,148 @@
+/*
+ * debigulator_b200.h -- batched C-ABI of the B200-native inflate / gzip / PNG
+ * decode path (libdebigulator_b200.so).
+ *
+ * The scalar, reference-compatible entry points live beside this file in
+ * inflate.h, decode_png.h and decode_gz.h (same names and signatures as the
+ * reference's src/inflate.h:22-60, src/decode_png.h:43-103 and
+ * src/decode_gz.h:23-38). This header adds what the reference does not have:
+ * batches of independent streams / images decoded by hand-written sm_100a CUDA
+ * kernels. There is NO CPU fallback: without a usable CUDA device dbg_create()
+ * returns NULL and every entry point reports DBG_ERR_NO_DEVICE.
+ *
+ * Conventions shared with the reference:
+ *   - success of an item is an out-param flag, 1 = good, 0 = failed
+ *     (uint32_t for inflate / gzip as in inflate.h:59, uint8_t for PNG as in
+ *     decode_png.h:103); the int return value of a batch call only reports
+ *     infrastructure failures (CUDA errors, bad arguments).
+ *   - inflate items follow inflate()'s contract: raw DEFLATE in, capacity
+ *     out_cap[i] must be >= in_size[i] and in_size[i] >= 5 (inflate.c:826-844),
+ *     out_size[i] is the reference's *final_recipient_size.
+ *   - gzip items follow decode_gz()'s framing (decode_gz.c:131-233, 270): 10
+ *     byte header, optional FNAME, deflate payload = rest - 8; CRC32 / ISIZE are
+ *     not verified (decode_gz.c:281-297).
+ *   - PNG items follow decode_png(): output is RGBA8, w*h*4 bytes, and
+ *     rgba_size[i] must equal w*h*4 (decode_png.c:970). Unlike the reference
+ *     the input buffers are NOT modified.
+ *
+ * Plain C, no CUDA or torch types in any signature: device pointers and
+ * streams cross this boundary as void* / uint8_t*.
+ */
+#ifndef DEBIGULATOR_B200_H
+#define DEBIGULATOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dbg_ctx dbg_ctx;
+
+enum {
+    DBG_OK = 0,
+    DBG_ERR_NO_DEVICE = -1, /* no CUDA device / driver: there is no CPU path */
+    DBG_ERR_CUDA = -2,      /* a CUDA call failed; see dbg_last_error() */
+    DBG_ERR_ARG = -3,       /* NULL / inconsistent arguments */
+    DBG_ERR_NOMEM = -4      /* host or device allocation failed */
+};
+
+/* Per-item status codes written by the *_device entry points (0 = good). The
+ * host entry points collapse them to the reference's 1/0 `good` flag. */
+enum {
+    DBG_ST_OK = 0,
+    DBG_ST_CAP_LT_INPUT = 1,
+    DBG_ST_INPUT_TOO_SMALL = 2,
+    DBG_ST_TOO_LARGE = 3,
+    DBG_ST_STORED_LEN = 4,
+    DBG_ST_BAD_TABLE = 5,
+    DBG_ST_BAD_CODE = 6,
+    DBG_ST_BAD_SYMBOL = 7,
+    DBG_ST_BAD_DISTANCE = 8,
+    DBG_ST_OUT_OVERFLOW = 9,
+    DBG_ST_TRUNCATED = 10,
+    DBG_ST_BAD_REPEAT = 11,
+    DBG_ST_CONTAINER = 12,  /* gzip / PNG framing rejected the item */
+    DBG_ST_CRC = 13,        /* PNG chunk CRC mismatch (decode_png.c:1341-1348) */
+    DBG_ST_FILTER = 14,     /* first filter byte > 4 (decode_png.c:847-858) */
+    DBG_ST_SHORT_STREAM = 15 /* inflated PNG stream shorter than h*(w*bpp+1) */
+};
+
+int dbg_version(void);
+int dbg_device_count(void); /* >= 0, or a DBG_ERR_* code */
+
+/* One context per GPU (one process per GPU in multi-GPU runs). */
+dbg_ctx *dbg_create(int device);
+void dbg_destroy(dbg_ctx *ctx);
+const char *dbg_last_error(const dbg_ctx *ctx); /* ctx may be NULL */
+int dbg_ctx_device(const dbg_ctx *ctx);
+uint64_t dbg_kernel_launches(const dbg_ctx *ctx); /* kernels launched by this ctx so far */
+
+/* ---- host-buffer batches: H2D + kernels + D2H inside the call ------------ */
+
+/* Batched inflate(): replaces n calls of inflate() (inflate.h:51-60). */
+int dbg_inflate_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                      uint8_t *const *out, const uint64_t *out_cap, uint64_t *out_size, uint32_t *good);
+
+/* Batched decode_gz(): replaces n calls of decode_gz() (decode_gz.h:36-38);
+ * the caller supplies the output buffers (e.g. sized from ISIZE). */
+int dbg_decode_gz_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                        uint8_t *const *out, const uint64_t *out_cap, uint64_t *out_size, uint32_t *good);
+
+/* Batched decode_png(): replaces n calls of decode_png() (decode_png.h:96-103). */
+int dbg_decode_png_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                         uint8_t *const *out_rgba, const uint64_t *rgba_size, uint8_t *good);
+
+/* Packed variants: one host input arena and one host output arena (ideally
+ * pinned), items addressed by offsets. kind: 0 = raw deflate, 1 = gzip member,
+ * 2 = PNG (out_cap = w*h*4; out_size[i] is set to out_cap[i] for good images).
+ * A single H2D and a single D2H per wave; this is the end-to-end fast path. */
+int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
+                            const uint64_t *in_size, uint8_t *h_out, const uint64_t *out_off,
+                            const uint64_t *out_cap, uint64_t *out_size, uint32_t *status);
+
+/* ---- device-resident batches: everything already in HBM ------------------ */
+/* All d_* pointers are device pointers on ctx's device. Input item i occupies
+ * d_in[in_off[i] .. in_off[i]+in_size[i]); the bytes from (address & ~15) up to
+ * the next 16-byte boundary after its end must be readable (pad the arena by
+ * 16). Output item i is written at d_out + out_off[i], at most out_cap[i]
+ * bytes. d_order (may be NULL) is a permutation giving the scheduling order
+ * (largest first balances best). Work is enqueued on `stream` (a cudaStream_t,
+ * NULL = the context's own stream) and NOT synchronised. */
+int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                             const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                             const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
+                             const uint32_t *d_order, void *stream);
+
+int dbg_decode_gz_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                               const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                               const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
+                               const uint32_t *d_order, void *stream);
+
+/* PNG: d_out_cap[i] = w*h*4 as the caller computed it from
+ * decode_png_get_width_height(). scratch_bytes (host value) must be at least
+ * dbg_png_scratch_bytes(n, total_in_bytes, total_rgba_bytes); the context
+ * allocates and keeps that scratch (compacted IDAT streams + filtered
+ * scanlines). */
+uint64_t dbg_png_scratch_bytes(uint64_t n, uint64_t total_in_bytes, uint64_t total_rgba_bytes);
+int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                                const uint64_t *d_out_cap, uint32_t *d_status, uint64_t total_in_bytes,
+                                uint64_t total_rgba_bytes, void *stream);
+
+/* Optional timing of the dominant kernel (inflate): after dbg_profile_enable(ctx, 1)
+ * every inflate launch is bracketed by CUDA events on its own stream;
+ * dbg_profile_read() waits for them, returns the summed device time and the
+ * number of launches, and resets the counters. */
+int dbg_profile_enable(dbg_ctx *ctx, int on);
+int dbg_profile_read(dbg_ctx *ctx, double *total_ms, uint64_t *launches);
+
+/* Blocks until everything the context enqueued on its own stream is done. */
+int dbg_synchronize(dbg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DEBIGULATOR_B200_H */

@@ -1,0 +1,223 @@
+// tests/simt_emu/emu.cpp -- TEST SCAFFOLDING, not product code.
+//
+// A single-threaded 32-lane SIMT emulator (ucontext coroutines) that compiles
+// the *device* kernel bodies from debigulator_b200/csrc/*_core.h for the host,
+// so their logic can be checked against the oracle on a CPU-only box before
+// GPU minutes are spent. Warp collectives are rendezvous points: a lane runs
+// until its next collective, then the next lane runs, so a missing
+// __syncwarp() between a store and another lane's load shows up as a wrong
+// answer in at least one of the two lane orders (`reverse`).
+//
+// Nothing here is linked into libdebigulator_b200.so and no product entry
+// point can reach it; the product fails loudly without a GPU.
+#define DBG_SIMT_EMU 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include "../../debigulator_b200/csrc/simt.h"
+
+namespace simt {
+int g_lane = 0;
+uint32_t g_slot[32];
+static ucontext_t g_ctx[32], g_main;
+static bool g_done[32];
+static int g_order[32], g_rank[32];
+
+static int next_alive(int cur)
+{
+    int r = g_rank[cur];
+    for (int k = 1; k <= 32; k++) {
+        int cand = g_order[(r + k) & 31];
+        if (!g_done[cand]) return cand;
+    }
+    return -1;
+}
+void emu_barrier()
+{
+    int cur = g_lane;
+    int nxt = next_alive(cur);
+    if (nxt < 0 || nxt == cur) return;
+    g_lane = nxt;
+    swapcontext(&g_ctx[cur], &g_ctx[nxt]);
+    g_lane = cur;
+}
+static void (*g_body)(void *);
+static void *g_arg;
+static void trampoline()
+{
+    g_body(g_arg);
+    int cur = g_lane;
+    g_done[cur] = true;
+    int nxt = next_alive(cur);
+    if (nxt < 0) {
+        setcontext(&g_main);
+    } else {
+        g_lane = nxt;
+        setcontext(&g_ctx[nxt]);
+    }
+}
+static void run_warp(void (*body)(void *), void *arg, int reverse)
+{
+    static char *stacks = nullptr;
+    const size_t STK = 512 * 1024;
+    if (!stacks) stacks = (char *)malloc(32 * STK);
+    g_body = body;
+    g_arg = arg;
+    for (int i = 0; i < 32; i++) {
+        g_order[i] = reverse ? 31 - i : i;
+        g_rank[g_order[i]] = i;
+        g_done[i] = false;
+    }
+    for (int i = 0; i < 32; i++) {
+        getcontext(&g_ctx[i]);
+        g_ctx[i].uc_stack.ss_sp = stacks + i * STK;
+        g_ctx[i].uc_stack.ss_size = STK;
+        g_ctx[i].uc_link = nullptr;
+        makecontext(&g_ctx[i], trampoline, 0);
+    }
+    g_lane = g_order[0];
+    swapcontext(&g_main, &g_ctx[g_lane]);
+}
+}  // namespace simt
+
+#include "../../debigulator_b200/csrc/inflate_core.h"
+
+struct InflateArgs {
+    dbg::InflateSmem *sm;
+    const uint8_t *in;
+    uint64_t in_size;
+    uint8_t *out;
+    uint64_t cap;
+    uint64_t final_size[32];
+    uint32_t status[32];
+};
+static void inflate_body(void *p)
+{
+    InflateArgs *a = (InflateArgs *)p;
+    int l = simt::lane();
+    a->status[l] = dbg::inflate_warp(a->sm, a->in, a->in_size, a->out, a->cap, &a->final_size[l]);
+}
+
+// Returns the status (or 0x1000 | lane if the lanes disagree, which would be a
+// uniformity bug in the kernel body).
+extern "C" uint32_t emu_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
+                                int misalign, int reverse)
+{
+    // stage the input at the requested misalignment inside a 16-byte aligned,
+    // padded arena whose surroundings are poisoned (0xA5) up to the 16 B rule.
+    size_t arena_sz = (size_t)in_size + 64 + 32;
+    uint8_t *arena = (uint8_t *)aligned_alloc(16, (arena_sz + 15) & ~(size_t)15);
+    memset(arena, 0xA5, (arena_sz + 15) & ~(size_t)15);
+    uint8_t *src = arena + 16 + (misalign & 15);
+    memcpy(src, in, in_size);
+    dbg::InflateSmem *sm = (dbg::InflateSmem *)aligned_alloc(16, sizeof(dbg::InflateSmem));
+    memset(sm, 0xCD, sizeof(*sm));
+    InflateArgs a;
+    a.sm = sm;
+    a.in = src;
+    a.in_size = in_size;
+    a.out = out;
+    a.cap = cap;
+    simt::run_warp(inflate_body, &a, reverse);
+    uint32_t st = a.status[0];
+    for (int i = 1; i < 32; i++)
+        if (a.status[i] != st || a.final_size[i] != a.final_size[0]) st = 0x1000 | i;
+    *final_size = a.final_size[0];
+    free(sm);
+    free(arena);
+    return st;
+}
+
+// ------------------------------------------------------------------- PNG -----
+#include "../../debigulator_b200/csrc/png_core.h"
+
+struct PngArgs {
+    const uint8_t *file;
+    uint64_t size;
+    uint8_t *out;
+    uint64_t rgba_size;
+    dbg::CrcTables *tables;
+    dbg::InflateSmem *ism;
+    dbg::UnfilterSmem *usm;
+    uint8_t *zbuf;
+    uint64_t zcap;
+    uint8_t *scan;
+    uint32_t status[32];
+    uint32_t crc_only;   // when set: just CRC `size` bytes of `file`
+    uint32_t crc[32];
+};
+static void png_body(void *p)
+{
+    PngArgs *a = (PngArgs *)p;
+    int l = simt::lane();
+    dbg::crc_tables_init(a->tables, l, 32);
+    simt::syncwarp();
+    uint32_t lane_k = dbg::gf2_xpow_bytes(dbg::CRC_SLICE * (31 - l));
+    if (a->crc_only) {
+        a->crc[l] = dbg::crc32_warp(a->tables, lane_k, a->file, a->size);
+        return;
+    }
+    dbg::PngInfo info;
+    info.w = info.h = info.bpp = 0;
+    uint64_t zs = 0;
+    uint32_t st = dbg::png_scan_warp(a->tables, lane_k, a->file, a->size, a->rgba_size, a->zbuf, a->zcap, &info, &zs);
+    if (st == dbg::ST_OK) {
+        uint64_t est = (uint64_t)info.w * info.h * 4 + info.h + 1, ssize = 0;
+        st = dbg::inflate_warp(a->ism, a->zbuf, zs, a->scan, est, &ssize);
+        if (st == dbg::ST_OK) {
+            uint64_t need = (uint64_t)info.h * ((uint64_t)info.w * info.bpp + 1);
+            if (a->scan[0] > 4) st = dbg::ST_PNG_FILTER;
+            else if (ssize < need) st = dbg::ST_PNG_SHORT;
+            else if (info.bpp == 4) dbg::png_unfilter_warp<4>(a->usm, a->scan, info.w, info.h, a->out, nullptr, 0);
+            else if (info.bpp == 3) dbg::png_unfilter_warp<3>(a->usm, a->scan, info.w, info.h, a->out, nullptr, 0);
+            else dbg::png_unfilter_warp<1>(a->usm, a->scan, info.w, info.h, a->out, a->file + info.plte_off, info.plte_size);
+        }
+    }
+    a->status[l] = st;
+}
+
+extern "C" uint32_t emu_png_decode(const uint8_t *file, uint64_t size, uint8_t *out, uint64_t rgba_size, int reverse)
+{
+    PngArgs a;
+    memset(&a, 0, sizeof(a));
+    uint8_t *fcopy = (uint8_t *)aligned_alloc(16, (size + 64 + 15) & ~(uint64_t)15);
+    memset(fcopy, 0xA5, (size + 64 + 15) & ~(uint64_t)15);
+    memcpy(fcopy, file, size);
+    a.file = fcopy;
+    a.size = size;
+    a.out = out;
+    a.rgba_size = rgba_size;
+    a.tables = (dbg::CrcTables *)aligned_alloc(16, sizeof(dbg::CrcTables));
+    a.ism = (dbg::InflateSmem *)aligned_alloc(16, sizeof(dbg::InflateSmem));
+    a.usm = (dbg::UnfilterSmem *)aligned_alloc(16, (sizeof(dbg::UnfilterSmem) + 15) & ~(size_t)15);
+    a.zcap = (size + 16 + 15) & ~(uint64_t)15;
+    a.zbuf = (uint8_t *)aligned_alloc(16, a.zcap + 16);
+    memset(a.zbuf, 0x5A, a.zcap + 16);
+    uint64_t scan_cap = (rgba_size + rgba_size / 4 + 64 + 15) & ~(uint64_t)15;
+    a.scan = (uint8_t *)aligned_alloc(16, scan_cap);
+    memset(a.scan, 0x77, scan_cap);
+    simt::run_warp(png_body, &a, reverse);
+    uint32_t st = a.status[0];
+    for (int i = 1; i < 32; i++)
+        if (a.status[i] != st) st = 0x1000 | i;
+    free(fcopy); free(a.tables); free(a.ism); free(a.usm); free(a.zbuf); free(a.scan);
+    return st;
+}
+
+extern "C" uint32_t emu_crc32(const uint8_t *p, uint64_t n, int reverse)
+{
+    PngArgs a;
+    memset(&a, 0, sizeof(a));
+    a.file = p;
+    a.size = n;
+    a.crc_only = 1;
+    a.tables = (dbg::CrcTables *)aligned_alloc(16, sizeof(dbg::CrcTables));
+    simt::run_warp(png_body, &a, reverse);
+    uint32_t c = a.crc[0];
+    for (int i = 1; i < 32; i++)
+        if (a.crc[i] != c) c = 0xDEADBEEF;
+    free(a.tables);
+    return c;
+}

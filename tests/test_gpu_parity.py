@@ -1,0 +1,173 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against
+(a) the committed golden vectors produced by the unmodified reference and
+(b) the reference itself (oracle/_ref) on seeded synthetic inputs.
+Bit-exact on [0, out_size) and equal `good` flags."""
+import base64
+import hashlib
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from debigulator_b200 import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def test_inflate_golden_vectors(ctx, manifest):
+    vecs = manifest["inflate"]
+    res = ctx.inflate_batch([base64.b64decode(v["in_b64"]) for v in vecs], [v["cap"] for v in vecs])
+    bad = []
+    for v, (good, out) in zip(vecs, res):
+        if good != v["good"] or (good and (len(out) != v["out_len"] or sha(out) != v["out_sha256"])):
+            bad.append((v["name"], good, len(out), v["good"], v["out_len"]))
+    assert not bad, bad
+
+
+def test_gz_golden_vectors(ctx, manifest):
+    vecs = manifest["gz"]
+    res = ctx.decode_gz_batch([base64.b64decode(v["in_b64"]) for v in vecs], [v["cap"] for v in vecs])
+    for v, (good, out) in zip(vecs, res):
+        assert good == v["good"], v["name"]
+        if good:
+            assert len(out) == v["out_len"] and sha(out) == v["out_sha256"], v["name"]
+
+
+def test_png_golden_vectors(ctx, manifest):
+    vecs = manifest["png"]
+    res = ctx.decode_png_batch([base64.b64decode(v["in_b64"]) for v in vecs])
+    bad = []
+    for v, (good, w, h, rgba) in zip(vecs, res):
+        if good != v["good"] or (good and ((w, h) != (v["w"], v["h"]) or sha(rgba) != v["out_sha256"])):
+            bad.append((v["name"], good, v["good"]))
+    assert not bad, bad
+
+
+def test_fixture_files(ctx, manifest, golden_dir):
+    """BASELINE config 1 (gimp_test.png) and the other bundled fixtures.
+    phoebus.png (D1) and backgrounddetailed1.png (D3) are the two documented
+    divergences: there this decoder must match the spec decoders instead."""
+    names = sorted(manifest["fixtures"])
+    pngs = [n for n in names if manifest["fixtures"][n]["kind"] == "png"]
+    res = ctx.decode_png_batch([open(os.path.join(golden_dir, n), "rb").read() for n in pngs])
+    for n, (good, w, h, rgba) in zip(pngs, res):
+        f = manifest["fixtures"][n]
+        assert good == 1 and (w, h) == (f["w"], f["h"]), n
+        want = f["ref_sha256"] if f["equals_spec"] else f["spec_sha256"]
+        assert sha(rgba) == want, n
+    gz = open(os.path.join(golden_dir, "gzipsample.gz"), "rb").read()
+    f = manifest["fixtures"]["gzipsample.gz"]
+    (good, out), = ctx.decode_gz_batch([gz], [f["out_len"] + len(gz)])
+    assert good == 1 and len(out) == f["out_len"] and sha(out) == f["ref_sha256"]
+
+
+def test_gimp_readme_golden(ctx, golden_dir):
+    """README.md:41-47: 1024x1024, 4,194,304 RGBA values, average pixel [248,249,251,158]."""
+    (good, w, h, rgba), = ctx.decode_png_batch([open(os.path.join(golden_dir, "gimp_test.png"), "rb").read()])
+    assert good == 1 and (w, h) == (1024, 1024) and len(rgba) == 4194304
+    avg = np.frombuffer(rgba, np.uint8).reshape(-1, 4).astype(np.uint64).sum(axis=0) // (w * h)
+    assert list(avg) == [248, 249, 251, 158]
+
+
+def test_gz_cfg2_members_vs_reference(ctx, ref):
+    """BASELINE config 2 shape: 1 MiB members, classes stored/fixed/dynamic/mixed."""
+    members = [corpus.gz_member_cfg2(i) for i in range(16)]
+    caps = [len(d) + len(g) for g, d in members]
+    res = ctx.decode_gz_batch([g for g, _ in members], caps)
+    for i, ((g, d), (good, out)) in enumerate(zip(members, res)):
+        rgood, rout = ref.decode_gz(g, caps[i])
+        assert good == rgood == 1, i
+        assert out == rout, i
+        assert out == d, i
+
+
+def test_cfg5_sweep_vs_reference(ctx, ref):
+    sizes = [65536, 100000, 300000, 1 << 20, 70000, 2 << 20, 150000, 500000]
+    members = [corpus.gz_member_cfg5(i, sizes[i % 8]) for i in range(16)]
+    caps = [len(d) + len(g) + 64 for g, d in members]
+    res = ctx.decode_gz_batch([g for g, _ in members], caps)
+    for i, ((g, d), (good, out)) in enumerate(zip(members, res)):
+        rgood, rout = ref.decode_gz(g, caps[i])
+        assert good == rgood, i
+        assert out == rout, i
+
+
+def test_png_cfg3_vs_reference(ctx, ref):
+    """BASELINE config 3 shape at reduced size plus two full-size images; all six filter modes,
+    written by the reference's stb_write (one fixed-Huffman block) and by corpus.write_png."""
+    files, want = [], []
+    for i in range(12):
+        img = corpus.gradient_noise_rgba(256, 192, 77 + i)
+        files.append(ref.stb_png(img.tobytes(), 256, 192, 4, i % 6 - 1))
+        want.append(img.tobytes())
+    for i in range(2):
+        img = corpus.gradient_noise_rgba(1024, 1024, 99 + i)
+        files.append(ref.stb_png(img.tobytes(), 1024, 1024, 4, 4 if i else -1))
+        want.append(img.tobytes())
+    for i in range(6):
+        p, rgba = corpus.png_cfg3(i, 300, 200)
+        files.append(p)
+        want.append(rgba)
+    res = ctx.decode_png_batch(files)
+    for i, (f, (good, w, h, rgba)) in enumerate(zip(files, res)):
+        rgood, rw, rh, rrgba = ref.decode_png(f)
+        assert good == rgood, i
+        if good:
+            assert rgba == rrgba, i
+            assert rgba == want[i], i
+
+
+def test_png_variants(ctx, ref):
+    """Multi-IDAT, ancillary chunks before/after IDAT, palette and RGB images."""
+    img = corpus.gradient_noise_rgba(200, 120, 5)
+    files = [
+        corpus.write_png(img, -1, idat_split=1000),
+        corpus.write_png(img, 4, idat_split=7, strategy=zlib.Z_DEFAULT_STRATEGY),
+        corpus.write_png(img, 3, extra_chunks=[(b"tEXt", b"Comment\0hello"), (b"gAMA", b"\0\1\x86\xa0")]),
+    ]
+    res = ctx.decode_png_batch(files)
+    for f, (good, w, h, rgba) in zip(files, res):
+        rgood, _, _, rrgba = ref.decode_png(f)
+        assert good == rgood == 1
+        assert rgba == rrgba == img.tobytes()
+    # palette (colour type 3): reference is correct here
+    r = np.random.default_rng(3)
+    pal = r.integers(0, 256, size=(256, 3), dtype=np.uint8)
+    idx = (np.add.outer(np.arange(90), np.arange(130)) % 200).astype(np.uint8)[..., None]
+    f = corpus.write_png(idx, -1, strategy=zlib.Z_DEFAULT_STRATEGY, palette=pal.tobytes())
+    (good, w, h, rgba), = ctx.decode_png_batch([f])
+    rgood, _, _, rrgba = ref.decode_png(f)
+    assert good == rgood == 1 and rgba == rrgba
+    exp = np.concatenate([pal[idx[..., 0]], np.full((90, 130, 1), 255, np.uint8)], axis=2)
+    assert rgba == exp.tobytes()
+    # RGB (colour type 2): the reference is wrong (D3); this decoder must match the source
+    rgb = corpus.gradient_noise_rgba(77, 50, 9)[..., :3].copy()
+    f = corpus.write_png(rgb, -1, strategy=zlib.Z_DEFAULT_STRATEGY)
+    (good, w, h, rgba), = ctx.decode_png_batch([f])
+    exp = np.concatenate([rgb, np.full((50, 77, 1), 255, np.uint8)], axis=2)
+    assert good == 1 and rgba == exp.tobytes()
+
+
+def test_empty_and_ragged_batches(ctx):
+    assert ctx.inflate_batch([], []) == []
+    d = corpus.word_salad(1000, 1)
+    s = corpus.raw_deflate(d)
+    res = ctx.inflate_batch([s, b"", s[:3], s], [2000, 10, 10, len(s)])  # last: cap == in_size < output
+    assert res[0] == (1, d)
+    assert res[1][0] == 0 and res[2][0] == 0
+    assert res[3][0] == 0  # output overflow fails instead of writing past the buffer
+
+
+def test_large_batch_roundtrip_property(ctx):
+    """Size-independent property at scale: 2048 streams, decode(compress(x)) == x by sha256."""
+    base = [corpus.gz_member_cfg2(i, 1 << 16) for i in range(64)]
+    members = [base[i % 64] for i in range(2048)]
+    res = ctx.decode_gz_batch([g for g, _ in members], [len(d) + len(g) for g, d in members])
+    want = [sha(d) for _, d in base]
+    for i, (good, out) in enumerate(res):
+        assert good == 1 and sha(out) == want[i % 64], i
