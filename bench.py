@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 MEMBER_BYTES = 1 << 20
 N_MEMBERS = 4096
 N_UNIQUE = 64
-PNG_N, PNG_W, PNG_H, PNG_UNIQUE = 1024, 1024, 1024, 12
+PNG_N, PNG_W, PNG_H, PNG_UNIQUE = 2048, 1024, 1024, 12
 METRIC = "inflate_output_GBps"
 UNIT = "GB/s"
 
@@ -219,6 +219,11 @@ def run_ours(args):
 
     ctx = dbg.Context(local)
     n, size = args.members, MEMBER_BYTES
+    if args.png_only:
+        tstream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(tstream)
+        print(json.dumps({"png": bench_png(ctx, dev, torch, args.png_images)}))
+        return
 
     # ---- corpus: N_UNIQUE distinct members (16 per class), cycled to n, every copy at its own address
     uniq = make_unique(_gen_gz, N_UNIQUE)
@@ -312,7 +317,7 @@ def run_ours(args):
     # ---- PNG (BASELINE config 3 shape), secondary metric
     png = None
     if args.png and rank == 0 and world == 1:
-        png = bench_png(ctx, dev, torch)
+        png = bench_png(ctx, dev, torch, args.png_images)
 
     # ---- CPU baseline: the reference C on this box's host cores (rank 0, N=1 only)
     cpu = None
@@ -362,8 +367,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_png(ctx, dev, torch):
-    n = PNG_N
+def bench_png(ctx, dev, torch, n=PNG_N):
     uniq = make_unique(_gen_png, PNG_UNIQUE)
     offs, sizes, in_total = pack([u[0] for u in uniq], n)
     h_in = np.zeros(in_total + 64, dtype=np.uint8)
@@ -415,6 +419,8 @@ def main():
     ap.add_argument("--members", type=int, default=N_MEMBERS)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--png", type=int, default=1)
+    ap.add_argument("--png-only", action="store_true")
+    ap.add_argument("--png-images", type=int, default=PNG_N)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

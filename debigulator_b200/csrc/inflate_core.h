@@ -53,7 +53,7 @@ enum InflateStatus : uint32_t {
 struct InflateSmem {
     uint32_t ring[256];      // 2 x 512 B input ring
     uint32_t lit_lut[512];   // 9-bit primary litlen table
-    uint32_t dist_lut[128];  // 7-bit primary distance table (also: code-length code table)
+    uint32_t dist_lut[256];  // 8-bit primary distance table (its first 128 entries double as the code-length code table)
     uint16_t lit_sorted[288];
     uint16_t lit_first[16], lit_offs[16], lit_cnt[16];
     uint16_t dist_first[16], dist_offs[16], dist_cnt[16];
@@ -66,7 +66,7 @@ struct InflateSmem {
 // and extra-bit count in [12:8], bit7 undecodable symbol.
 enum { E_LIT = 0x10, E_EOB = 0x20, E_BASE = 0x40, E_BAD = 0x80 };
 enum { K_CLEN = 0, K_LITLEN = 1, K_DIST = 2 };
-enum { LIT_ROOT = 9, DIST_ROOT = 7 };
+enum { LIT_ROOT = 9, DIST_ROOT = 8 };
 
 template <int KIND>
 DBG_DEV uint32_t make_entry(uint32_t sym, uint32_t l)
@@ -89,14 +89,18 @@ DBG_DEV uint32_t make_entry(uint32_t sym, uint32_t l)
 }
 
 // ---------------------------------------------------------------- bit reader --
-struct BitReader {
+// A 128-bit window (4 words, identical in every lane) over the shared-memory
+// input ring. `s` is the bit offset of the next unread bit inside w0. The same
+// structure serves the serial header parsing (peek32 / consume, uniform) and
+// the lane-parallel symbol decode, where lane k looks at the stream from bit
+// offset k of the window.
+struct Window {
     const uint8_t *base;  // 16-byte aligned global address at or below the stream start
     uint32_t *ring;
-    uint64_t buf;
-    uint32_t bitcnt;
-    uint32_t wpos;   // ring-coordinate index of the word held in `nw`
-    uint32_t nw;     // prefetched next word
-    uint32_t end16;  // ring-coordinate byte offset past which input reads as zero
+    uint32_t end16;       // ring-coordinate byte offset past which input reads as zero
+    uint32_t w0, w1, w2, w3;
+    uint32_t wb;          // ring-coordinate index of the word held in w0
+    uint32_t s;           // 0..31
 
     DBG_DEVM void load_chunk(uint32_t c)
     {
@@ -106,36 +110,38 @@ struct BitReader {
     }
     DBG_DEVM void maintain()
     {
-        if (wpos & 64) {  // half way through a chunk: the next one has landed
+        if (wb & 64) {  // half way through a chunk: the next one has landed
             simt::cp_async_wait_all();
             simt::syncwarp();
-        } else {          // entered a new chunk: recycle the slot behind us
+        } else {        // entered a new chunk: recycle the slot behind us
             simt::syncwarp();
-            load_chunk((wpos >> 7) + 1);
+            load_chunk((wb >> 7) + 1);
             simt::cp_async_commit();
         }
     }
-    DBG_DEVM uint32_t take()
+    DBG_DEVM void shift()
     {
-        uint32_t w = nw;
-        wpos++;
-        if ((wpos & 63) == 0) maintain();
-        nw = ring[wpos & 255];
-        return w;
+        w0 = w1;
+        w1 = w2;
+        w2 = w3;
+        wb++;
+        if ((wb & 63) == 0) maintain();
+        w3 = ring[(wb + 3) & 255];
     }
-    DBG_DEVM void refill()
+    DBG_DEVM void shift_n(uint32_t n)
     {
-        if (bitcnt < 32) {
-            buf |= (uint64_t)take() << bitcnt;
-            bitcnt += 32;
+        for (; n; n--) shift();
+    }
+    DBG_DEVM uint32_t peek32() const { return simt::funnel_r(w0, w1, s); }
+    DBG_DEVM void consume(uint32_t n)  // n <= 64
+    {
+        s += n;
+        while (s >= 32) {
+            s -= 32;
+            shift();
         }
     }
-    DBG_DEVM void consume(uint32_t n)
-    {
-        buf >>= n;
-        bitcnt -= n;
-    }
-    DBG_DEVM uint64_t abs_bits() const { return ((uint64_t)wpos << 5) - bitcnt; }
+    DBG_DEVM uint64_t abs_bits() const { return ((uint64_t)wb << 5) + s; }
     DBG_DEVM void seek(uint64_t bytepos)
     {
         uint32_t c = (uint32_t)(bytepos >> 9);
@@ -146,11 +152,12 @@ struct BitReader {
         simt::cp_async_commit();
         simt::cp_async_wait_all();
         simt::syncwarp();
-        wpos = (uint32_t)(bytepos >> 2);
-        nw = ring[wpos & 255];
-        uint32_t skip = ((uint32_t)bytepos & 3) << 3;
-        buf = (uint64_t)(take() >> skip);
-        bitcnt = 32 - skip;
+        wb = (uint32_t)(bytepos >> 2);
+        w0 = ring[wb & 255];
+        w1 = ring[(wb + 1) & 255];
+        w2 = ring[(wb + 2) & 255];
+        w3 = ring[(wb + 3) & 255];
+        s = ((uint32_t)bytepos & 3) << 3;
     }
 };
 
@@ -269,14 +276,41 @@ DBG_DEV_NOINLINE uint32_t slow_decode(uint32_t bits, int root, uint32_t maxlen, 
 }
 
 // ------------------------------------------------------------------- copies --
+// One deferred store per lane: the first <=32 bytes of a match are loaded when
+// the match is decoded and written when the NEXT match (or the end of the
+// stream) needs them, so the global-load latency overlaps the decode of the
+// following symbols instead of stalling the warp.
+struct PendingStore {
+    uint32_t val;
+    uint32_t off;
+    bool on;
+};
+
+DBG_DEV void flush_pending(uint8_t *out, PendingStore &pd)
+{
+    if (pd.on) out[pd.off] = (uint8_t)pd.val;
+    pd.on = false;
+}
+
 // LZ77 match (inflate.c:1861-1897). The caller guarantees dist <= pos and
 // pos + len <= cap. All lanes participate.
-DBG_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist)
+DBG_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist, PendingStore &pd)
 {
     const uint32_t ln = (uint32_t)simt::lane();
+    flush_pending(out, pd);
+    simt::syncwarp();  // earlier stores by other lanes are visible from here on
     uint8_t *dst = out + pos;
     const uint8_t *src = dst - dist;
-    simt::syncwarp();  // earlier stores by other lanes are visible from here on
+    if (len <= 32) {
+        // the common case: one chunk, deferred. Overlap (dist < len) replicates the pattern.
+        uint32_t idx = dist >= len ? ln : (dist == 1 ? 0 : ln % dist);
+        if (ln < len) {
+            pd.val = src[idx];
+            pd.off = pos + ln;
+            pd.on = true;
+        }
+        return;
+    }
     if (dist >= len) {
         for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
     } else if (dist >= 32) {
@@ -308,6 +342,37 @@ DBG_DEV uint32_t swizzle_at(uint32_t i)
     return (uint32_t)((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31);
 }
 
+// --------------------------------------------------- lane-parallel symbol decode --
+// Candidate word of lane k = "the symbol that would start at bit k of the
+// window": [6:0] window offset of the next symbol (<= 79), [15:7] match length
+// (0 = literal, 1 = special), [31:16] literal byte | distance-1 | special code.
+enum { CAND_EOB = 0, CAND_ERR = 1, CAND_SLOW = 2 };
+DBG_DEV uint32_t cand_special(uint32_t next, uint32_t code) { return next | (1u << 7) | (code << 16); }
+
+DBG_DEV uint32_t decode_candidate(const InflateSmem *sm, uint32_t lo, uint32_t mid, uint32_t k)
+{
+    uint32_t e = sm->lit_lut[lo & ((1u << LIT_ROOT) - 1)];
+    uint32_t l1 = e & 15;
+    if (e & E_LIT) return (k + l1) | (e & 0xffff0000u);
+    if (e & E_BASE) {
+        uint32_t xb = (e >> 8) & 31;
+        uint32_t len = (e >> 16) + ((lo >> l1) & ((1u << xb) - 1));
+        uint32_t t1 = l1 + xb;
+        uint32_t v = simt::funnel_r(lo, mid, t1);
+        uint32_t e2 = sm->dist_lut[v & ((1u << DIST_ROOT) - 1)];
+        uint32_t l2 = e2 & 15;
+        if (e2 & E_BASE) {
+            uint32_t xb2 = (e2 >> 8) & 31;
+            uint32_t dist = (e2 >> 16) + ((v >> l2) & ((1u << xb2) - 1));
+            return (k + t1 + l2 + xb2) | (len << 7) | ((dist - 1) << 16);
+        }
+        return cand_special(32, l2 == 0 ? CAND_SLOW : CAND_ERR);
+    }
+    if (l1 == 0) return cand_special(32, CAND_SLOW);
+    if (e & E_EOB) return cand_special(k + l1, CAND_EOB);
+    return cand_special(32, CAND_ERR);
+}
+
 // ---------------------------------------------------------------- the stream --
 // Decodes one raw DEFLATE stream of `in_size` bytes at `in` into out[0..cap).
 // Every lane of the warp must call it with identical arguments; the return
@@ -324,44 +389,46 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     const uint32_t ln = (uint32_t)simt::lane();
     const uint32_t mis = (uint32_t)((uintptr_t)in & 15);
     const uint64_t end_byte = (uint64_t)mis + in_size;  // ring coordinates
-    BitReader br;
-    br.base = in - mis;
-    br.ring = sm->ring;
-    br.end16 = (uint32_t)((end_byte + 15) & ~15ull);
-    br.seek(mis);
+    Window w;
+    w.base = in - mis;
+    w.ring = sm->ring;
+    w.end16 = (uint32_t)((end_byte + 15) & ~15ull);
+    w.seek(mis);
 
     // Q2 (inflate.c:1702-1717): the stream ends, successfully, as soon as the
     // byte cursor ceil(P/8) has reached in_size, i.e. P >= 8*in_size - 7.
     const uint64_t q2_limit = 8 * end_byte - 7;
-    const uint32_t q2_w = (uint32_t)(q2_limit >> 5);
+    const uint32_t q2_w = (uint32_t)(q2_limit >> 5), q2_b = (uint32_t)(q2_limit & 31);
 
     uint32_t pos = 0;
     const uint32_t cap32 = (uint32_t)cap;
     uint32_t lit_max = 0, dist_max = 0;
+    PendingStore pd;
+    pd.val = 0;
+    pd.off = 0;
+    pd.on = false;
     bool more = true;
     while (more) {
-        if (br.abs_bits() >= 8 * end_byte) return ST_TRUNCATED;
-        br.refill();
-        uint32_t hdr = (uint32_t)br.buf & 7;
-        br.consume(3);
+        if (w.abs_bits() >= 8 * end_byte) return ST_TRUNCATED;
+        uint32_t hdr = w.peek32() & 7;
+        w.consume(3);
         if (hdr & 1) more = false;
         uint32_t btype = hdr >> 1;
         if (btype == 0) {
-            br.consume(br.bitcnt & 7);
-            br.refill();
-            uint32_t len = (uint32_t)br.buf & 0xffff;
-            uint32_t nlen = ((uint32_t)br.buf >> 16) & 0xffff;
-            br.consume(32);
+            w.consume((0u - w.s) & 7);  // to the next byte boundary (32*wb is byte aligned)
+            uint32_t v = w.peek32();
+            uint32_t len = v & 0xffff, nlen = v >> 16;
+            w.consume(32);
             if (len != (~nlen & 0xffff)) return ST_STORED_LEN;
             if (len) {
-                uint64_t bytepos = br.abs_bits() >> 3;
+                uint64_t bytepos = w.abs_bits() >> 3;
                 if (bytepos + len > end_byte) return ST_TRUNCATED;
                 if ((uint64_t)pos + len > cap32) return ST_OUT_OVERFLOW;
-                const uint8_t *src = br.base + bytepos;
+                const uint8_t *src = w.base + bytepos;
                 uint8_t *dst = out + pos;
                 for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
                 pos += len;
-                br.seek(bytepos + len);
+                w.seek(bytepos + len);
             }
             continue;
         }
@@ -374,32 +441,32 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
                 sm->lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
             simt::syncwarp();
         } else {
-            br.refill();
-            hlit = ((uint32_t)br.buf & 31) + 257;
-            hdist = (((uint32_t)br.buf >> 5) & 31) + 1;
-            uint32_t hclen = (((uint32_t)br.buf >> 10) & 15) + 4;
-            br.consume(14);
+            uint32_t v = w.peek32();
+            hlit = (v & 31) + 257;
+            hdist = ((v >> 5) & 31) + 1;
+            uint32_t hclen = ((v >> 10) & 15) + 4;
+            w.consume(14);
             if (ln < 19) sm->lens[ln] = 0;
             simt::syncwarp();
             for (uint32_t i = 0; i < hclen; i++) {
-                br.refill();
-                if (ln == 0) sm->lens[swizzle_at(i)] = (uint8_t)((uint32_t)br.buf & 7);
-                br.consume(3);
+                if (ln == 0) sm->lens[swizzle_at(i)] = (uint8_t)(w.peek32() & 7);
+                w.consume(3);
             }
             simt::syncwarp();
             uint32_t cl_max;
-            if (!build_table<K_CLEN, uint8_t>(sm->lens, 19, DIST_ROOT, sm->dist_lut, sm->dist_sorted, sm->dist_first,
+            if (!build_table<K_CLEN, uint8_t>(sm->lens, 19, 7, sm->dist_lut, sm->dist_sorted, sm->dist_first,
                                               sm->dist_offs, sm->dist_cnt, &cl_max))
                 return ST_BAD_TABLE;
             const uint32_t n = hlit + hdist;
             uint32_t i = 0, prev = 0;
             while (i < n) {
-                br.refill();
-                uint32_t e = sm->dist_lut[(uint32_t)br.buf & 127];
-                if ((e & 15) == 0) return ST_BAD_CODE;
-                br.consume(e & 15);
+                uint32_t bits = w.peek32();
+                uint32_t e = sm->dist_lut[bits & 127];
+                uint32_t l = e & 15;
+                if (l == 0) return ST_BAD_CODE;
                 uint32_t sym = e >> 16;
                 if (sym < 16) {
+                    w.consume(l);
                     if (ln == 0) sm->lens[i] = (uint8_t)sym;
                     prev = sym;
                     i++;
@@ -408,16 +475,16 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
                 uint32_t rep, val;
                 if (sym == 16) {  // inflate.c:1439-1469
                     if (i == 0) return ST_BAD_REPEAT;
-                    rep = 3 + ((uint32_t)br.buf & 3);
-                    br.consume(2);
+                    rep = 3 + ((bits >> l) & 3);
+                    w.consume(l + 2);
                     val = prev;
                 } else if (sym == 17) {  // :1471-1488
-                    rep = 3 + ((uint32_t)br.buf & 7);
-                    br.consume(3);
+                    rep = 3 + ((bits >> l) & 7);
+                    w.consume(l + 3);
                     val = 0;
                 } else {  // :1490-1509
-                    rep = 11 + ((uint32_t)br.buf & 127);
-                    br.consume(7);
+                    rep = 11 + ((bits >> l) & 127);
+                    w.consume(l + 7);
                     val = 0;
                 }
                 for (uint32_t k = ln; k < rep; k += 32)
@@ -434,48 +501,102 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
                                           sm->dist_first, sm->dist_offs, sm->dist_cnt, &dist_max))
             return ST_BAD_TABLE;
 
-        for (;;) {
-            if (br.wpos >= q2_w && br.abs_bits() >= q2_limit) {
+        // ---- symbols. Each pass looks at one 32-bit window: every lane decodes
+        // the candidate symbol at its own bit offset (LUT lookups, extra bits,
+        // distance) in parallel, then the warp walks the chain of real symbol
+        // starts with one shuffle per symbol.
+        bool eob = false;
+        while (!eob) {
+            // Q2: symbols may only start below bit `lim` of this window
+            const uint32_t lim = w.wb < q2_w ? 32u : (w.wb == q2_w ? q2_b : 0u);
+            if (w.s >= lim) {
                 more = false;
                 break;
             }
-            br.refill();
-            uint32_t e = sm->lit_lut[(uint32_t)br.buf & ((1u << LIT_ROOT) - 1)];
-            if ((e & 15) == 0) {
-                e = slow_decode<K_LITLEN, uint16_t>((uint32_t)br.buf, LIT_ROOT, lit_max, sm->lit_sorted, sm->lit_first,
-                                                    sm->lit_offs, sm->lit_cnt);
-                if (!e) return ST_BAD_CODE;
+            const uint32_t lo = simt::funnel_r(w.w0, w.w1, ln);
+            const uint32_t mid = simt::funnel_r(w.w1, w.w2, ln);
+            const uint32_t cand = decode_candidate(sm, lo, mid, ln);
+            uint32_t p = w.s;
+            bool slow = false;
+            while (p < lim) {
+                const uint32_t info = simt::shfl(cand, (int)p);
+                const uint32_t lf = (info >> 7) & 511;
+                if (lf == 0) {  // literal
+                    if (pos >= cap32) return ST_OUT_OVERFLOW;
+                    if (ln == 0) out[pos] = (uint8_t)(info >> 16);
+                    pos++;
+                    p = info & 127;
+                    continue;
+                }
+                if (lf >= 3) {  // match
+                    const uint32_t dist = (info >> 16) + 1;
+                    if (dist > pos) return ST_BAD_DISTANCE;
+                    if ((uint64_t)pos + lf > cap32) return ST_OUT_OVERFLOW;
+                    copy_match(out, pos, lf, dist, pd);
+                    pos += lf;
+                    p = info & 127;
+                    continue;
+                }
+                const uint32_t code = info >> 16;
+                if (code == CAND_EOB) {
+                    p = info & 127;
+                    eob = true;
+                    break;
+                }
+                if (code == CAND_ERR) return ST_BAD_SYMBOL;
+                slow = true;  // a code longer than the primary LUT index starts here
+                break;
             }
-            br.consume(e & 15);
-            if (e & E_LIT) {
-                if (pos >= cap32) return ST_OUT_OVERFLOW;
-                if (ln == 0) out[pos] = (uint8_t)(e >> 16);
-                pos++;
+            if (slow) {
+                // rare: decode this one symbol serially (uniform), then rebuild the window candidates
+                w.s = p;
+                uint32_t bits = w.peek32();
+                uint32_t e = sm->lit_lut[bits & ((1u << LIT_ROOT) - 1)];
+                if ((e & 15) == 0) {
+                    e = slow_decode<K_LITLEN, uint16_t>(bits, LIT_ROOT, lit_max, sm->lit_sorted, sm->lit_first,
+                                                        sm->lit_offs, sm->lit_cnt);
+                    if (!e) return ST_BAD_CODE;
+                }
+                w.consume(e & 15);
+                if (e & E_LIT) {
+                    if (pos >= cap32) return ST_OUT_OVERFLOW;
+                    if (ln == 0) out[pos] = (uint8_t)(e >> 16);
+                    pos++;
+                    continue;
+                }
+                if (e & E_EOB) break;
+                if (e & E_BAD) return ST_BAD_SYMBOL;
+                bits = w.peek32();
+                uint32_t xb = (e >> 8) & 31;
+                uint32_t len = (e >> 16) + (bits & ((1u << xb) - 1));
+                w.consume(xb);
+                bits = w.peek32();
+                e = sm->dist_lut[bits & ((1u << DIST_ROOT) - 1)];
+                if ((e & 15) == 0) {
+                    e = slow_decode<K_DIST, uint8_t>(bits, DIST_ROOT, dist_max, sm->dist_sorted, sm->dist_first,
+                                                     sm->dist_offs, sm->dist_cnt);
+                    if (!e) return ST_BAD_CODE;
+                }
+                if (e & E_BAD) return ST_BAD_SYMBOL;
+                xb = (e >> 8) & 31;
+                uint32_t l2 = e & 15;
+                uint32_t dist = (e >> 16) + ((bits >> l2) & ((1u << xb) - 1));
+                w.consume(l2 + xb);
+                if (dist > pos) return ST_BAD_DISTANCE;
+                if ((uint64_t)pos + len > cap32) return ST_OUT_OVERFLOW;
+                copy_match(out, pos, len, dist, pd);
+                pos += len;
                 continue;
             }
-            if (e & E_EOB) break;
-            if (e & E_BAD) return ST_BAD_SYMBOL;
-            uint32_t xb = (e >> 8) & 31;
-            uint32_t len = (e >> 16) + ((uint32_t)br.buf & ((1u << xb) - 1));
-            br.consume(xb);
-            br.refill();
-            e = sm->dist_lut[(uint32_t)br.buf & ((1u << DIST_ROOT) - 1)];
-            if ((e & 15) == 0) {
-                e = slow_decode<K_DIST, uint8_t>((uint32_t)br.buf, DIST_ROOT, dist_max, sm->dist_sorted, sm->dist_first,
-                                                 sm->dist_offs, sm->dist_cnt);
-                if (!e) return ST_BAD_CODE;
+            if (!eob && lim < 32) {  // the walk ran into the Q2 limit
+                more = false;
+                break;
             }
-            br.consume(e & 15);
-            if (e & E_BAD) return ST_BAD_SYMBOL;
-            xb = (e >> 8) & 31;
-            uint32_t dist = (e >> 16) + ((uint32_t)br.buf & ((1u << xb) - 1));
-            br.consume(xb);
-            if (dist > pos) return ST_BAD_DISTANCE;
-            if ((uint64_t)pos + len > cap32) return ST_OUT_OVERFLOW;
-            copy_match(out, pos, len, dist);
-            pos += len;
+            w.s = p & 31;
+            w.shift_n(p >> 5);
         }
     }
+    flush_pending(out, pd);
     *final_size = pos;
     return ST_OK;
 }
