@@ -56,6 +56,9 @@ struct dbg_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    static constexpr int MAX_WAVES = 4;
+    cudaStream_t wave_stream[MAX_WAVES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t wave_ready = nullptr;
     uint64_t launches = 0;
     char err[512] = "";
     // optional per-launch timing of the dominant (inflate) kernel, for roofline reports
@@ -138,6 +141,8 @@ extern "C" dbg_ctx *dbg_create(int device)
         delete ctx;
         return nullptr;
     }
+    for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) cudaStreamCreateWithFlags(&ctx->wave_stream[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->wave_ready, cudaEventDisableTiming);
     size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
@@ -153,6 +158,9 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
     Buf *all[] = {&ctx->d_counter, &ctx->d_meta, &ctx->d_png_scratch, &ctx->d_in, &ctx->d_out,
                   &ctx->d_desc,    &ctx->h_in,   &ctx->h_out,         &ctx->h_desc};
     for (Buf *b : all) b->release();
+    for (int i = 0; i < dbg_ctx::MAX_WAVES; i++)
+        if (ctx->wave_stream[i]) cudaStreamDestroy(ctx->wave_stream[i]);
+    if (ctx->wave_ready) cudaEventDestroy(ctx->wave_ready);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -219,6 +227,27 @@ static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter
     return DBG_OK;
 }
 
+// `slot` selects an independent work-queue counter / descriptor scratch so that
+// several waves of one host batch can be in flight on different streams.
+static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                               const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                               const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
+                               const uint32_t *d_order, cudaStream_t s, uint64_t *gz_off, uint64_t *gz_size,
+                               uint32_t *gz_pre)
+{
+    CU(ctx->d_counter.reserve(64 * sizeof(uint32_t)));
+    uint32_t *counter = (uint32_t *)ctx->d_counter.p + 8 * slot;
+    if (gz_off) {
+        dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, gz_off, gz_size, gz_pre);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, d_order, nullptr, (uint32_t)n};
+        return launch_inflate(ctx, a, counter, s);
+    }
+    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, d_order, nullptr, (uint32_t)n};
+    return launch_inflate(ctx, a, counter, s);
+}
+
 extern "C" int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                                         const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
                                         const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
@@ -233,9 +262,8 @@ extern "C" int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t 
     }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    CU(ctx->d_counter.reserve(64));
-    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, d_order, nullptr, (uint32_t)n};
-    return launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
+    return inflate_device_slot(ctx, 0, n, d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, d_order,
+                               s, nullptr, nullptr, nullptr);
 }
 
 extern "C" int dbg_decode_gz_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -252,16 +280,12 @@ extern "C" int dbg_decode_gz_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_
     }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    CU(ctx->d_counter.reserve(64));
     CU(ctx->d_meta.reserve(n * 20 + 64));
     uint64_t *p_off = (uint64_t *)ctx->d_meta.p;
     uint64_t *p_size = p_off + n;
     uint32_t *pre = (uint32_t *)(p_size + n);
-    dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, p_off, p_size, pre);
-    ctx->launches++;
-    CU(cudaGetLastError());
-    dbg::InflateBatch a{d_in, p_off, p_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, pre, d_order, nullptr, (uint32_t)n};
-    return launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
+    return inflate_device_slot(ctx, 0, n, d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, d_order,
+                               s, p_off, p_size, pre);
 }
 
 extern "C" uint64_t dbg_png_scratch_bytes(uint64_t n, uint64_t total_in_bytes, uint64_t total_rgba_bytes)
@@ -282,7 +306,7 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
     }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    CU(ctx->d_counter.reserve(64));
+    CU(ctx->d_counter.reserve(64 * sizeof(uint32_t)));
     CU(ctx->d_png_scratch.reserve(dbg::png_scratch_bytes(n, total_in_bytes, total_rgba_bytes)));
     dbg::PngLayout lay = dbg::png_layout((uint8_t *)ctx->d_png_scratch.p, n, total_in_bytes, total_rgba_bytes);
 
@@ -339,26 +363,65 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
     memcpy(hd + 3 * n, out_cap, n * 8);
     uint32_t *h_status = (uint32_t *)(hd + 5 * n);
     uint32_t *h_order = h_status + n;
-    std::iota(h_order, h_order + n, 0u);
-    std::stable_sort(h_order, h_order + n, [&](uint32_t a, uint32_t b) { return in_size[a] > in_size[b]; });
     uint64_t *dd = (uint64_t *)ctx->d_desc.p;
     uint32_t *d_status = (uint32_t *)(dd + 5 * n);
     uint32_t *d_order = d_status + n;
-    CU(cudaMemcpyAsync(ctx->d_in.p, h_in, in_span, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
-    CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
-    int rc;
-    if (kind == 0)
-        rc = dbg_inflate_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p, dd + 2 * n,
-                                      dd + 3 * n, dd + 4 * n, d_status, d_order, s);
-    else if (kind == 1)
-        rc = dbg_decode_gz_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p,
-                                        dd + 2 * n, dd + 3 * n, dd + 4 * n, d_status, d_order, s);
-    else
-        rc = dbg_decode_png_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p,
-                                         dd + 2 * n, dd + 3 * n, d_status, tot_in, tot_out, s);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h_out, ctx->d_out.p, out_span, cudaMemcpyDeviceToHost, s));
+    // ---- waves: when the items sit in index order in both arenas, the batch is cut into up to
+    // MAX_WAVES contiguous waves, each on its own stream (H2D -> kernels -> D2H), so the copy
+    // engines and the SMs overlap. Otherwise (or for PNG, whose scratch is per batch) one wave.
+    bool mono = kind != 2;
+    for (uint64_t i = 1; i < n && mono; i++)
+        mono = in_off[i] >= in_off[i - 1] + in_size[i - 1] && out_off[i] >= out_off[i - 1] + out_cap[i - 1];
+    int nw = mono ? (int)std::min<uint64_t>(dbg_ctx::MAX_WAVES, std::max<uint64_t>(1, n / 256)) : 1;
+    CU(cudaMemcpyAsync(dd, hd, 4 * n * 8, cudaMemcpyHostToDevice, s));
+    if (kind == 1) CU(ctx->d_meta.reserve(n * 20 + 64));
+    uint64_t *gz_off = kind == 1 ? (uint64_t *)ctx->d_meta.p : nullptr;
+    uint64_t *gz_size = gz_off ? gz_off + n : nullptr;
+    uint32_t *gz_pre = gz_off ? (uint32_t *)(gz_size + n) : nullptr;
+    if (nw == 1) {
+        std::iota(h_order, h_order + n, 0u);
+        std::stable_sort(h_order, h_order + n, [&](uint32_t a, uint32_t b) { return in_size[a] > in_size[b]; });
+        CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(ctx->d_in.p, h_in, in_span, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
+        int rc;
+        if (kind == 2)
+            rc = dbg_decode_png_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p,
+                                             dd + 2 * n, dd + 3 * n, d_status, tot_in, tot_out, s);
+        else
+            rc = inflate_device_slot(ctx, 0, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p, dd + 2 * n,
+                                     dd + 3 * n, dd + 4 * n, d_status, d_order, s, gz_off, gz_size, gz_pre);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h_out, ctx->d_out.p, out_span, cudaMemcpyDeviceToHost, s));
+    } else {
+        // per-wave largest-first order (indices relative to the wave)
+        std::vector<uint64_t> cut(nw + 1);
+        for (int k = 0; k <= nw; k++) cut[k] = n * (uint64_t)k / nw;
+        for (int k = 0; k < nw; k++) {
+            uint32_t *o = h_order + cut[k];
+            uint64_t m = cut[k + 1] - cut[k], b = cut[k];
+            std::iota(o, o + m, 0u);
+            std::stable_sort(o, o + m, [&](uint32_t x, uint32_t y) { return in_size[b + x] > in_size[b + y]; });
+        }
+        CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
+        CU(cudaEventRecord(ctx->wave_ready, s));
+        for (int k = 0; k < nw; k++) {
+            cudaStream_t ws = ctx->wave_stream[k];
+            uint64_t b = cut[k], e = cut[k + 1], m = e - b;
+            uint64_t i0 = in_off[b], i1 = in_off[e - 1] + in_size[e - 1];
+            uint64_t o0 = out_off[b], o1 = out_off[e - 1] + out_cap[e - 1];
+            CU(cudaStreamWaitEvent(ws, ctx->wave_ready, 0));
+            CU(cudaMemcpyAsync((uint8_t *)ctx->d_in.p + i0, h_in + i0, i1 - i0, cudaMemcpyHostToDevice, ws));
+            int rc = inflate_device_slot(ctx, k, m, (const uint8_t *)ctx->d_in.p, dd + b, dd + n + b, (uint8_t *)ctx->d_out.p,
+                                         dd + 2 * n + b, dd + 3 * n + b, dd + 4 * n + b, d_status + b, d_order + b, ws,
+                                         gz_off ? gz_off + b : nullptr, gz_off ? gz_size + b : nullptr,
+                                         gz_off ? gz_pre + b : nullptr);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(h_out + o0, (uint8_t *)ctx->d_out.p + o0, o1 - o0, cudaMemcpyDeviceToHost, ws));
+        }
+        for (int k = 0; k < nw; k++) CU(cudaStreamSynchronize(ctx->wave_stream[k]));
+    }
     CU(cudaMemcpyAsync(hd + 4 * n, dd + 4 * n, n * 8 + n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     memcpy(status, h_status, n * 4);

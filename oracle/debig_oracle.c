@@ -131,6 +131,10 @@ static const uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 
 static const uint8_t DIST_XB[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 static const uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15}; /* :25-26 */
 
+/* symbol statistics of the last oracle_inflate() call (for workload characterisation in DESIGN.md) */
+static uint64_t g_stats[8]; /* literals, matches, match bytes, dist<=32, dist>4096, len<=8, blocks, stored bytes */
+void oracle_stats(uint64_t *out8) { memcpy(out8, g_stats, sizeof g_stats); }
+
 /* ---------------------------------------------------------------- inflate ---- */
 void oracle_inflate(const uint8_t *in, uint64_t in_size, uint64_t in_avail, uint8_t *out, uint64_t cap,
                     uint64_t *out_size, uint32_t *good)
@@ -141,6 +145,7 @@ void oracle_inflate(const uint8_t *in, uint64_t in_size, uint64_t in_avail, uint
     if (cap < in_size) return;  /* inflate.c:826 */
     if (in_size < 5) return;    /* :836 */
     BitIn b = {in, in_size, in_avail < in_size ? in_size : in_avail, 0};
+    memset(g_stats, 0, sizeof g_stats);
     uint64_t pos = 0;
     int more = 1;
     static Huff lit, dist, cl; /* single-threaded checker */
@@ -150,6 +155,7 @@ void oracle_inflate(const uint8_t *in, uint64_t in_size, uint64_t in_avail, uint
         uint32_t bfinal = take(&b, 1);       /* :901-917 */
         uint32_t btype = take(&b, 2);
         if (bfinal) more = 0;
+        g_stats[6]++;
         if (btype == 0) { /* :919-989 */
             b.bitpos = (b.bitpos + 7) & ~7ull;
             uint32_t len = take(&b, 16), nlen = take(&b, 16);
@@ -158,6 +164,7 @@ void oracle_inflate(const uint8_t *in, uint64_t in_size, uint64_t in_avail, uint
             if (at + len > in_size) return;
             if (pos + len > cap) return;
             memcpy(out + pos, in + at, len);
+            g_stats[7] += len;
             pos += len;
             b.bitpos += 8ull * len;
             continue;
@@ -209,6 +216,7 @@ void oracle_inflate(const uint8_t *in, uint64_t in_size, uint64_t in_avail, uint
             if (s < 256) {
                 if (pos >= cap) return;
                 out[pos++] = (uint8_t)s;
+                g_stats[0]++;
                 continue;
             }
             if (s == 256) break;
@@ -226,6 +234,7 @@ void oracle_inflate(const uint8_t *in, uint64_t in_size, uint64_t in_avail, uint
             uint32_t dd = DIST_BASE[ds] + (DIST_XB[ds] ? take(&b, DIST_XB[ds]) : 0);
             if (dd > pos) return; /* :1843 */
             if (pos + len > cap) return;
+            g_stats[1]++; g_stats[2] += len; g_stats[3] += dd <= 32; g_stats[4] += dd > 4096; g_stats[5] += len <= 8;
             for (uint32_t k = 0; k < len; k++) out[pos + k] = out[pos + k - dd]; /* :1861-1897 */
             pos += len;
         }

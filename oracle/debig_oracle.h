@@ -10,6 +10,7 @@ extern "C" {
  * reference's bit reader over-reads, inflate.c:252-256). */
 void oracle_inflate(const uint8_t *in, uint64_t in_size, uint64_t in_avail, uint8_t *out, uint64_t cap,
                     uint64_t *out_size, uint32_t *good);
+void oracle_stats(uint64_t *out8);
 void oracle_decode_gz(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *out_size,
                       uint32_t *good);
 void oracle_png_dims(const uint8_t *in, uint64_t in_size, uint32_t *w, uint32_t *h, uint8_t *good);
