@@ -101,6 +101,8 @@ struct Window {
     uint32_t w0, w1, w2, w3;
     uint32_t wb;          // ring-coordinate index of the word held in w0
     uint32_t s;           // 0..31
+    int32_t wleft;        // words until the one holding the Q2 limit bit (<= 0: the limit is in or before w0)
+    uint32_t q2_w;        // ring-coordinate word index of the Q2 limit bit
 
     DBG_DEVM void load_chunk(uint32_t c)
     {
@@ -125,6 +127,7 @@ struct Window {
         w1 = w2;
         w2 = w3;
         wb++;
+        wleft--;
         if ((wb & 63) == 0) maintain();
         w3 = ring[(wb + 3) & 255];
     }
@@ -158,6 +161,7 @@ struct Window {
         w2 = ring[(wb + 2) & 255];
         w3 = ring[(wb + 3) & 255];
         s = ((uint32_t)bytepos & 3) << 3;
+        wleft = (int32_t)(q2_w - wb);
     }
 };
 
@@ -281,36 +285,26 @@ DBG_DEV_NOINLINE uint32_t slow_decode(uint32_t bits, int root, uint32_t maxlen, 
 // stream) needs them, so the global-load latency overlaps the decode of the
 // following symbols instead of stalling the warp.
 struct PendingStore {
+    uint8_t *ptr;
     uint32_t val;
-    uint32_t off;
     bool on;
 };
 
-DBG_DEV void flush_pending(uint8_t *out, PendingStore &pd)
+DBG_DEV void flush_pending(PendingStore &pd)
 {
-    if (pd.on) out[pd.off] = (uint8_t)pd.val;
+    if (pd.on) *pd.ptr = (uint8_t)pd.val;
     pd.on = false;
 }
 
-// LZ77 match (inflate.c:1861-1897). The caller guarantees dist <= pos and
-// pos + len <= cap. All lanes participate.
-DBG_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist, PendingStore &pd)
+// LZ77 match, general case (inflate.c:1861-1897): longer than one 32-byte
+// chunk and / or overlapping. The caller guarantees dist <= pos and
+// pos + len <= cap and has flushed the pending store. All lanes participate.
+DBG_DEV_NOINLINE void copy_match_slow(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist)
 {
     const uint32_t ln = (uint32_t)simt::lane();
-    flush_pending(out, pd);
-    simt::syncwarp();  // earlier stores by other lanes are visible from here on
     uint8_t *dst = out + pos;
     const uint8_t *src = dst - dist;
-    if (len <= 32) {
-        // the common case: one chunk, deferred. Overlap (dist < len) replicates the pattern.
-        uint32_t idx = dist >= len ? ln : (dist == 1 ? 0 : ln % dist);
-        if (ln < len) {
-            pd.val = src[idx];
-            pd.off = pos + ln;
-            pd.on = true;
-        }
-        return;
-    }
+    simt::syncwarp();  // earlier stores by other lanes are visible from here on
     if (dist >= len) {
         for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
     } else if (dist >= 32) {
@@ -330,6 +324,22 @@ DBG_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist,
             idx += step;
             if (idx >= dist) idx -= dist;
         }
+    }
+}
+
+// Match dispatch: the common short non-overlapping match becomes a deferred
+// load/store pair; everything else goes through copy_match_slow.
+DBG_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist, PendingStore &pd)
+{
+    flush_pending(pd);
+    if ((len <= 32) & (dist >= len)) {
+        simt::syncwarp();  // earlier stores by other lanes are visible from here on
+        const uint8_t *sp = out + (pos - dist + (uint32_t)simt::lane());
+        pd.on = (uint32_t)simt::lane() < len;
+        if (pd.on) pd.val = *sp;
+        pd.ptr = const_cast<uint8_t *>(sp) + dist;
+    } else {
+        copy_match_slow(out, pos, len, dist);
     }
 }
 
@@ -384,7 +394,7 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     *final_size = 0;
     if (cap < in_size) return ST_CAP_LT_INPUT;
     if (in_size < 5) return ST_INPUT_TOO_SMALL;
-    if (in_size >= (1ull << 31) || cap >= (1ull << 32)) return ST_TOO_LARGE;
+    if (in_size >= (1ull << 31) || cap >= (1ull << 32) - 1024) return ST_TOO_LARGE;  // keeps pos + len in 32 bits
 
     const uint32_t ln = (uint32_t)simt::lane();
     const uint32_t mis = (uint32_t)((uintptr_t)in & 15);
@@ -393,19 +403,18 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     w.base = in - mis;
     w.ring = sm->ring;
     w.end16 = (uint32_t)((end_byte + 15) & ~15ull);
-    w.seek(mis);
-
     // Q2 (inflate.c:1702-1717): the stream ends, successfully, as soon as the
     // byte cursor ceil(P/8) has reached in_size, i.e. P >= 8*in_size - 7.
     const uint64_t q2_limit = 8 * end_byte - 7;
-    const uint32_t q2_w = (uint32_t)(q2_limit >> 5), q2_b = (uint32_t)(q2_limit & 31);
+    w.q2_w = (uint32_t)(q2_limit >> 5);
+    w.seek(mis);
 
     uint32_t pos = 0;
     const uint32_t cap32 = (uint32_t)cap;
     uint32_t lit_max = 0, dist_max = 0;
     PendingStore pd;
+    pd.ptr = out;
     pd.val = 0;
-    pd.off = 0;
     pd.on = false;
     bool more = true;
     while (more) {
@@ -505,51 +514,53 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
         // the candidate symbol at its own bit offset (LUT lookups, extra bits,
         // distance) in parallel, then the warp walks the chain of real symbol
         // starts with one shuffle per symbol.
-        bool eob = false;
-        while (!eob) {
+        for (;;) {
             // Q2: symbols may only start below bit `lim` of this window
-            const uint32_t lim = w.wb < q2_w ? 32u : (w.wb == q2_w ? q2_b : 0u);
-            if (w.s >= lim) {
-                more = false;
-                break;
+            uint32_t lim = 32;
+            if (w.wleft <= 0) {
+                lim = w.wleft == 0 ? (uint32_t)(q2_limit & 31) : 0u;
+                if (w.s >= lim) {
+                    more = false;
+                    break;
+                }
             }
             const uint32_t lo = simt::funnel_r(w.w0, w.w1, ln);
             const uint32_t mid = simt::funnel_r(w.w1, w.w2, ln);
             const uint32_t cand = decode_candidate(sm, lo, mid, ln);
-            uint32_t p = w.s;
-            bool slow = false;
-            while (p < lim) {
+            uint32_t p = w.s, cur, err = 0;
+            bool eob = false, slow = false;
+            do {
+                cur = p;
                 const uint32_t info = simt::shfl(cand, (int)p);
                 const uint32_t lf = (info >> 7) & 511;
+                p = info & 127;
                 if (lf == 0) {  // literal
-                    if (pos >= cap32) return ST_OUT_OVERFLOW;
+                    if (pos >= cap32) {
+                        err = ST_OUT_OVERFLOW;
+                        break;
+                    }
                     if (ln == 0) out[pos] = (uint8_t)(info >> 16);
                     pos++;
-                    p = info & 127;
-                    continue;
-                }
-                if (lf >= 3) {  // match
+                } else if (lf >= 3) {  // match
                     const uint32_t dist = (info >> 16) + 1;
-                    if (dist > pos) return ST_BAD_DISTANCE;
-                    if ((uint64_t)pos + lf > cap32) return ST_OUT_OVERFLOW;
+                    if ((dist > pos) | (pos + lf > cap32)) {
+                        err = dist > pos ? ST_BAD_DISTANCE : ST_OUT_OVERFLOW;
+                        break;
+                    }
                     copy_match(out, pos, lf, dist, pd);
                     pos += lf;
-                    p = info & 127;
-                    continue;
-                }
-                const uint32_t code = info >> 16;
-                if (code == CAND_EOB) {
-                    p = info & 127;
-                    eob = true;
+                } else {
+                    const uint32_t code = info >> 16;
+                    if (code == CAND_EOB) eob = true;
+                    else if (code == CAND_ERR) err = ST_BAD_SYMBOL;
+                    else slow = true;  // a code longer than the primary LUT index starts at `cur`
                     break;
                 }
-                if (code == CAND_ERR) return ST_BAD_SYMBOL;
-                slow = true;  // a code longer than the primary LUT index starts here
-                break;
-            }
+            } while (p < lim);
+            if (err) return err;
             if (slow) {
                 // rare: decode this one symbol serially (uniform), then rebuild the window candidates
-                w.s = p;
+                w.s = cur;
                 uint32_t bits = w.peek32();
                 uint32_t e = sm->lit_lut[bits & ((1u << LIT_ROOT) - 1)];
                 if ((e & 15) == 0) {
@@ -583,7 +594,7 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
                 uint32_t dist = (e >> 16) + ((bits >> l2) & ((1u << xb) - 1));
                 w.consume(l2 + xb);
                 if (dist > pos) return ST_BAD_DISTANCE;
-                if ((uint64_t)pos + len > cap32) return ST_OUT_OVERFLOW;
+                if (pos + len > cap32) return ST_OUT_OVERFLOW;
                 copy_match(out, pos, len, dist, pd);
                 pos += len;
                 continue;
@@ -593,10 +604,14 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
                 break;
             }
             w.s = p & 31;
-            w.shift_n(p >> 5);
+            if (p >= 32) {
+                w.shift();
+                if (p >= 64) w.shift();
+            }
+            if (eob) break;
         }
     }
-    flush_pending(out, pd);
+    flush_pending(pd);
     *final_size = pos;
     return ST_OK;
 }
