@@ -6,17 +6,20 @@
 // :565-706 + huffman_to_hashmap :494-557), symbol decode (:421-474) and the
 // LZ77 copy (:1861-1897). It is a new design, not a translation:
 //
-//   * one warp owns one stream. Symbol decode is executed redundantly and
-//     uniformly by all 32 lanes (same registers, broadcast shared-memory LUT
-//     reads), so there is no divergence and no shuffle on the serial path;
-//     the lanes fan out only where there is parallel work: Huffman table
-//     construction (match_any/ballot ranking, warp scans) and LZ77 / stored
-//     copies (one byte per lane, pattern replication for short distances).
+//   * one warp owns one stream; inside a Huffman block the 32 lanes decode 32
+//     consecutive 288-bit zones of the compressed stream in parallel (see
+//     "round decoder" below): the exact symbol chain across zone boundaries is
+//     found by iterating lane exits to a fixed point, output offsets by a warp
+//     scan, and the bytes are produced in a second, lane-parallel pass;
+//   * block headers, code-length codes and stored blocks are read by a uniform
+//     reader (all lanes hold the same window registers); Huffman tables are
+//     built cooperatively (match_any ranking, warp scans, bit-reversed LUT fill);
 //   * compressed bytes are staged global -> shared with 16-byte cp.async
-//     (LDGSTS) into a 2 x 512 B per-warp ring, requested one chunk ahead.
-//   * decode tables are two-level: a 9-bit (litlen) / 7-bit (distance) primary
+//     (LDGSTS) into a 4 KiB per-warp ring, requested at least one 512 B chunk
+//     ahead of the furthest reader;
+//   * decode tables are two-level: a 9-bit (litlen) / 8-bit (distance) primary
 //     LUT with pre-baked base/extra-bit fields, and a canonical first-code
-//     walk for the rare longer codes -- 4.7 KB of shared memory per warp
+//     walk for the rare longer codes -- 4.3 KB of shared memory per warp
 //     instead of the reference's 3 x 792 KB hash maps (inflate.c:112-118).
 //
 // Behavioural parity with the reference's silent, no-assert build is kept where
@@ -50,8 +53,10 @@ enum InflateStatus : uint32_t {
     ST_CONTAINER = 12,      // set by container parsers (PNG / gzip), not by inflate
 };
 
+enum { RING_WORDS = 1024, RING_MASK = RING_WORDS - 1 };
+
 struct InflateSmem {
-    uint32_t ring[256];      // 2 x 512 B input ring
+    uint32_t ring[RING_WORDS];  // 8 x 512 B input ring
     uint32_t lit_lut[512];   // 9-bit primary litlen table
     uint32_t dist_lut[256];  // 8-bit primary distance table (its first 128 entries double as the code-length code table)
     uint16_t lit_sorted[288];
@@ -89,37 +94,47 @@ DBG_DEV uint32_t make_entry(uint32_t sym, uint32_t l)
 }
 
 // ---------------------------------------------------------------- bit reader --
-// A 128-bit window (4 words, identical in every lane) over the shared-memory
-// input ring. `s` is the bit offset of the next unread bit inside w0. The same
-// structure serves the serial header parsing (peek32 / consume, uniform) and
-// the lane-parallel symbol decode, where lane k looks at the stream from bit
-// offset k of the window.
+// Input lives in a 4 KiB shared-memory ring of 512-byte chunks, filled with
+// 16-byte cp.async (LDGSTS) copies and kept at least one chunk ahead of the
+// furthest reader. Ring coordinates count from the 16-byte aligned address at
+// or below the stream start. Two kinds of reader use it:
+//   * the uniform header reader (every lane holds the same 4-word window):
+//     block headers, code-length codes, stored-block framing;
+//   * the lane readers of the round decoder below, where every lane fetches
+//     bits at its own offset.
 struct Window {
     const uint8_t *base;  // 16-byte aligned global address at or below the stream start
     uint32_t *ring;
     uint32_t end16;       // ring-coordinate byte offset past which input reads as zero
+    uint32_t loaded_hi;   // chunks [first, loaded_hi) have been requested
     uint32_t w0, w1, w2, w3;
     uint32_t wb;          // ring-coordinate index of the word held in w0
-    uint32_t s;           // 0..31
-    int32_t wleft;        // words until the one holding the Q2 limit bit (<= 0: the limit is in or before w0)
-    uint32_t q2_w;        // ring-coordinate word index of the Q2 limit bit
+    uint32_t s;           // bit offset of the next unread bit inside w0, 0..31
 
     DBG_DEVM void load_chunk(uint32_t c)
     {
         uint32_t off = (c << 9) + ((uint32_t)simt::lane() << 4);
         bool in = off < end16;
-        simt::cp_async16(&ring[((c & 1) << 7) + ((uint32_t)simt::lane() << 2)], base + (in ? off : 0), in ? 16 : 0);
+        simt::cp_async16(&ring[((c & 7) << 7) + ((uint32_t)simt::lane() << 2)], base + (in ? off : 0), in ? 16 : 0);
+        simt::cp_async_commit();
     }
-    DBG_DEVM void maintain()
+    // Makes ring words [wb, last_word] readable and keeps one more chunk in flight.
+    DBG_DEVM void ensure(uint32_t last_word)
     {
-        if (wb & 64) {  // half way through a chunk: the next one has landed
-            simt::cp_async_wait_all();
+        uint32_t want = (last_word >> 7) + 2;  // needed chunks + one spare
+        if (loaded_hi < want) {
+            simt::syncwarp();  // nobody still reads the slots about to be recycled
+            while (loaded_hi < want) load_chunk(loaded_hi++);
+            simt::cp_async_wait_but_one();  // groups retire in order: only the spare may be pending
             simt::syncwarp();
-        } else {        // entered a new chunk: recycle the slot behind us
-            simt::syncwarp();
-            load_chunk((wb >> 7) + 1);
-            simt::cp_async_commit();
         }
+    }
+    DBG_DEVM void reload()
+    {
+        w0 = ring[wb & RING_MASK];
+        w1 = ring[(wb + 1) & RING_MASK];
+        w2 = ring[(wb + 2) & RING_MASK];
+        w3 = ring[(wb + 3) & RING_MASK];
     }
     DBG_DEVM void shift()
     {
@@ -127,13 +142,8 @@ struct Window {
         w1 = w2;
         w2 = w3;
         wb++;
-        wleft--;
-        if ((wb & 63) == 0) maintain();
-        w3 = ring[(wb + 3) & 255];
-    }
-    DBG_DEVM void shift_n(uint32_t n)
-    {
-        for (; n; n--) shift();
+        if ((wb & 63) == 0) ensure(wb + 64 + 3);
+        w3 = ring[(wb + 3) & RING_MASK];
     }
     DBG_DEVM uint32_t peek32() const { return simt::funnel_r(w0, w1, s); }
     DBG_DEVM void consume(uint32_t n)  // n <= 64
@@ -145,23 +155,20 @@ struct Window {
         }
     }
     DBG_DEVM uint64_t abs_bits() const { return ((uint64_t)wb << 5) + s; }
-    DBG_DEVM void seek(uint64_t bytepos)
+    // Jumps to an arbitrary ring-coordinate bit position at or after the current one.
+    DBG_DEVM void seek_bits(uint64_t bitpos)
     {
-        uint32_t c = (uint32_t)(bytepos >> 9);
-        simt::cp_async_wait_all();  // nothing from an earlier position may land after this
-        simt::syncwarp();
-        load_chunk(c);
-        load_chunk(c + 1);
-        simt::cp_async_commit();
-        simt::cp_async_wait_all();
-        simt::syncwarp();
-        wb = (uint32_t)(bytepos >> 2);
-        w0 = ring[wb & 255];
-        w1 = ring[(wb + 1) & 255];
-        w2 = ring[(wb + 2) & 255];
-        w3 = ring[(wb + 3) & 255];
-        s = ((uint32_t)bytepos & 3) << 3;
-        wleft = (int32_t)(q2_w - wb);
+        uint32_t nwb = (uint32_t)(bitpos >> 5);
+        uint32_t c = nwb >> 7;
+        if (c >= loaded_hi) {  // far jump (stored blocks): restart the ring
+            simt::cp_async_wait_all();
+            simt::syncwarp();
+            loaded_hi = c;
+        }
+        wb = nwb;
+        s = (uint32_t)bitpos & 31;
+        ensure(wb + 64 + 3);
+        reload();
     }
 };
 
@@ -279,68 +286,237 @@ DBG_DEV_NOINLINE uint32_t slow_decode(uint32_t bits, int root, uint32_t maxlen, 
     return 0;
 }
 
-// ------------------------------------------------------------------- copies --
-// One deferred store per lane: the first <=32 bytes of a match are loaded when
-// the match is decoded and written when the NEXT match (or the end of the
-// stream) needs them, so the global-load latency overlaps the decode of the
-// following symbols instead of stalling the warp.
-struct PendingStore {
-    uint8_t *ptr;
-    uint32_t val;
-    bool on;
+// ------------------------------------------------------------ round decoder --
+// Symbols of a Huffman block are decoded 32 sub-chunks at a time ("a round").
+// Lane j owns the SUB_BITS-bit zone Z_j = [start + j*SUB_BITS, start + (j+1)*SUB_BITS)
+// of the compressed stream and decodes, serially and on its own, every symbol
+// that STARTS inside its zone. Where the first symbol of a zone starts is not
+// known up front (only lane 0's is); it is found exactly, not guessed:
+//
+//   iterate:  every lane decodes its zone from its current entry bit and
+//             reports where its last symbol ended ("exit"); lane j+1 takes
+//             lane j's exit as its next entry. Lane 0 is exact from the start,
+//             so lane j is exact after at most j iterations, and as soon as no
+//             entry changes the whole chain is exact. Because Huffman streams
+//             tend to re-synchronise, a lane that started from a wrong entry
+//             usually still produces the right exit, and the chain settles in
+//             a handful of iterations. After ROUND_ITERS iterations the longest
+//             stable prefix of lanes is committed and the rest is retried in
+//             the next round (lane 0 always commits, so progress is guaranteed).
+//   scan:     exclusive prefix sum of the committed lanes' output byte counts.
+//   write:    every committed lane decodes its zone again, now writing literals
+//             and copying matches at its own output offset. A match whose
+//             source lies in the output range of a lower lane of the same round
+//             waits (ballot per phase) until all lower lanes have finished;
+//             lanes only ever wait for lower lanes, so this cannot deadlock.
+//
+// Compared with decoding one symbol per warp instruction this does the serial
+// Huffman work of 32 symbols per instruction; the price is decoding every zone
+// 2 + (iterations) times.
+enum { SUB_WORDS = 9, SUB_BITS = SUB_WORDS * 32, ROUND_WORDS = 32 * SUB_WORDS, ROUND_ITERS = 6 };
+enum { LF_RUN = 0, LF_EOB = 1, LF_LIMIT = 2, LF_ERR = 3, LF_IDLE = 4 };  // how a lane's zone decode ended
+
+struct LaneSym {  // one decoded symbol, lane-local
+    uint32_t bits;   // total compressed bits, 0 = undecodable
+    uint32_t len;    // 0 literal, >= 3 match, 1 = end of block
+    uint32_t val;    // literal byte or distance
 };
 
-DBG_DEV void flush_pending(PendingStore &pd)
+// Decodes the symbol that starts at bit `rel` (relative to ring word `rb`).
+DBG_DEV LaneSym lane_symbol(const InflateSmem *sm, uint32_t rb, uint32_t rel, uint32_t lit_max, uint32_t dist_max)
 {
-    if (pd.on) *pd.ptr = (uint8_t)pd.val;
-    pd.on = false;
+    LaneSym r;
+    r.bits = 0;
+    r.len = 0;
+    r.val = 0;
+    const uint32_t wi = rb + (rel >> 5), sh = rel & 31;
+    const uint32_t a = sm->ring[wi & RING_MASK], b = sm->ring[(wi + 1) & RING_MASK], c = sm->ring[(wi + 2) & RING_MASK];
+    const uint32_t lo = simt::funnel_r(a, b, sh), hi = simt::funnel_r(b, c, sh);
+    uint32_t e = sm->lit_lut[lo & ((1u << LIT_ROOT) - 1)];
+    if ((e & 15) == 0) {
+        e = slow_decode<K_LITLEN, uint16_t>(lo, LIT_ROOT, lit_max, sm->lit_sorted, sm->lit_first, sm->lit_offs, sm->lit_cnt);
+        if (!e) return r;
+    }
+    const uint32_t l1 = e & 15;
+    if (e & E_LIT) {
+        r.bits = l1;
+        r.val = e >> 16;
+        return r;
+    }
+    if (e & E_BASE) {
+        const uint32_t xb = (e >> 8) & 31;
+        r.len = (e >> 16) + ((lo >> l1) & ((1u << xb) - 1));
+        const uint32_t t1 = l1 + xb;
+        const uint32_t v = simt::funnel_r(lo, hi, t1);
+        uint32_t e2 = sm->dist_lut[v & ((1u << DIST_ROOT) - 1)];
+        if ((e2 & 15) == 0) {
+            e2 = slow_decode<K_DIST, uint8_t>(v, DIST_ROOT, dist_max, sm->dist_sorted, sm->dist_first, sm->dist_offs, sm->dist_cnt);
+            if (!e2) return r;
+        }
+        if (!(e2 & E_BASE)) return r;  // distance symbols 30 / 31
+        const uint32_t l2 = e2 & 15, xb2 = (e2 >> 8) & 31;
+        r.val = (e2 >> 16) + ((v >> l2) & ((1u << xb2) - 1));
+        r.bits = t1 + l2 + xb2;
+        return r;
+    }
+    if (e & E_EOB) {
+        r.bits = l1;
+        r.len = 1;
+    }
+    return r;  // E_BAD: bits stays 0
 }
 
-// LZ77 match, general case (inflate.c:1861-1897): longer than one 32-byte
-// chunk and / or overlapping. The caller guarantees dist <= pos and
-// pos + len <= cap and has flushed the pending store. All lanes participate.
-DBG_DEV_NOINLINE void copy_match_slow(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist)
+// Result of one round, uniform across the warp.
+struct RoundResult {
+    uint32_t status;    // ST_OK or the failure
+    uint32_t end_rel;   // bit (relative to the round's base word) where decoding resumes
+    uint32_t out_bytes; // bytes appended to the output
+    bool eob;           // the block ended inside this round
+    bool limit;         // rule Q2 ended the stream inside this round
+};
+
+DBG_DEV RoundResult decode_round(InflateSmem *sm, uint32_t rb, uint32_t start, uint32_t limit, uint8_t *out, uint32_t pos,
+                                 uint32_t cap, uint32_t lit_max, uint32_t dist_max)
 {
     const uint32_t ln = (uint32_t)simt::lane();
-    uint8_t *dst = out + pos;
-    const uint8_t *src = dst - dist;
-    simt::syncwarp();  // earlier stores by other lanes are visible from here on
-    if (dist >= len) {
-        for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
-    } else if (dist >= 32) {
-        for (uint32_t b = 0; b < len; b += 32) {
-            uint32_t i = b + ln;
-            if (i < len) dst[i] = src[i];
-            simt::syncwarp();
-        }
-    } else {
-        // overlapping short distance: replicate the dist-byte pattern from registers
-        uint32_t idx = ln % dist;
-        uint32_t v = src[idx];
-        uint32_t step = 32 % dist;
-        for (uint32_t b = 0; b < len; b += 32) {
-            uint32_t x = simt::shfl(v, (int)idx);
-            if (b + ln < len) dst[b + ln] = (uint8_t)x;
-            idx += step;
-            if (idx >= dist) idx -= dist;
-        }
-    }
-}
+    const uint32_t zone_end = start + (ln + 1) * SUB_BITS;
+    RoundResult rr;
+    rr.status = ST_OK;
+    rr.eob = false;
+    rr.limit = false;
 
-// Match dispatch: the common short non-overlapping match becomes a deferred
-// load/store pair; everything else goes through copy_match_slow.
-DBG_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist, PendingStore &pd)
-{
-    flush_pending(pd);
-    if ((len <= 32) & (dist >= len)) {
-        simt::syncwarp();  // earlier stores by other lanes are visible from here on
-        const uint8_t *sp = out + (pos - dist + (uint32_t)simt::lane());
-        pd.on = (uint32_t)simt::lane() < len;
-        if (pd.on) pd.val = *sp;
-        pd.ptr = const_cast<uint8_t *>(sp) + dist;
-    } else {
-        copy_match_slow(out, pos, len, dist);
+    // ---- iterate to the exact chain of zone entries
+    uint32_t entry = start + ln * SUB_BITS;  // exact for lane 0, a first guess elsewhere
+    uint32_t exitp = 0, outlen = 0, flag = LF_RUN, changed_mask = 0;
+    bool active = true;  // false once a lower lane ended the block / stream
+    for (int it = 0; it < ROUND_ITERS; it++) {
+        uint32_t rel = entry;
+        outlen = 0;
+        flag = active ? LF_RUN : LF_IDLE;
+        while (flag == LF_RUN && rel < zone_end) {
+            if (rel >= limit) {
+                flag = LF_LIMIT;
+                break;
+            }
+            LaneSym y = lane_symbol(sm, rb, rel, lit_max, dist_max);
+            if (y.bits == 0) {
+                flag = LF_ERR;
+                break;
+            }
+            rel += y.bits;
+            if (y.len == 1) {
+                flag = LF_EOB;
+                break;
+            }
+            outlen += y.len ? y.len : 1;
+        }
+        exitp = rel;
+        // hand the exit to the next lane
+        uint32_t pexit = simt::shfl_up(exitp, 1), pflag = simt::shfl_up(flag, 1);
+        uint32_t nentry = entry;
+        bool nactive = active;
+        if (ln > 0) {
+            nactive = pflag == LF_RUN;
+            // a lower lane that stopped on an undecodable code was (if the chain is not yet exact)
+            // probably just misaligned: keep guessing from the zone start
+            nentry = pflag == LF_RUN ? pexit : (pflag == LF_ERR ? start + ln * SUB_BITS : entry);
+            if (pflag == LF_ERR) nactive = true;
+        }
+        changed_mask = simt::ballot(nentry != entry || nactive != active);
+        if (changed_mask == 0) break;
+        entry = nentry;
+        active = nactive;
     }
+    // lanes below the first changed one decoded from their final entry: they are exact
+    uint32_t ncommit = changed_mask ? (uint32_t)simt::ffs(changed_mask) - 1 : 32;
+    // the chain also ends at the first lane that did not run to its zone end
+    uint32_t stop_mask = simt::ballot(flag != LF_RUN) & (ncommit >= 32 ? 0xffffffffu : ((1u << ncommit) - 1));
+    uint32_t last = ncommit - 1;
+    if (stop_mask) last = (uint32_t)simt::ffs(stop_mask) - 1;
+    const uint32_t lflag = simt::shfl(flag, (int)last);
+    if (lflag == LF_ERR) {
+        rr.status = ST_BAD_CODE;
+        return rr;
+    }
+    const bool mine = ln <= last;  // this lane's symbols are committed
+
+    // ---- scan: output offsets
+    uint32_t incl = mine ? outlen : 0;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = simt::shfl_up(incl, d);
+        if ((int)ln >= d) incl += t;
+    }
+    const uint32_t total = simt::shfl(incl, 31);
+    if (total > cap - pos) {
+        rr.status = ST_OUT_OVERFLOW;
+        return rr;
+    }
+    const uint32_t my_out = pos + incl - (mine ? outlen : 0);
+
+    // ---- write: decode again, producing bytes
+    {
+        simt::syncwarp();  // everything written before this round is visible to every lane
+        uint32_t rel = entry, wp = my_out;
+        bool fin = !mine;
+        uint32_t err = 0;
+        const uint32_t below = (1u << ln) - 1;
+        uint32_t done = simt::ballot(fin);
+        for (;;) {
+            const bool lower_done = (~done & below) == 0;
+            while (!fin) {
+                if (rel >= zone_end || rel >= limit) {
+                    fin = true;
+                    break;
+                }
+                LaneSym y = lane_symbol(sm, rb, rel, lit_max, dist_max);
+                if (y.len == 1) {
+                    fin = true;
+                    break;
+                }
+                if (y.len == 0) {
+                    out[wp++] = (uint8_t)y.val;
+                    rel += y.bits;
+                    continue;
+                }
+                const uint32_t dist = y.val, len = y.len;
+                if (dist > wp) {  // inflate.c:1843
+                    err = ST_BAD_DISTANCE;
+                    fin = true;
+                    break;
+                }
+                const uint32_t src = wp - dist;
+                // safe: the source was written before this round, or by this lane itself
+                if (!(src + len <= pos || src >= my_out || lower_done)) break;  // wait for the lower lanes
+                if (dist >= len && len <= 8) {
+                    uint32_t t[8];
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; k++)
+                        if (k < len) t[k] = out[src + k];
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; k++)
+                        if (k < len) out[wp + k] = (uint8_t)t[k];
+                } else {
+                    for (uint32_t k = 0; k < len; k++) out[wp + k] = out[src + k];
+                }
+                wp += len;
+                rel += y.bits;
+            }
+            simt::syncwarp();  // bytes written by finished lanes become visible to the waiting ones
+            const uint32_t ndone = simt::ballot(fin);
+            if (ndone == 0xffffffffu) break;
+            done = ndone;
+        }
+        const uint32_t emask = simt::ballot(err != 0);
+        if (emask) {
+            rr.status = simt::shfl(err, simt::ffs(emask) - 1);
+            return rr;
+        }
+    }
+    rr.end_rel = simt::shfl(exitp, (int)last);
+    rr.out_bytes = total;
+    rr.eob = lflag == LF_EOB;
+    rr.limit = lflag == LF_LIMIT;
+    return rr;
 }
 
 DBG_DEV uint32_t swizzle_at(uint32_t i)
@@ -350,37 +526,6 @@ DBG_DEV uint32_t swizzle_at(uint32_t i)
                         (9ull << 30) | (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
     const uint64_t hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
     return (uint32_t)((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12))) & 31);
-}
-
-// --------------------------------------------------- lane-parallel symbol decode --
-// Candidate word of lane k = "the symbol that would start at bit k of the
-// window": [6:0] window offset of the next symbol (<= 79), [15:7] match length
-// (0 = literal, 1 = special), [31:16] literal byte | distance-1 | special code.
-enum { CAND_EOB = 0, CAND_ERR = 1, CAND_SLOW = 2 };
-DBG_DEV uint32_t cand_special(uint32_t next, uint32_t code) { return next | (1u << 7) | (code << 16); }
-
-DBG_DEV uint32_t decode_candidate(const InflateSmem *sm, uint32_t lo, uint32_t mid, uint32_t k)
-{
-    uint32_t e = sm->lit_lut[lo & ((1u << LIT_ROOT) - 1)];
-    uint32_t l1 = e & 15;
-    if (e & E_LIT) return (k + l1) | (e & 0xffff0000u);
-    if (e & E_BASE) {
-        uint32_t xb = (e >> 8) & 31;
-        uint32_t len = (e >> 16) + ((lo >> l1) & ((1u << xb) - 1));
-        uint32_t t1 = l1 + xb;
-        uint32_t v = simt::funnel_r(lo, mid, t1);
-        uint32_t e2 = sm->dist_lut[v & ((1u << DIST_ROOT) - 1)];
-        uint32_t l2 = e2 & 15;
-        if (e2 & E_BASE) {
-            uint32_t xb2 = (e2 >> 8) & 31;
-            uint32_t dist = (e2 >> 16) + ((v >> l2) & ((1u << xb2) - 1));
-            return (k + t1 + l2 + xb2) | (len << 7) | ((dist - 1) << 16);
-        }
-        return cand_special(32, l2 == 0 ? CAND_SLOW : CAND_ERR);
-    }
-    if (l1 == 0) return cand_special(32, CAND_SLOW);
-    if (e & E_EOB) return cand_special(k + l1, CAND_EOB);
-    return cand_special(32, CAND_ERR);
 }
 
 // ---------------------------------------------------------------- the stream --
@@ -394,7 +539,7 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     *final_size = 0;
     if (cap < in_size) return ST_CAP_LT_INPUT;
     if (in_size < 5) return ST_INPUT_TOO_SMALL;
-    if (in_size >= (1ull << 31) || cap >= (1ull << 32) - 1024) return ST_TOO_LARGE;  // keeps pos + len in 32 bits
+    if (in_size >= (1ull << 31) || cap >= (1ull << 32) - 1024) return ST_TOO_LARGE;
 
     const uint32_t ln = (uint32_t)simt::lane();
     const uint32_t mis = (uint32_t)((uintptr_t)in & 15);
@@ -403,19 +548,20 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     w.base = in - mis;
     w.ring = sm->ring;
     w.end16 = (uint32_t)((end_byte + 15) & ~15ull);
+    simt::cp_async_wait_all();
+    simt::syncwarp();
+    w.loaded_hi = 0;
+    w.wb = 0;
+    w.s = 0;
+    w.seek_bits((uint64_t)mis * 8);
+
     // Q2 (inflate.c:1702-1717): the stream ends, successfully, as soon as the
     // byte cursor ceil(P/8) has reached in_size, i.e. P >= 8*in_size - 7.
     const uint64_t q2_limit = 8 * end_byte - 7;
-    w.q2_w = (uint32_t)(q2_limit >> 5);
-    w.seek(mis);
 
     uint32_t pos = 0;
     const uint32_t cap32 = (uint32_t)cap;
     uint32_t lit_max = 0, dist_max = 0;
-    PendingStore pd;
-    pd.ptr = out;
-    pd.val = 0;
-    pd.on = false;
     bool more = true;
     while (more) {
         if (w.abs_bits() >= 8 * end_byte) return ST_TRUNCATED;
@@ -436,8 +582,9 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
                 const uint8_t *src = w.base + bytepos;
                 uint8_t *dst = out + pos;
                 for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
+                simt::syncwarp();
                 pos += len;
-                w.seek(bytepos + len);
+                w.seek_bits((bytepos + len) * 8);
             }
             continue;
         }
@@ -510,108 +657,23 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
                                           sm->dist_first, sm->dist_offs, sm->dist_cnt, &dist_max))
             return ST_BAD_TABLE;
 
-        // ---- symbols. Each pass looks at one 32-bit window: every lane decodes
-        // the candidate symbol at its own bit offset (LUT lookups, extra bits,
-        // distance) in parallel, then the warp walks the chain of real symbol
-        // starts with one shuffle per symbol.
+        // ---- symbols, one round of 32 zones at a time
         for (;;) {
-            // Q2: symbols may only start below bit `lim` of this window
-            uint32_t lim = 32;
-            if (w.wleft <= 0) {
-                lim = w.wleft == 0 ? (uint32_t)(q2_limit & 31) : 0u;
-                if (w.s >= lim) {
-                    more = false;
-                    break;
-                }
-            }
-            const uint32_t lo = simt::funnel_r(w.w0, w.w1, ln);
-            const uint32_t mid = simt::funnel_r(w.w1, w.w2, ln);
-            const uint32_t cand = decode_candidate(sm, lo, mid, ln);
-            uint32_t p = w.s, cur, err = 0;
-            bool eob = false, slow = false;
-            do {
-                cur = p;
-                const uint32_t info = simt::shfl(cand, (int)p);
-                const uint32_t lf = (info >> 7) & 511;
-                p = info & 127;
-                if (lf == 0) {  // literal
-                    if (pos >= cap32) {
-                        err = ST_OUT_OVERFLOW;
-                        break;
-                    }
-                    if (ln == 0) out[pos] = (uint8_t)(info >> 16);
-                    pos++;
-                } else if (lf >= 3) {  // match
-                    const uint32_t dist = (info >> 16) + 1;
-                    if ((dist > pos) | (pos + lf > cap32)) {
-                        err = dist > pos ? ST_BAD_DISTANCE : ST_OUT_OVERFLOW;
-                        break;
-                    }
-                    copy_match(out, pos, lf, dist, pd);
-                    pos += lf;
-                } else {
-                    const uint32_t code = info >> 16;
-                    if (code == CAND_EOB) eob = true;
-                    else if (code == CAND_ERR) err = ST_BAD_SYMBOL;
-                    else slow = true;  // a code longer than the primary LUT index starts at `cur`
-                    break;
-                }
-            } while (p < lim);
-            if (err) return err;
-            if (slow) {
-                // rare: decode this one symbol serially (uniform), then rebuild the window candidates
-                w.s = cur;
-                uint32_t bits = w.peek32();
-                uint32_t e = sm->lit_lut[bits & ((1u << LIT_ROOT) - 1)];
-                if ((e & 15) == 0) {
-                    e = slow_decode<K_LITLEN, uint16_t>(bits, LIT_ROOT, lit_max, sm->lit_sorted, sm->lit_first,
-                                                        sm->lit_offs, sm->lit_cnt);
-                    if (!e) return ST_BAD_CODE;
-                }
-                w.consume(e & 15);
-                if (e & E_LIT) {
-                    if (pos >= cap32) return ST_OUT_OVERFLOW;
-                    if (ln == 0) out[pos] = (uint8_t)(e >> 16);
-                    pos++;
-                    continue;
-                }
-                if (e & E_EOB) break;
-                if (e & E_BAD) return ST_BAD_SYMBOL;
-                bits = w.peek32();
-                uint32_t xb = (e >> 8) & 31;
-                uint32_t len = (e >> 16) + (bits & ((1u << xb) - 1));
-                w.consume(xb);
-                bits = w.peek32();
-                e = sm->dist_lut[bits & ((1u << DIST_ROOT) - 1)];
-                if ((e & 15) == 0) {
-                    e = slow_decode<K_DIST, uint8_t>(bits, DIST_ROOT, dist_max, sm->dist_sorted, sm->dist_first,
-                                                     sm->dist_offs, sm->dist_cnt);
-                    if (!e) return ST_BAD_CODE;
-                }
-                if (e & E_BAD) return ST_BAD_SYMBOL;
-                xb = (e >> 8) & 31;
-                uint32_t l2 = e & 15;
-                uint32_t dist = (e >> 16) + ((bits >> l2) & ((1u << xb) - 1));
-                w.consume(l2 + xb);
-                if (dist > pos) return ST_BAD_DISTANCE;
-                if (pos + len > cap32) return ST_OUT_OVERFLOW;
-                copy_match(out, pos, len, dist, pd);
-                pos += len;
-                continue;
-            }
-            if (!eob && lim < 32) {  // the walk ran into the Q2 limit
+            w.ensure(w.wb + ROUND_WORDS + 4);
+            const uint64_t base_bits = (uint64_t)w.wb << 5;
+            const uint32_t limit = q2_limit - base_bits < (1u << 30) ? (uint32_t)(q2_limit - base_bits)
+                                                                      : (q2_limit < base_bits ? 0u : (1u << 30));
+            RoundResult rr = decode_round(sm, w.wb, w.s, limit, out, pos, cap32, lit_max, dist_max);
+            if (rr.status != ST_OK) return rr.status;
+            pos += rr.out_bytes;
+            w.seek_bits(base_bits + rr.end_rel);
+            if (rr.limit) {
                 more = false;
                 break;
             }
-            w.s = p & 31;
-            if (p >= 32) {
-                w.shift();
-                if (p >= 64) w.shift();
-            }
-            if (eob) break;
+            if (rr.eob) break;
         }
     }
-    flush_pending(pd);
     *final_size = pos;
     return ST_OK;
 }
