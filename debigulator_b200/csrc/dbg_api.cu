@@ -145,7 +145,7 @@ extern "C" dbg_ctx *dbg_create(int device)
     cudaEventCreateWithFlags(&ctx->wave_ready, cudaEventDisableTiming);
     size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 90);
+    cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
     dbg::png_configure_kernels();
     return ctx;
 }

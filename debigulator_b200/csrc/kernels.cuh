@@ -9,7 +9,7 @@ namespace dbg {
 
 constexpr int INFLATE_WARPS_PER_CTA = 4;
 constexpr int INFLATE_THREADS = INFLATE_WARPS_PER_CTA * 32;
-constexpr int INFLATE_CTAS_PER_SM = 6;  // 24 resident warps per SM (8.1 KB of shared memory each), <= 85 registers per thread
+constexpr int INFLATE_CTAS_PER_SM = 8;  // 32 resident warps per SM, 64 registers per thread
 
 struct InflateBatch {
     const uint8_t *in_base;

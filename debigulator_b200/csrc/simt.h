@@ -48,7 +48,6 @@ DBG_DEV void cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
 }
 DBG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 DBG_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-DBG_DEV void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 }  // namespace simt
 
@@ -149,7 +148,6 @@ DBG_DEV void cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
 }
 DBG_DEV void cp_async_commit() {}
 DBG_DEV void cp_async_wait_all() {}
-DBG_DEV void cp_async_wait_but_one() {}
 
 }  // namespace simt
 #endif
