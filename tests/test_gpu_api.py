@@ -1,0 +1,207 @@
+"""GPU tests of every entry point of the C-ABI: the reference-compatible scalar
+API (include/inflate.h, decode_png.h, decode_gz.h + legacy aliases), the packed
+host API (single- and multi-wave), and the device-resident API."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import debigulator_b200 as dbg
+from debigulator_b200 import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def L():
+    return dbg.load_library()
+
+
+def test_scalar_inflate(L, ctx, ref):
+    L.inflate_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.inflate.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                          C.POINTER(C.c_uint32), C.c_uint32]
+    L.inflate.restype = None
+    L.inflate_init(None, None, None, 1)
+    data = corpus.word_salad(50000, 3)
+    for level, strat in ((6, 0), (6, 4), (0, 0)):
+        s = corpus.raw_deflate(data, level, strat)
+        cap = max(len(data), len(s)) + 64
+        ib = C.create_string_buffer(s + bytes(16), len(s) + 16)
+        ob = C.create_string_buffer(cap)
+        n, g = C.c_uint64(123), C.c_uint32(7)
+        L.inflate(ob, cap, C.byref(n), None, 0, ib, len(s), C.byref(g), 1)
+        rg, rout = ref.inflate(s, cap)
+        assert g.value == rg == 1 and ob.raw[: n.value] == rout == data
+    # argument checks (inflate.c:797-844)
+    g = C.c_uint32(7)
+    n = C.c_uint64(0)
+    L.inflate(None, 10, C.byref(n), None, 0, ib, 10, C.byref(g), 1)
+    assert g.value == 0
+    L.inflate(ob, 3, C.byref(n), None, 0, ib, 10, C.byref(g), 1)      # recipient_size < compressed_input_size
+    assert g.value == 0
+    L.inflate(ob, 100, C.byref(n), None, 0, ib, 4, C.byref(g), 1)     # compressed_input_size < 5
+    assert g.value == 0
+
+
+def test_scalar_png_and_legacy(L, golden_dir, manifest):
+    L.decode_png_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.decode_png.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint8)]
+    L.decode_png.restype = None
+    L.decode_png_deinit.argtypes = [C.c_uint32]
+    data = open(os.path.join(golden_dir, "gimp_test.png"), "rb").read()
+    want = manifest["fixtures"]["gimp_test.png"]["ref_sha256"]
+    ib = C.create_string_buffer(data, len(data))
+    ob = C.create_string_buffer(1024 * 1024 * 4)
+    g = C.c_uint8(9)
+    L.decode_png(ib, len(data), ob, len(ob), 2, C.byref(g))            # slot 2 not initialised (decode_png.c:691)
+    assert g.value == 0
+    L.decode_png_init(None, None, None, None, 1024 * 1024 * 4 + 1024 + 1 + 3000000, 2)
+    L.decode_png(ib, len(data), ob, len(ob), 2, C.byref(g))
+    assert g.value == 1 and sha(ob.raw) == want
+    assert ib.raw == data                                              # unlike the reference, the input is untouched
+    L.decode_png(ib, len(data), ob, len(ob) - 4, 2, C.byref(g))        # rgba size mismatch (decode_png.c:970)
+    assert g.value == 0
+    L.decode_png_deinit(2)
+    L.decode_png_init(None, None, None, None, 1000000, 2)              # working memory too small (:1060-1081)
+    L.decode_png(ib, len(data), ob, len(ob), 2, C.byref(g))
+    assert g.value == 0
+    L.decode_png_deinit(2)
+    # legacy names (hellopng.c:154-200)
+    L.init_PNG_decoder.argtypes = [C.c_void_p]
+    L.get_PNG_width_height.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.decode_PNG.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    L.init_PNG_decoder(None)
+    w, h, g32 = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    L.get_PNG_width_height(ib, len(data), C.byref(w), C.byref(h), C.byref(g32))
+    assert (g32.value, w.value, h.value) == (1, 1024, 1024)
+    L.decode_PNG(ib, len(data), ob, len(ob), C.byref(g32))
+    assert g32.value == 1 and sha(ob.raw) == want
+
+
+class DecodedData(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_size", C.c_uint32), ("good", C.c_uint32)]
+
+
+def test_scalar_gz(L, golden_dir, manifest):
+    libc = C.CDLL(None)
+    L.init_decode_gz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.decode_gz.argtypes = [C.c_void_p, C.c_uint32]
+    L.decode_gz.restype = C.POINTER(DecodedData)
+    data = open(os.path.join(golden_dir, "gzipsample.gz"), "rb").read()
+    ib = C.create_string_buffer(data, len(data))
+    L.init_decode_gz(C.cast(libc.malloc, C.c_void_p), C.cast(libc.memset, C.c_void_p), C.cast(libc.memcpy, C.c_void_p))
+    r = L.decode_gz(ib, len(data))
+    f = manifest["fixtures"]["gzipsample.gz"]
+    assert r.contents.good == 1 and r.contents.data_size == f["out_len"]
+    assert sha(C.string_at(r.contents.data, r.contents.data_size)) == f["ref_sha256"]
+    bad = C.create_string_buffer(b"\x1f\x8c" + data[2:], len(data))
+    r2 = L.decode_gz(bad, len(data))
+    assert r2.contents.good == 0 and not r2.contents.data and r2.contents.data_size == 0     # Q15 fixed
+
+
+def test_packed_api_waves_and_ragged(ctx):
+    """Monotonic arenas take the multi-wave pipelined path; shuffled offsets the single-wave path."""
+    n = 600
+    base = [corpus.gz_member_cfg5(i, 20000 + 977 * (i % 13)) for i in range(40)]
+    items = [base[i % 40] for i in range(n)]
+    for shuffled in (False, True):
+        order = list(range(n))
+        if shuffled:
+            np.random.default_rng(1).shuffle(order)
+        in_off, out_off = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        ti = to = 0
+        for i in order:
+            g, d = items[i]
+            in_off[i], out_off[i] = ti, to
+            ti += (len(g) + 16 + 15) // 16 * 16
+            to += (len(d) + len(g) + 15) // 16 * 16
+        h_in = np.zeros(ti + 64, np.uint8)
+        h_out = np.zeros(to + 64, np.uint8)
+        for i, (g, d) in enumerate(items):
+            h_in[int(in_off[i]):int(in_off[i]) + len(g)] = np.frombuffer(g, np.uint8)
+        in_size = np.array([len(g) for g, _ in items], np.uint64)
+        out_cap = np.array([len(d) + len(g) for g, d in items], np.uint64)
+        osz, st = ctx.decode_packed(dbg.api.KIND_GZ, h_in, in_off, in_size, h_out, out_off, out_cap)
+        assert int(st.sum()) == 0
+        for i, (g, d) in enumerate(items):
+            assert int(osz[i]) == len(d)
+            assert h_out[int(out_off[i]):int(out_off[i]) + len(d)].tobytes() == d, (shuffled, i)
+
+
+def test_device_api_misaligned_inputs(ctx):
+    import torch
+    dev = torch.device("cuda", 0)
+    data = [corpus.word_salad(30000 + 1000 * i, i) for i in range(33)]
+    streams = [corpus.raw_deflate(d, 6 if i % 2 else 1) for i, d in enumerate(data)]
+    offs, total = [], 16
+    for i, s in enumerate(streams):
+        total += (i * 7) % 16 + 1           # every alignment 0..15 occurs
+        offs.append(total)
+        total += len(s)
+    arena = np.zeros((total + 64 + 15) // 16 * 16, np.uint8)
+    for o, s in zip(offs, streams):
+        arena[o:o + len(s)] = np.frombuffer(s, np.uint8)
+    caps = [len(d) + 64 for d in data]
+    out_off = np.cumsum([0] + caps[:-1]).astype(np.uint64)
+    i64 = lambda a: torch.from_numpy(np.asarray(a, np.uint64).view(np.int64)).to(dev)
+    d_in = torch.from_numpy(arena).to(dev)
+    d_out = torch.zeros(int(sum(caps)), dtype=torch.uint8, device=dev)
+    d_size = torch.zeros(len(data), dtype=torch.int64, device=dev)
+    d_st = torch.full((len(data),), -1, dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        ctx.inflate_device(d_in, i64(offs), i64([len(x) for x in streams]), d_out, i64(out_off), i64(caps), d_size, d_st,
+                           order=None, stream=s.cuda_stream)
+    s.synchronize()
+    assert d_st.abs().sum().item() == 0
+    out = d_out.cpu().numpy()
+    for i, d in enumerate(data):
+        assert int(d_size[i]) == len(d)
+        assert out[int(out_off[i]):int(out_off[i]) + len(d)].tobytes() == d, i
+
+
+def test_png_device_api_large_images(ctx, ref):
+    """One 2048x1536 image per filter mode through the device-resident PNG entry point."""
+    import torch
+    dev = torch.device("cuda", 0)
+    imgs = [corpus.gradient_noise_rgba(2048, 1536, 40 + i) for i in range(3)]
+    files = [corpus.write_png(im, f) for im, f in zip(imgs, (4, 3, -1))]
+    offs, total = [], 0
+    for f in files:
+        offs.append(total)
+        total += (len(f) + 16 + 15) // 16 * 16
+    arena = np.zeros(total + 64, np.uint8)
+    for o, f in zip(offs, files):
+        arena[o:o + len(f)] = np.frombuffer(f, np.uint8)
+    rgba = 2048 * 1536 * 4
+    i64 = lambda a: torch.from_numpy(np.asarray(a, np.uint64).view(np.int64)).to(dev)
+    d_in = torch.from_numpy(arena).to(dev)
+    d_out = torch.zeros(3 * rgba, dtype=torch.uint8, device=dev)
+    d_st = torch.full((3,), -1, dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        ctx.png_device(d_in, i64(offs), i64([len(f) for f in files]), d_out, i64([0, rgba, 2 * rgba]), i64([rgba] * 3), d_st,
+                       sum(len(f) for f in files), 3 * rgba, stream=s.cuda_stream)
+    s.synchronize()
+    assert d_st.tolist() == [0, 0, 0]
+    out = d_out.cpu().numpy()
+    for i, im in enumerate(imgs):
+        assert out[i * rgba:(i + 1) * rgba].tobytes() == im.tobytes(), i
+
+
+def test_failed_items_do_not_poison_batch(ctx):
+    good = corpus.gz_member_cfg2(2, 1 << 15)
+    bad_magic = b"\x00" + good[0][1:]
+    truncated = good[0][: len(good[0]) // 2]
+    items = [good[0], bad_magic, good[0], truncated, b"", good[0]]
+    res = ctx.decode_gz_batch(items, [len(good[1]) + len(good[0])] * len(items))
+    assert [r[0] for r in res] == [1, 0, 1, res[3][0], 0, 1]
+    for k in (0, 2, 5):
+        assert res[k][1] == good[1]
