@@ -17,6 +17,7 @@
 #include "../../include/debigulator_b200.h"
 #include "kernels.cuh"
 #include "png_kernels.cuh"
+#include "split_kernels.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -69,12 +70,14 @@ struct dbg_ctx {
     Buf d_counter;                 // work-queue heads
     Buf d_meta;                    // derived descriptors (gzip payloads, PNG streams)
     Buf d_png_scratch;             // compacted IDAT + filtered scanlines
+    Buf d_split, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
+    uint32_t split_max_streams = 1024;  // batches with fewer streams may use the split-stream path
     // host-API staging
     Buf d_in, d_out, d_desc;       // arenas + descriptor tables
     Buf h_in, h_out, h_desc;       // pinned mirrors
     dbg_ctx()
     {
-        h_in.pinned_host = h_out.pinned_host = h_desc.pinned_host = true;
+        h_in.pinned_host = h_out.pinned_host = h_desc.pinned_host = h_summary.pinned_host = true;
     }
 };
 
@@ -147,6 +150,11 @@ extern "C" dbg_ctx *dbg_create(int device)
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
     dbg::png_configure_kernels();
+    cudaFuncSetAttribute(dbg::split_transfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA));
+    cudaFuncSetAttribute(dbg::split_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA));
+    if (const char *e = getenv("DBG_SPLIT_MAX_STREAMS")) ctx->split_max_streams = (uint32_t)atoi(e);
     return ctx;
 }
 
@@ -155,8 +163,8 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Buf *all[] = {&ctx->d_counter, &ctx->d_meta, &ctx->d_png_scratch, &ctx->d_in, &ctx->d_out,
-                  &ctx->d_desc,    &ctx->h_in,   &ctx->h_out,         &ctx->h_desc};
+    Buf *all[] = {&ctx->d_counter, &ctx->d_meta, &ctx->d_png_scratch, &ctx->d_in,    &ctx->d_out,    &ctx->d_desc,
+                  &ctx->h_in,      &ctx->h_out,  &ctx->h_desc,        &ctx->d_split, &ctx->d_cells, &ctx->h_summary};
     for (Buf *b : all) b->release();
     for (int i = 0; i < dbg_ctx::MAX_WAVES; i++)
         if (ctx->wave_stream[i]) cudaStreamDestroy(ctx->wave_stream[i]);
@@ -201,7 +209,7 @@ extern "C" int dbg_synchronize(dbg_ctx *ctx)
 }
 
 // ------------------------------------------------------------------ launches --
-static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s)
+static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s)
 {
     a.counter = d_counter;
     CU(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), s));
@@ -227,6 +235,85 @@ static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter
     return DBG_OK;
 }
 
+// Split-stream path for batches that cannot fill the GPU with one warp per stream: streams that are a
+// single fixed-Huffman block (every stb-written PNG) are cut into 32 KiB chunks decoded by one warp each.
+// Needs one small device->host read (how many chunks / cells) and therefore synchronises `s` once.
+static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t **skip_out)
+{
+    *skip_out = nullptr;
+    const uint32_t n = a.n;
+    CU(ctx->h_summary.reserve(sizeof(dbg::SplitSummary)));
+    // per-stream scratch first; per-chunk scratch once the chunk count is known
+    size_t per_stream = (size_t)n * (4 + 4 + 8) + 256;
+    CU(ctx->d_split.reserve(per_stream + sizeof(dbg::SplitSummary) + 256));
+    uint8_t *p = (uint8_t *)ctx->d_split.p;
+    dbg::SplitBatch b{};
+    b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
+    b.out_base = a.out_base; b.out_off = a.out_off; b.out_cap = a.out_cap;
+    b.out_size = a.out_size; b.status = a.status; b.pre_status = a.pre_status; b.n = n;
+    b.summary = (dbg::SplitSummary *)p;
+    b.cell_base = (uint64_t *)(p + 256);
+    b.split_flag = (uint32_t *)(b.cell_base + n);
+    b.chunk_base = b.split_flag + n;
+    CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::SplitSummary), s));
+    dbg::split_classify_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    dbg::SplitSummary *hs = (dbg::SplitSummary *)ctx->h_summary.p;
+    CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::SplitSummary), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (hs->total_chunks == 0) return DBG_OK;
+    const uint32_t T = hs->total_chunks;
+    // growing d_split would drop the per-stream arrays just written: they are re-created below if it moves
+    size_t per_chunk = (size_t)T * (4 + 8 + 8 + 4 + 4 + 32 * sizeof(dbg::TransferEntry)) + 1024;
+    size_t need = per_stream + sizeof(dbg::SplitSummary) + 256 + per_chunk;
+    if (need > ctx->d_split.cap) {
+        CU(ctx->d_split.reserve(need));
+        p = (uint8_t *)ctx->d_split.p;
+        b.summary = (dbg::SplitSummary *)p;
+        b.cell_base = (uint64_t *)(p + 256);
+        b.split_flag = (uint32_t *)(b.cell_base + n);
+        b.chunk_base = b.split_flag + n;
+        CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::SplitSummary), s));
+        dbg::split_classify_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);  // same inputs, same decisions
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    uint8_t *q = p + ((per_stream + sizeof(dbg::SplitSummary) + 256 + 255) & ~(size_t)255);
+    b.entry_bits = (uint64_t *)q;
+    b.c_out_off = b.entry_bits + T;
+    b.tf = (dbg::TransferEntry *)(b.c_out_off + T);
+    b.chunk_stream = (uint32_t *)(b.tf + (size_t)T * 32);
+    b.c_out_len = b.chunk_stream + T;
+    b.c_flag = b.c_out_len + T;
+    CU(ctx->d_cells.reserve((size_t)hs->cells_cap * 2 + 256));
+    b.cells = (uint16_t *)ctx->d_cells.p;
+    size_t smem = sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA;
+    uint32_t grid = std::min<uint32_t>((T + dbg::SPLIT_WARPS_PER_CTA - 1) / dbg::SPLIT_WARPS_PER_CTA,
+                                       (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);
+    dbg::split_fill_kernel<<<n, 128, 0, s>>>(b);
+    dbg::split_transfer_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b, T);
+    dbg::split_chain_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);
+    dbg::split_decode_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b, T);
+    dbg::split_resolve_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(b);
+    ctx->launches += 5;
+    CU(cudaGetLastError());
+    *skip_out = b.split_flag;
+    return DBG_OK;
+}
+
+static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s)
+{
+    a.skip = nullptr;
+    if (a.n < ctx->split_max_streams) {
+        const uint32_t *skip = nullptr;
+        int rc = run_split(ctx, a, s, &skip);
+        if (rc) return rc;
+        a.skip = skip;
+    }
+    return launch_inflate_plain(ctx, a, d_counter, s);
+}
+
 // `slot` selects an independent work-queue counter / descriptor scratch so that
 // several waves of one host batch can be in flight on different streams.
 static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -241,10 +328,10 @@ static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t
         dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, gz_off, gz_size, gz_pre);
         ctx->launches++;
         CU(cudaGetLastError());
-        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, d_order, nullptr, (uint32_t)n};
+        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, d_order, nullptr, (uint32_t)n};
         return launch_inflate(ctx, a, counter, s);
     }
-    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, d_order, nullptr, (uint32_t)n};
+    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
     return launch_inflate(ctx, a, counter, s);
 }
 
@@ -317,7 +404,7 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
     if (rc) CU((cudaError_t)rc);
     // 2. inflate the compacted zlib payloads into the filtered-scanline buffers
     dbg::InflateBatch a{lay.idat, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
-                        lay.pre_status, nullptr, nullptr, (uint32_t)n};
+                        lay.pre_status, nullptr, nullptr, nullptr, (uint32_t)n};
     rc = launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
     if (rc) return rc;
     // 3. un-filter (+ palette / RGB expansion) straight into the caller's RGBA
@@ -373,6 +460,7 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
     for (uint64_t i = 1; i < n && mono; i++)
         mono = in_off[i] >= in_off[i - 1] + in_size[i - 1] && out_off[i] >= out_off[i - 1] + out_cap[i - 1];
     int nw = mono ? (int)std::min<uint64_t>(dbg_ctx::MAX_WAVES, std::max<uint64_t>(1, n / 256)) : 1;
+    if (n < ctx->split_max_streams) nw = 1;  // small batches may take the split-stream path, which owns per-context scratch
     CU(cudaMemcpyAsync(dd, hd, 4 * n * 8, cudaMemcpyHostToDevice, s));
     if (kind == 1) CU(ctx->d_meta.reserve(n * 20 + 64));
     uint64_t *gz_off = kind == 1 ? (uint64_t *)ctx->d_meta.p : nullptr;

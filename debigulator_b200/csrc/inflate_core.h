@@ -101,8 +101,8 @@ struct Window {
     uint32_t w0, w1, w2, w3;
     uint32_t wb;          // ring-coordinate index of the word held in w0
     uint32_t s;           // 0..31
-    int32_t wleft;        // words until the one holding the Q2 limit bit (<= 0: the limit is in or before w0)
-    uint32_t q2_w;        // ring-coordinate word index of the Q2 limit bit
+    int32_t wleft;        // words until the one holding the limit bit (<= 0: the limit is in or before w0)
+    uint32_t lim_w, lim_b;  // ring-coordinate word index / bit of the limit: no symbol may start at or past it
 
     DBG_DEVM void load_chunk(uint32_t c)
     {
@@ -161,7 +161,18 @@ struct Window {
         w2 = ring[(wb + 2) & 255];
         w3 = ring[(wb + 3) & 255];
         s = ((uint32_t)bytepos & 3) << 3;
-        wleft = (int32_t)(q2_w - wb);
+        wleft = (int32_t)(lim_w - wb);
+    }
+    DBG_DEVM void seek_bits(uint64_t bitpos)
+    {
+        seek(bitpos >> 3);
+        consume((uint32_t)bitpos & 7);
+    }
+    DBG_DEVM void set_limit(uint64_t limit_bits)
+    {
+        lim_w = (uint32_t)(limit_bits >> 5);
+        lim_b = (uint32_t)limit_bits & 31;
+        wleft = (int32_t)(lim_w - wb);
     }
 };
 
@@ -383,7 +394,284 @@ DBG_DEV uint32_t decode_candidate(const InflateSmem *sm, uint32_t lo, uint32_t m
     return cand_special(32, CAND_ERR);
 }
 
+// ------------------------------------------------------------- output sinks --
+// The symbol decoder is shared by three consumers:
+//   SINK_BYTES  the normal decode: bytes to the output buffer (deferred match stores);
+//   SINK_COUNT  chunk probing for the split-stream path: only sizes are counted;
+//   SINK_U16    chunk decode for the split-stream path: 16-bit cells, where a value
+//               >= 256 is a marker "byte at distance 32768 - (v - 256) before this chunk's
+//               output start", resolved later against the finished output.
+enum { SINK_BYTES = 0, SINK_COUNT = 1, SINK_U16 = 2 };
+enum { END_EOB = 0, END_LIMIT = 1 };
+
+struct Sink {
+    uint8_t *out;     // SINK_BYTES
+    uint16_t *out16;  // SINK_U16
+    uint32_t pos;     // bytes produced so far (relative to out / out16)
+    uint32_t cap;
+    uint64_t abs_base;  // SINK_U16: stream output offset of out16[0] (markers may not reach before the stream)
+    PendingStore pd;
+};
+
+template <int SINK>
+DBG_DEV uint32_t emit_literal(Sink &k, uint32_t byte)
+{
+    if (SINK != SINK_COUNT) {
+        if (k.pos >= k.cap) return ST_OUT_OVERFLOW;
+        if (simt::lane() == 0) {
+            if (SINK == SINK_BYTES) k.out[k.pos] = (uint8_t)byte;
+            else k.out16[k.pos] = (uint16_t)byte;
+        }
+    }
+    k.pos++;
+    return ST_OK;
+}
+
+DBG_DEV_NOINLINE void copy_match_u16(uint16_t *o, uint32_t pos, uint32_t len, uint32_t dist)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    simt::syncwarp();
+    // every source index lies before `pos` (overlaps replicate the dist-long pattern), so all
+    // reads precede all writes of this match; negative indices are markers into the 32 KiB
+    // window that ends where this chunk's output starts
+    uint32_t idx = dist >= len ? ln : ln % dist;
+    const uint32_t step = dist >= len ? 32 : 32 % dist;
+    for (uint32_t b = 0; b < len; b += 32) {
+        if (b + ln < len) {
+            int32_t si = (int32_t)pos - (int32_t)dist + (int32_t)idx;
+            uint32_t v = si < 0 ? (uint32_t)(256 + 32768 + si) : o[si];
+            o[pos + b + ln] = (uint16_t)v;
+        }
+        idx += step;
+        if (dist < len && idx >= dist) idx -= dist;
+    }
+    simt::syncwarp();
+}
+
+template <int SINK>
+DBG_DEV uint32_t emit_match(Sink &k, uint32_t len, uint32_t dist)
+{
+    if (SINK == SINK_COUNT) {
+        k.pos += len;
+        return ST_OK;
+    }
+    if (k.pos + len > k.cap) return ST_OUT_OVERFLOW;
+    if (SINK == SINK_BYTES) {
+        if (dist > k.pos) return ST_BAD_DISTANCE;  // inflate.c:1843
+        copy_match(k.out, k.pos, len, dist, k.pd);
+    } else {
+        if (dist > 32768 || dist > k.abs_base + k.pos) return ST_BAD_DISTANCE;
+        copy_match_u16(k.out16, k.pos, len, dist);
+    }
+    k.pos += len;
+    return ST_OK;
+}
+
+// ------------------------------------------------------------- block headers --
+struct BlockTables {
+    uint32_t lit_max, dist_max;
+};
+
+// Builds the decode tables of a fixed (btype 1) or dynamic (btype 2) block whose
+// 3 header bits have just been consumed (inflate.c:1018-1181 / :1182-1667).
+DBG_DEV uint32_t read_huffman_tables(Window &w, InflateSmem *sm, uint32_t btype, BlockTables &bt)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    uint32_t hlit = 288, hdist = 32;
+    if (btype == 1) {
+        // fixed code (inflate.c:1035-1084); distances are 5-bit codes (:1783-1788)
+        for (uint32_t i = ln; i < 320; i += 32)
+            sm->lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
+        simt::syncwarp();
+    } else {
+        uint32_t v = w.peek32();
+        hlit = (v & 31) + 257;
+        hdist = ((v >> 5) & 31) + 1;
+        uint32_t hclen = ((v >> 10) & 15) + 4;
+        w.consume(14);
+        if (ln < 19) sm->lens[ln] = 0;
+        simt::syncwarp();
+        for (uint32_t i = 0; i < hclen; i++) {
+            if (ln == 0) sm->lens[swizzle_at(i)] = (uint8_t)(w.peek32() & 7);
+            w.consume(3);
+        }
+        simt::syncwarp();
+        uint32_t cl_max;
+        if (!build_table<K_CLEN, uint8_t>(sm->lens, 19, 7, sm->dist_lut, sm->dist_sorted, sm->dist_first, sm->dist_offs,
+                                          sm->dist_cnt, &cl_max))
+            return ST_BAD_TABLE;
+        const uint32_t n = hlit + hdist;
+        uint32_t i = 0, prev = 0;
+        while (i < n) {
+            uint32_t bits = w.peek32();
+            uint32_t e = sm->dist_lut[bits & 127];
+            uint32_t l = e & 15;
+            if (l == 0) return ST_BAD_CODE;
+            uint32_t sym = e >> 16;
+            if (sym < 16) {
+                w.consume(l);
+                if (ln == 0) sm->lens[i] = (uint8_t)sym;
+                prev = sym;
+                i++;
+                continue;
+            }
+            uint32_t rep, val;
+            if (sym == 16) {  // inflate.c:1439-1469
+                if (i == 0) return ST_BAD_REPEAT;
+                rep = 3 + ((bits >> l) & 3);
+                w.consume(l + 2);
+                val = prev;
+            } else if (sym == 17) {  // :1471-1488
+                rep = 3 + ((bits >> l) & 7);
+                w.consume(l + 3);
+                val = 0;
+            } else {  // :1490-1509
+                rep = 11 + ((bits >> l) & 127);
+                w.consume(l + 7);
+                val = 0;
+            }
+            for (uint32_t k = ln; k < rep; k += 32)
+                if (i + k < n) sm->lens[i + k] = (uint8_t)val;
+            prev = val;
+            i += rep;
+        }
+        simt::syncwarp();
+    }
+    if (!build_table<K_LITLEN, uint16_t>(sm->lens, (int)hlit, LIT_ROOT, sm->lit_lut, sm->lit_sorted, sm->lit_first,
+                                         sm->lit_offs, sm->lit_cnt, &bt.lit_max))
+        return ST_BAD_TABLE;
+    if (!build_table<K_DIST, uint8_t>(sm->lens + hlit, (int)hdist, DIST_ROOT, sm->dist_lut, sm->dist_sorted, sm->dist_first,
+                                      sm->dist_offs, sm->dist_cnt, &bt.dist_max))
+        return ST_BAD_TABLE;
+    return ST_OK;
+}
+
+// ------------------------------------------------------------ symbol decoder --
+// Decodes symbols from the window position until end-of-block (END_EOB) or
+// until the next symbol would start at or past the window's limit (END_LIMIT).
+// Each pass looks at one 32-bit window: every lane decodes the candidate
+// symbol at its own bit offset (LUT lookups, extra bits, distance) in
+// parallel, then the warp walks the chain of real symbol starts with one
+// shuffle per symbol.
+template <int SINK>
+DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &bt, Sink &k, uint32_t &end_reason)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    for (;;) {
+        uint32_t lim = 32;
+        if (w.wleft <= 0) {
+            lim = w.wleft == 0 ? w.lim_b : 0u;
+            if (w.s >= lim) {
+                end_reason = END_LIMIT;
+                return ST_OK;
+            }
+        }
+        const uint32_t lo = simt::funnel_r(w.w0, w.w1, ln);
+        const uint32_t mid = simt::funnel_r(w.w1, w.w2, ln);
+        const uint32_t cand = decode_candidate(sm, lo, mid, ln);
+        uint32_t p = w.s, cur, err = 0;
+        bool eob = false, slow = false;
+        do {
+            cur = p;
+            const uint32_t info = simt::shfl(cand, (int)p);
+            const uint32_t lf = (info >> 7) & 511;
+            p = info & 127;
+            if (lf == 0) {
+                err = emit_literal<SINK>(k, info >> 16);
+                if (err) break;
+            } else if (lf >= 3) {
+                err = emit_match<SINK>(k, lf, (info >> 16) + 1);
+                if (err) break;
+            } else {
+                const uint32_t code = info >> 16;
+                if (code == CAND_EOB) eob = true;
+                else if (code == CAND_ERR) err = ST_BAD_SYMBOL;
+                else slow = true;  // a code longer than the primary LUT index starts at `cur`
+                break;
+            }
+        } while (p < lim);
+        if (err) return err;
+        if (slow) {
+            // rare: decode this one symbol serially (uniform), then rebuild the window candidates
+            w.s = cur;
+            uint32_t bits = w.peek32();
+            uint32_t e = sm->lit_lut[bits & ((1u << LIT_ROOT) - 1)];
+            if ((e & 15) == 0) {
+                e = slow_decode<K_LITLEN, uint16_t>(bits, LIT_ROOT, bt.lit_max, sm->lit_sorted, sm->lit_first, sm->lit_offs,
+                                                    sm->lit_cnt);
+                if (!e) return ST_BAD_CODE;
+            }
+            w.consume(e & 15);
+            if (e & E_LIT) {
+                err = emit_literal<SINK>(k, e >> 16);
+                if (err) return err;
+                continue;
+            }
+            if (e & E_EOB) {
+                end_reason = END_EOB;
+                return ST_OK;
+            }
+            if (e & E_BAD) return ST_BAD_SYMBOL;
+            bits = w.peek32();
+            uint32_t xb = (e >> 8) & 31;
+            uint32_t len = (e >> 16) + (bits & ((1u << xb) - 1));
+            w.consume(xb);
+            bits = w.peek32();
+            e = sm->dist_lut[bits & ((1u << DIST_ROOT) - 1)];
+            if ((e & 15) == 0) {
+                e = slow_decode<K_DIST, uint8_t>(bits, DIST_ROOT, bt.dist_max, sm->dist_sorted, sm->dist_first, sm->dist_offs,
+                                                 sm->dist_cnt);
+                if (!e) return ST_BAD_CODE;
+            }
+            if (e & E_BAD) return ST_BAD_SYMBOL;
+            xb = (e >> 8) & 31;
+            uint32_t l2 = e & 15;
+            uint32_t dist = (e >> 16) + ((bits >> l2) & ((1u << xb) - 1));
+            w.consume(l2 + xb);
+            err = emit_match<SINK>(k, len, dist);
+            if (err) return err;
+            continue;
+        }
+        // the window now sits exactly on the next symbol start (the chunk prober relies on it)
+        w.s = p & 31;
+        if (p >= 32) {
+            w.shift();
+            if (p >= 64) w.shift();
+        }
+        if (eob) {
+            end_reason = END_EOB;
+            return ST_OK;
+        }
+        if (lim < 32) {  // the walk ran into the limit
+            end_reason = END_LIMIT;
+            return ST_OK;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- the stream --
+struct StreamIn {
+    uint32_t mis;        // in & 15
+    uint64_t end_byte;   // ring coordinates
+    uint64_t q2_limit;   // ring-coordinate bit: rule Q2 (inflate.c:1702-1717)
+};
+
+DBG_DEV StreamIn open_stream(Window &w, InflateSmem *sm, const uint8_t *in, uint64_t in_size)
+{
+    StreamIn g;
+    g.mis = (uint32_t)((uintptr_t)in & 15);
+    g.end_byte = (uint64_t)g.mis + in_size;
+    // Q2: the stream ends, successfully, as soon as the byte cursor ceil(P/8) has
+    // reached in_size, i.e. P >= 8*in_size - 7.
+    g.q2_limit = 8 * g.end_byte - 7;
+    w.base = in - g.mis;
+    w.ring = sm->ring;
+    w.end16 = (uint32_t)((g.end_byte + 15) & ~15ull);
+    w.lim_w = (uint32_t)(g.q2_limit >> 5);
+    w.lim_b = (uint32_t)g.q2_limit & 31;
+    return g;
+}
+
 // Decodes one raw DEFLATE stream of `in_size` bytes at `in` into out[0..cap).
 // Every lane of the warp must call it with identical arguments; the return
 // value and *final_size are uniform. `in` may have any alignment; bytes from
@@ -397,28 +685,24 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     if (in_size >= (1ull << 31) || cap >= (1ull << 32) - 1024) return ST_TOO_LARGE;  // keeps pos + len in 32 bits
 
     const uint32_t ln = (uint32_t)simt::lane();
-    const uint32_t mis = (uint32_t)((uintptr_t)in & 15);
-    const uint64_t end_byte = (uint64_t)mis + in_size;  // ring coordinates
     Window w;
-    w.base = in - mis;
-    w.ring = sm->ring;
-    w.end16 = (uint32_t)((end_byte + 15) & ~15ull);
-    // Q2 (inflate.c:1702-1717): the stream ends, successfully, as soon as the
-    // byte cursor ceil(P/8) has reached in_size, i.e. P >= 8*in_size - 7.
-    const uint64_t q2_limit = 8 * end_byte - 7;
-    w.q2_w = (uint32_t)(q2_limit >> 5);
-    w.seek(mis);
+    const StreamIn g = open_stream(w, sm, in, in_size);
+    w.seek(g.mis);
 
-    uint32_t pos = 0;
-    const uint32_t cap32 = (uint32_t)cap;
-    uint32_t lit_max = 0, dist_max = 0;
-    PendingStore pd;
-    pd.ptr = out;
-    pd.val = 0;
-    pd.on = false;
+    Sink k;
+    k.out = out;
+    k.out16 = nullptr;
+    k.abs_base = 0;
+    k.pos = 0;
+    k.cap = (uint32_t)cap;
+    k.pd.ptr = out;
+    k.pd.val = 0;
+    k.pd.on = false;
+    BlockTables bt;
+    bt.lit_max = bt.dist_max = 0;
     bool more = true;
     while (more) {
-        if (w.abs_bits() >= 8 * end_byte) return ST_TRUNCATED;
+        if (w.abs_bits() >= 8 * g.end_byte) return ST_TRUNCATED;
         uint32_t hdr = w.peek32() & 7;
         w.consume(3);
         if (hdr & 1) more = false;
@@ -431,189 +715,192 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
             if (len != (~nlen & 0xffff)) return ST_STORED_LEN;
             if (len) {
                 uint64_t bytepos = w.abs_bits() >> 3;
-                if (bytepos + len > end_byte) return ST_TRUNCATED;
-                if ((uint64_t)pos + len > cap32) return ST_OUT_OVERFLOW;
+                if (bytepos + len > g.end_byte) return ST_TRUNCATED;
+                if ((uint64_t)k.pos + len > k.cap) return ST_OUT_OVERFLOW;
                 const uint8_t *src = w.base + bytepos;
-                uint8_t *dst = out + pos;
+                uint8_t *dst = out + k.pos;
                 for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
-                pos += len;
+                k.pos += len;
                 w.seek(bytepos + len);
             }
             continue;
         }
         if (btype == 3) continue;  // inflate.c:990-998: ignored in the no-assert build
+        uint32_t st = read_huffman_tables(w, sm, btype, bt);
+        if (st) return st;
+        uint32_t why = END_EOB;
+        st = decode_symbols<SINK_BYTES>(w, sm, bt, k, why);
+        if (st) return st;
+        if (why == END_LIMIT) more = false;  // rule Q2
+    }
+    flush_pending(k.pd);
+    *final_size = k.pos;
+    return ST_OK;
+}
 
-        uint32_t hlit = 288, hdist = 32;
-        if (btype == 1) {
-            // fixed code (inflate.c:1035-1084); distances are 5-bit codes (:1783-1788)
-            for (uint32_t i = ln; i < 320; i += 32)
-                sm->lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
-            simt::syncwarp();
-        } else {
-            uint32_t v = w.peek32();
-            hlit = (v & 31) + 257;
-            hdist = ((v >> 5) & 31) + 1;
-            uint32_t hclen = ((v >> 10) & 15) + 4;
-            w.consume(14);
-            if (ln < 19) sm->lens[ln] = 0;
-            simt::syncwarp();
-            for (uint32_t i = 0; i < hclen; i++) {
-                if (ln == 0) sm->lens[swizzle_at(i)] = (uint8_t)(w.peek32() & 7);
-                w.consume(3);
-            }
-            simt::syncwarp();
-            uint32_t cl_max;
-            if (!build_table<K_CLEN, uint8_t>(sm->lens, 19, 7, sm->dist_lut, sm->dist_sorted, sm->dist_first,
-                                              sm->dist_offs, sm->dist_cnt, &cl_max))
-                return ST_BAD_TABLE;
-            const uint32_t n = hlit + hdist;
-            uint32_t i = 0, prev = 0;
-            while (i < n) {
-                uint32_t bits = w.peek32();
-                uint32_t e = sm->dist_lut[bits & 127];
-                uint32_t l = e & 15;
-                if (l == 0) return ST_BAD_CODE;
-                uint32_t sym = e >> 16;
-                if (sym < 16) {
-                    w.consume(l);
-                    if (ln == 0) sm->lens[i] = (uint8_t)sym;
-                    prev = sym;
-                    i++;
-                    continue;
-                }
-                uint32_t rep, val;
-                if (sym == 16) {  // inflate.c:1439-1469
-                    if (i == 0) return ST_BAD_REPEAT;
-                    rep = 3 + ((bits >> l) & 3);
-                    w.consume(l + 2);
-                    val = prev;
-                } else if (sym == 17) {  // :1471-1488
-                    rep = 3 + ((bits >> l) & 7);
-                    w.consume(l + 3);
-                    val = 0;
-                } else {  // :1490-1509
-                    rep = 11 + ((bits >> l) & 127);
-                    w.consume(l + 7);
-                    val = 0;
-                }
-                for (uint32_t k = ln; k < rep; k += 32)
-                    if (i + k < n) sm->lens[i + k] = (uint8_t)val;
-                prev = val;
-                i += rep;
-            }
-            simt::syncwarp();
-        }
-        if (!build_table<K_LITLEN, uint16_t>(sm->lens, (int)hlit, LIT_ROOT, sm->lit_lut, sm->lit_sorted, sm->lit_first,
-                                             sm->lit_offs, sm->lit_cnt, &lit_max))
-            return ST_BAD_TABLE;
-        if (!build_table<K_DIST, uint8_t>(sm->lens + hlit, (int)hdist, DIST_ROOT, sm->dist_lut, sm->dist_sorted,
-                                          sm->dist_first, sm->dist_offs, sm->dist_cnt, &dist_max))
-            return ST_BAD_TABLE;
+// ------------------------------------------------------------- split stream --
+// Intra-stream parallelism for streams that are ONE FIXED-Huffman block: what
+// stb_image_write emits for every PNG (stb_write.h:913-916), i.e. BASELINE
+// configs 3 and 4, where a handful of 150 MB streams would otherwise be decoded
+// by a handful of warps ("hard parts").
+//
+// Fixed-Huffman streams do not self-synchronise (measured: profiles/experiments),
+// so chunk boundaries are not guessed. Instead, because a fixed-code symbol is at
+// most 31 bits long (9 + 5 + 5 + 13 - 1), some symbol starts within any 31
+// consecutive bits, and the 32 lanes of a warp can carry ALL 32 possible entry
+// offsets of a chunk at once:
+//   transfer  one warp per CHUNK_BYTES of compressed data; lane j decodes
+//             (sizes only) from bit j of the chunk to the chunk end and records
+//             where it leaves the chunk, how many bytes it produced and how it
+//             ended: an exact transfer table  entry offset -> (exit offset, bytes).
+//   chain     one thread per stream walks the tables from chunk 0: exact entry
+//             bit and output offset of every chunk.
+//   decode    one warp per chunk decodes from its exact entry into 16-bit cells;
+//             a match that reaches before the chunk's own output becomes a
+//             marker (256 + 32768 - distance_before_chunk_start).
+//   resolve   one CTA per stream, chunk after chunk: cells -> bytes, markers
+//             read the already finished output.
+enum { CHUNK_BYTES = 32768, CHUNK_BITS = CHUNK_BYTES * 8 };
+enum : uint32_t { CH_RUN = 0, CH_EOB = 1, CH_Q2 = 2, CH_IDLE = 3, CH_ERR = 16 };  // CH_ERR + status
 
-        // ---- symbols. Each pass looks at one 32-bit window: every lane decodes
-        // the candidate symbol at its own bit offset (LUT lookups, extra bits,
-        // distance) in parallel, then the warp walks the chain of real symbol
-        // starts with one shuffle per symbol.
-        for (;;) {
-            // Q2: symbols may only start below bit `lim` of this window
-            uint32_t lim = 32;
-            if (w.wleft <= 0) {
-                lim = w.wleft == 0 ? (uint32_t)(q2_limit & 31) : 0u;
-                if (w.s >= lim) {
-                    more = false;
-                    break;
-                }
-            }
-            const uint32_t lo = simt::funnel_r(w.w0, w.w1, ln);
-            const uint32_t mid = simt::funnel_r(w.w1, w.w2, ln);
-            const uint32_t cand = decode_candidate(sm, lo, mid, ln);
-            uint32_t p = w.s, cur, err = 0;
-            bool eob = false, slow = false;
-            do {
-                cur = p;
-                const uint32_t info = simt::shfl(cand, (int)p);
-                const uint32_t lf = (info >> 7) & 511;
-                p = info & 127;
-                if (lf == 0) {  // literal
-                    if (pos >= cap32) {
-                        err = ST_OUT_OVERFLOW;
-                        break;
-                    }
-                    if (ln == 0) out[pos] = (uint8_t)(info >> 16);
-                    pos++;
-                } else if (lf >= 3) {  // match
-                    const uint32_t dist = (info >> 16) + 1;
-                    if ((dist > pos) | (pos + lf > cap32)) {
-                        err = dist > pos ? ST_BAD_DISTANCE : ST_OUT_OVERFLOW;
-                        break;
-                    }
-                    copy_match(out, pos, lf, dist, pd);
-                    pos += lf;
-                } else {
-                    const uint32_t code = info >> 16;
-                    if (code == CAND_EOB) eob = true;
-                    else if (code == CAND_ERR) err = ST_BAD_SYMBOL;
-                    else slow = true;  // a code longer than the primary LUT index starts at `cur`
-                    break;
-                }
-            } while (p < lim);
-            if (err) return err;
-            if (slow) {
-                // rare: decode this one symbol serially (uniform), then rebuild the window candidates
-                w.s = cur;
-                uint32_t bits = w.peek32();
-                uint32_t e = sm->lit_lut[bits & ((1u << LIT_ROOT) - 1)];
-                if ((e & 15) == 0) {
-                    e = slow_decode<K_LITLEN, uint16_t>(bits, LIT_ROOT, lit_max, sm->lit_sorted, sm->lit_first,
-                                                        sm->lit_offs, sm->lit_cnt);
-                    if (!e) return ST_BAD_CODE;
-                }
-                w.consume(e & 15);
-                if (e & E_LIT) {
-                    if (pos >= cap32) return ST_OUT_OVERFLOW;
-                    if (ln == 0) out[pos] = (uint8_t)(e >> 16);
-                    pos++;
-                    continue;
-                }
-                if (e & E_EOB) break;
-                if (e & E_BAD) return ST_BAD_SYMBOL;
-                bits = w.peek32();
-                uint32_t xb = (e >> 8) & 31;
-                uint32_t len = (e >> 16) + (bits & ((1u << xb) - 1));
-                w.consume(xb);
-                bits = w.peek32();
-                e = sm->dist_lut[bits & ((1u << DIST_ROOT) - 1)];
-                if ((e & 15) == 0) {
-                    e = slow_decode<K_DIST, uint8_t>(bits, DIST_ROOT, dist_max, sm->dist_sorted, sm->dist_first,
-                                                     sm->dist_offs, sm->dist_cnt);
-                    if (!e) return ST_BAD_CODE;
-                }
-                if (e & E_BAD) return ST_BAD_SYMBOL;
-                xb = (e >> 8) & 31;
-                uint32_t l2 = e & 15;
-                uint32_t dist = (e >> 16) + ((bits >> l2) & ((1u << xb) - 1));
-                w.consume(l2 + xb);
-                if (dist > pos) return ST_BAD_DISTANCE;
-                if (pos + len > cap32) return ST_OUT_OVERFLOW;
-                copy_match(out, pos, len, dist, pd);
-                pos += len;
-                continue;
-            }
-            if (!eob && lim < 32) {  // the walk ran into the Q2 limit
-                more = false;
+// Lane-local fixed-Huffman size decode of the symbol at ring bit `pos`:
+// returns the symbol's bit length (0 = undecodable) and its output bytes in
+// *out_bytes (0 for end-of-block, flagged in *eob).
+DBG_DEV uint32_t lane_symbol_size(const InflateSmem *sm, uint32_t pos, uint32_t *out_bytes, bool *eob)
+{
+    const uint32_t wi = pos >> 5, sh = pos & 31;
+    const uint32_t a = sm->ring[wi & 255], b = sm->ring[(wi + 1) & 255], c = sm->ring[(wi + 2) & 255];
+    const uint32_t lo = simt::funnel_r(a, b, sh), hi = simt::funnel_r(b, c, sh);
+    const uint32_t e = sm->lit_lut[lo & ((1u << LIT_ROOT) - 1)];  // fixed code: every code fits the primary table
+    const uint32_t l1 = e & 15;
+    *eob = false;
+    *out_bytes = 1;
+    if (e & E_LIT) return l1;
+    if (e & E_BASE) {
+        const uint32_t xb = (e >> 8) & 31;
+        *out_bytes = (e >> 16) + ((lo >> l1) & ((1u << xb) - 1));
+        const uint32_t t1 = l1 + xb;
+        const uint32_t v = simt::funnel_r(lo, hi, t1);
+        const uint32_t e2 = sm->dist_lut[v & ((1u << DIST_ROOT) - 1)];
+        if (!(e2 & E_BASE)) return 0;  // distance symbols 30 / 31
+        return t1 + (e2 & 15) + ((e2 >> 8) & 31);
+    }
+    *out_bytes = 0;
+    if (e & E_EOB) {
+        *eob = true;
+        return l1;
+    }
+    return 0;  // litlen 286 / 287
+}
+
+struct TransferEntry {   // result of entering a chunk at bit (chunk start + lane)
+    uint32_t out_bytes;
+    uint8_t next;        // exit offset into the next chunk (0..30)
+    uint8_t flag;        // CH_RUN / CH_EOB / CH_Q2 / CH_ERR
+    uint16_t pad;
+};
+
+// Transfer table of chunk `chunk` (>= 1) of a single-fixed-block stream; lane j
+// writes table[j]. Chunk 0 has one known entry (bit 3) and is computed by lane 0
+// semantics: every lane starts at bit 3, so all 32 entries are identical.
+DBG_DEV void transfer_chunk_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint32_t chunk, TransferEntry *table)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    Window w;
+    const StreamIn g = open_stream(w, sm, in, in_size);
+    BlockTables bt;
+    bt.lit_max = bt.dist_max = 0;
+    read_huffman_tables(w, sm, 1, bt);  // the fixed code
+    const uint64_t off = 8ull * g.mis;  // stream-relative bit -> ring-coordinate bit
+    const uint64_t start = (uint64_t)chunk * CHUNK_BITS + off;
+    const uint64_t stop = start + CHUNK_BITS;
+    uint64_t pos = chunk == 0 ? off + 3 : start + ln;
+    uint32_t outb = 0, flag = CH_RUN;
+    // the input is walked in 512-byte ring chunks; all lanes stay within 31 bits of each other
+    const uint32_t c0 = (uint32_t)(start >> 12);                 // first 512 B ring chunk touched
+    const uint32_t c1 = (uint32_t)((stop + 31 + 95) >> 12);      // last one touched (3-word fetches)
+    simt::cp_async_wait_all();
+    simt::syncwarp();
+    w.load_chunk(c0);
+    simt::cp_async_commit();
+    for (uint32_t c = c0; c <= c1; c++) {
+        simt::syncwarp();
+        w.load_chunk(c + 1);  // the slot of ring chunk c-1, which no lane reads any more
+        simt::cp_async_commit();
+        simt::cp_async_wait_all();
+        simt::syncwarp();
+        const uint64_t seg_end = ((uint64_t)(c + 1) << 12) < stop ? ((uint64_t)(c + 1) << 12) : stop;
+        while (flag == CH_RUN && pos < seg_end) {
+            if (pos >= g.q2_limit) {  // rule Q2: no symbol may start here
+                flag = CH_Q2;
                 break;
             }
-            w.s = p & 31;
-            if (p >= 32) {
-                w.shift();
-                if (p >= 64) w.shift();
+            uint32_t ob;
+            bool eob;
+            uint32_t bits = lane_symbol_size(sm, (uint32_t)(pos & 0xffffffffu), &ob, &eob);
+            if (bits == 0) {
+                flag = CH_ERR;
+                break;
             }
-            if (eob) break;
+            pos += bits;
+            if (eob) {
+                flag = CH_EOB;
+                break;
+            }
+            outb += ob;
         }
     }
-    flush_pending(pd);
-    *final_size = pos;
-    return ST_OK;
+    TransferEntry t;
+    t.out_bytes = outb;
+    t.next = (uint8_t)(flag == CH_RUN ? (uint32_t)(pos - stop) : 0);
+    t.flag = (uint8_t)flag;
+    t.pad = 0;
+    table[ln] = t;
+}
+
+struct ChunkResult {
+    uint64_t exit_bits;  // stream-relative bit where the next chunk's first symbol starts
+    uint32_t out_bytes;
+    uint32_t flag;
+};
+
+// A stream qualifies for the split path when it is one final fixed-Huffman block.
+DBG_DEV bool is_single_fixed_block(const uint8_t *in) { return (in[0] & 7) == 3; }  // BFINAL=1, BTYPE=01
+
+// Decodes chunk `chunk` from its exact entry bit (stream-relative) into cells.
+template <int SINK>
+DBG_DEV ChunkResult decode_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint32_t chunk, uint64_t entry_bits,
+                                 uint16_t *cells, uint32_t cell_cap, uint64_t abs_base)
+{
+    ChunkResult r;
+    Window w;
+    const StreamIn g = open_stream(w, sm, in, in_size);
+    BlockTables bt;
+    bt.lit_max = bt.dist_max = 0;
+    read_huffman_tables(w, sm, 1, bt);
+    const uint64_t off = 8ull * g.mis;
+    const uint64_t chunk_end = (uint64_t)(chunk + 1) * CHUNK_BITS + off;
+    const bool q2_first = g.q2_limit <= chunk_end;
+    w.lim_w = (uint32_t)((q2_first ? g.q2_limit : chunk_end) >> 5);
+    w.lim_b = (uint32_t)(q2_first ? g.q2_limit : chunk_end) & 31;
+    w.seek_bits(entry_bits + off);
+    Sink k;
+    k.out = nullptr;
+    k.out16 = cells;
+    k.abs_base = abs_base;
+    k.pos = 0;
+    k.cap = cell_cap;
+    k.pd.ptr = nullptr;
+    k.pd.val = 0;
+    k.pd.on = false;
+    uint32_t why = END_EOB;
+    uint32_t st = decode_symbols<SINK>(w, sm, bt, k, why);
+    r.exit_bits = w.abs_bits() - off;
+    r.out_bytes = k.pos;
+    if (st) r.flag = CH_ERR + st;
+    else if (why == END_EOB) r.flag = CH_EOB;
+    else r.flag = q2_first ? CH_Q2 : CH_RUN;
+    return r;
 }
 
 }  // namespace dbg

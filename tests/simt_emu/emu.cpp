@@ -130,6 +130,91 @@ extern "C" uint32_t emu_inflate(const uint8_t *in, uint64_t in_size, uint8_t *ou
     return st;
 }
 
+// ----------------------------------------------------------- split stream ----
+struct ChunkArgs {
+    dbg::InflateSmem *sm;
+    const uint8_t *in;
+    uint64_t in_size;
+    uint32_t chunk;
+    uint64_t entry;
+    uint16_t *cells;
+    uint32_t cell_cap;
+    uint64_t abs_base;
+    int write;
+    dbg::TransferEntry *table;
+    dbg::ChunkResult res[32];
+};
+static void chunk_body(void *p)
+{
+    ChunkArgs *a = (ChunkArgs *)p;
+    int l = simt::lane();
+    if (a->write)
+        a->res[l] = dbg::decode_chunk<dbg::SINK_U16>(a->sm, a->in, a->in_size, a->chunk, a->entry, a->cells, a->cell_cap, a->abs_base);
+    else
+        dbg::transfer_chunk_warp(a->sm, a->in, a->in_size, a->chunk, a->table);
+}
+
+// The whole split-stream pipeline (transfer tables, chain, 16-bit decode, resolve) run chunk
+// by chunk through the emulator, mirroring split_kernels.cuh. Returns the status.
+extern "C" uint32_t emu_split_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
+                                      int misalign, int reverse)
+{
+    size_t arena_sz = ((size_t)in_size + 64 + 32 + 15) & ~(size_t)15;
+    uint8_t *arena = (uint8_t *)aligned_alloc(16, arena_sz);
+    memset(arena, 0xA5, arena_sz);
+    uint8_t *src = arena + 16 + (misalign & 15);
+    memcpy(src, in, in_size);
+    dbg::InflateSmem *sm = (dbg::InflateSmem *)aligned_alloc(16, sizeof(dbg::InflateSmem));
+    *final_size = 0;
+    uint32_t status = 0;
+    if (!dbg::is_single_fixed_block(src)) { free(sm); free(arena); return 0x2000; }
+    uint32_t nch = (uint32_t)((in_size + dbg::CHUNK_BYTES - 1) / dbg::CHUNK_BYTES);
+    dbg::TransferEntry *tf = (dbg::TransferEntry *)calloc((size_t)nch * 32, sizeof(dbg::TransferEntry));
+    uint64_t *entry = (uint64_t *)calloc(nch, 8), *ooff = (uint64_t *)calloc(nch + 1, 8);
+    uint32_t *olen = (uint32_t *)calloc(nch, 4), *flag = (uint32_t *)calloc(nch, 4);
+    ChunkArgs a;
+    a.sm = sm; a.in = src; a.in_size = in_size; a.cells = nullptr;
+    for (uint32_t c = 0; c < nch; c++) {
+        a.chunk = c; a.write = 0; a.table = tf + (size_t)c * 32;
+        simt::run_warp(chunk_body, &a, reverse);
+    }
+    uint64_t total = 0;
+    uint32_t idx = 0;
+    bool ended = false;
+    for (uint32_t c = 0; c < nch; c++) {
+        ooff[c] = total;
+        if (ended) { flag[c] = dbg::CH_IDLE; continue; }
+        dbg::TransferEntry t = tf[(size_t)c * 32 + idx];
+        entry[c] = c == 0 ? 3 : (uint64_t)c * dbg::CHUNK_BITS + idx;
+        olen[c] = t.out_bytes; flag[c] = t.flag; total += t.out_bytes;
+        if (t.flag != dbg::CH_RUN) { ended = true; if (t.flag >= dbg::CH_ERR) status = dbg::ST_BAD_SYMBOL; }
+        idx = t.next;
+    }
+    if (!ended) status = dbg::ST_TRUNCATED;
+    if (!status && total > cap) status = dbg::ST_OUT_OVERFLOW;
+    if (!status) {
+        uint16_t *cells = (uint16_t *)malloc((total + 16) * 2);
+        for (uint32_t c = 0; c < nch && !status; c++) {
+            if (flag[c] == dbg::CH_IDLE) break;
+            a.chunk = c; a.entry = entry[c]; a.write = 1; a.cells = cells + ooff[c]; a.cell_cap = olen[c]; a.abs_base = ooff[c];
+            simt::run_warp(chunk_body, &a, reverse);
+            if (a.res[0].flag >= dbg::CH_ERR) status = a.res[0].flag - dbg::CH_ERR;
+            else if (a.res[0].out_bytes != olen[c] || a.res[0].flag != flag[c]) status = 0x3000;
+        }
+        for (uint32_t c = 0; c < nch && !status; c++) {
+            if (flag[c] == dbg::CH_IDLE) break;
+            for (uint32_t i = 0; i < olen[c]; i++) {
+                uint32_t v = cells[ooff[c] + i];
+                out[ooff[c] + i] = v < 256 ? (uint8_t)v : out[ooff[c] + (int64_t)v - 33024];
+            }
+        }
+        free(cells);
+        if (!status) *final_size = total;
+    }
+    free(tf); free(entry); free(ooff); free(olen); free(flag); free(sm); free(arena);
+    return status;
+}
+
 // ------------------------------------------------------------------- PNG -----
 #include "../../debigulator_b200/csrc/png_core.h"
 

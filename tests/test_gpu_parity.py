@@ -171,3 +171,26 @@ def test_large_batch_roundtrip_property(ctx):
     want = [sha(d) for _, d in base]
     for i, (good, out) in enumerate(res):
         assert good == 1 and sha(out) == want[i % 64], i
+
+
+def test_split_stream_path_vs_reference(ctx, ref):
+    """Few large single-fixed-block streams (what stb writes): the batch is below the split threshold, so
+    these go through the chunk-parallel split-stream kernels. BASELINE config 4 shape at reduced size."""
+    imgs = [corpus.gradient_noise_rgba(1536, 1024, 500 + i) for i in range(3)]
+    files = [ref.stb_png(im.tobytes(), 1536, 1024, 4, f) for im, f in zip(imgs, (4, -1, 0))]
+    assert all(len(f) > 4 * 32768 for f in files)
+    res = ctx.decode_png_batch(files)
+    for f, im, (good, w, h, rgba) in zip(files, imgs, res):
+        rgood, _, _, rrgba = ref.decode_png(f)
+        assert good == rgood
+        if good:
+            assert rgba == rrgba == im.tobytes()
+    # raw inflate of stb zlib streams, incl. long-distance periodic data and a truncated stream
+    datas = [corpus.word_salad(900000, 3), corpus.periodic(700000, 4, 30011), bytes(500000)]
+    streams = [ref.stb_zlib(d)[2:-4] for d in datas]
+    streams.append(streams[0][: len(streams[0]) - 5000])
+    caps = [len(d) + len(s) + 64 for d, s in zip(datas + [datas[0]], streams)]
+    got = ctx.inflate_batch(streams, caps)
+    for s, c, (good, out) in zip(streams, caps, got):
+        rgood, rout = ref.inflate(s, c)
+        assert good == rgood and out == rout

@@ -31,6 +31,8 @@ def emu():
     L.emu_inflate.restype = C.c_uint32
     L.emu_png_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
     L.emu_png_decode.restype = C.c_uint32
+    L.emu_split_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+    L.emu_split_inflate.restype = C.c_uint32
     L.emu_crc32.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
     L.emu_crc32.restype = C.c_uint32
     return L
@@ -90,3 +92,31 @@ def test_png_fixture_small(emu, manifest, golden_dir):
         ib = C.create_string_buffer(data, len(data))
         assert emu.emu_png_decode(ib, len(data), ob, f["w"] * f["h"] * 4, 0) == 0
         assert sha(ob.raw[: f["w"] * f["h"] * 4]) == f["ref_sha256"], name
+
+
+def test_split_stream_kernel_source(emu):
+    """Split-stream path (transfer tables -> chain -> 16-bit cells -> resolve) on single fixed-Huffman
+    block streams, against zlib. Streams come from zlib's Z_FIXED with one block (small inputs)."""
+    import zlib
+    import numpy as np
+    from debigulator_b200 import corpus
+    rng = np.random.default_rng(7)
+    cases = []
+    img = corpus.gradient_noise_rgba(160, 120, 3)
+    cases.append(corpus.png_filter_rows(img, 4))                        # PNG-like residuals
+    cases.append(corpus.word_salad(70000, 5))                           # text, long distances
+    cases.append(corpus.periodic(120000, 2, 31000))                     # matches at the window limit
+    cases.append(bytes(rng.integers(0, 4, size=90000, dtype=np.uint8))) # low entropy, short distances
+    for k, data in enumerate(cases):
+        # one fixed block: compress with Z_FIXED and keep only inputs zlib emits as a single block
+        c = zlib.compressobj(9, zlib.DEFLATED, -15, 9, zlib.Z_FIXED)
+        z = c.compress(data) + c.flush()
+        if (z[0] & 7) != 3:
+            continue
+        cap = len(data) + 64
+        ib = C.create_string_buffer(z, len(z))
+        ob = C.create_string_buffer(cap + 64)
+        n = C.c_uint64(0)
+        st = emu.emu_split_inflate(ib, len(z), ob, cap, C.byref(n), (3 * k) % 16, k & 1)
+        assert st == 0, (k, st)
+        assert ob.raw[: n.value] == zlib.decompress(z, -15), k
