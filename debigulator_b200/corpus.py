@@ -6,10 +6,41 @@ ISIZE); PNGs are written here with a fixed-Huffman zlib stream (the shape
 stb_image_write produces: one IDAT, filter forced or adaptive), so the decoder
 under test never sees its own encoder.
 """
+import ctypes
+import os
 import struct
+import subprocess
 import zlib
 
 import numpy as np
+
+_TOOLS = None
+
+
+def _tools():
+    """Builds (gcc, once) and loads the corpus tools: the single-block fixed-Huffman encoder."""
+    global _TOOLS
+    if _TOOLS is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        src = os.path.join(here, "tools", "fixed_deflate.c")
+        so = os.path.join(here, "tools", "libcorpus_tools.so")
+        if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", src, "-o", so])
+        L = ctypes.CDLL(so)
+        L.dbg_fixed_deflate.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.dbg_fixed_deflate.restype = ctypes.c_size_t
+        _TOOLS = L
+    return _TOOLS
+
+
+def fixed_block_deflate(data):
+    """Raw DEFLATE of `data` as ONE final fixed-Huffman block (the shape stb_image_write emits)."""
+    data = bytes(data)
+    cap = len(data) + len(data) // 4 + 64
+    out = ctypes.create_string_buffer(cap)
+    n = _tools().dbg_fixed_deflate(data, len(data), out, cap)
+    assert n <= cap
+    return out.raw[:n]
 
 GZ_SEED_BASE = 0x64620000
 
@@ -175,12 +206,19 @@ def _chunk(tag, data):
     return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
 
 
-def write_png(img, filt=-1, level=6, strategy=zlib.Z_FIXED, idat_split=0, color_type=None, palette=None, extra_chunks=()):
-    """Minimal PNG writer: 8-bit, colour type from the channel count (4 -> 6, 3 -> 2, 1 -> 3)."""
+def write_png(img, filt=-1, level=6, strategy=zlib.Z_FIXED, idat_split=0, color_type=None, palette=None, extra_chunks=(),
+              single_block=False):
+    """Minimal PNG writer: 8-bit, colour type from the channel count (4 -> 6, 3 -> 2, 1 -> 3).
+    single_block=True writes the zlib stream the way stb_image_write does: header 78 5E, one final
+    fixed-Huffman block, Adler-32."""
     h, w, bpp = img.shape
     ct = color_type if color_type is not None else {4: 6, 3: 2, 1: 3}[bpp]
-    z = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
-    stream = z.compress(png_filter_rows(img, filt)) + z.flush()
+    rows = png_filter_rows(img, filt)
+    if single_block:
+        stream = b"\x78\x5e" + fixed_block_deflate(rows) + struct.pack(">I", zlib.adler32(rows) & 0xFFFFFFFF)
+    else:
+        z = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+        stream = z.compress(rows) + z.flush()
     out = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ct, 0, 0, 0))
     if ct == 3:
         out += _chunk(b"PLTE", bytes(palette))
@@ -197,4 +235,4 @@ def write_png(img, filt=-1, level=6, strategy=zlib.Z_FIXED, idat_split=0, color_
 def png_cfg3(i, w=1024, h=1024):
     """BASELINE config 3 image i: forced filter i%6-1 (-1 = adaptive). Returns (png bytes, rgba bytes)."""
     img = gradient_noise_rgba(w, h, 0x706E6700 + i)
-    return write_png(img, filt=i % 6 - 1), img.tobytes()
+    return write_png(img, filt=i % 6 - 1, single_block=True), img.tobytes()
