@@ -310,97 +310,136 @@ DBG_DEV uint32_t load_px(const uint8_t *p)
     return v;
 }
 
-// Reconstructs one image. `scan` holds h rows of (1 filter byte + w*BPP bytes);
-// it is overwritten in place with reconstructed bytes when BPP != 4 (those rows
-// are the "previous scanline" of the next band). RGBA pixels go to `out`.
+// Up-row pixel written by ANOTHER warp (the band above): read it from L2, not from a
+// possibly stale L1 line.
 template <int BPP>
-DBG_DEV void png_unfilter_warp(UnfilterSmem *sm, uint8_t *scan, uint32_t w, uint32_t h, uint8_t *out,
-                               const uint8_t *plte, uint32_t plte_size)
+DBG_DEV uint32_t load_px_l2(const uint8_t *p)
+{
+    if (BPP == 4) return simt::ldcg_u32((const uint32_t *)p);  // RGBA output rows are 4-byte aligned
+    uint32_t v = 0;
+    for (int k = 0; k < BPP; k++) v |= simt::ldcg_u8(p + k) << (8 * k);
+    return v;
+}
+
+enum { BAND_ROWS = 32, BAND_SLOTS = 64 };
+
+// Reconstructs band `band` (rows 32*band .. 32*band+31) of one image. `scan`
+// holds h rows of (1 filter byte + w*BPP bytes); it is overwritten in place
+// with reconstructed bytes when BPP != 4 (those rows are the "previous
+// scanline" of the next band). RGBA pixels go to `out`.
+//
+// Bands of one image are processed by different warps as a pipeline: band b
+// may work on tile k once band b-1 has finished tile k+1 (its last row is this
+// band's `b`/`c` input). Progress is handed over through `prog`, a ring of
+// BAND_SLOTS 64-bit words per image: slot (b % BAND_SLOTS) = (b+1) << 32 | tiles
+// done. Work items are issued in (image, band) order, so the band above is
+// always already running when a band waits for it.
+template <int BPP>
+DBG_DEV void png_unfilter_band(UnfilterSmem *sm, uint8_t *scan, uint32_t w, uint32_t h, uint8_t *out, const uint8_t *plte,
+                               uint32_t plte_size, uint32_t band, uint64_t *prog)
 {
     const uint32_t ln = (uint32_t)simt::lane();
     const uint64_t stride = (uint64_t)w * BPP + 1;
     const uint32_t mask = BPP == 4 ? 0xffffffffu : ((1u << (8 * (BPP & 3))) - 1);
     const uint32_t ntiles = (w + 31 + 31) / 32;
     uint32_t *out32 = (uint32_t *)out;
-    for (uint32_t r0 = 0; r0 < h; r0 += 32) {
-        const uint32_t r = r0 + ln;
-        const bool row_ok = r < h;
-        const uint32_t ft = row_ok ? scan[(uint64_t)r * stride] : 0;
-        uint32_t prev_out = 0, prev_b = 0;
-        for (uint32_t k = 0; k < ntiles; k++) {
-            // stage the skewed tile: row jj holds pixels [32k - jj, 32k - jj + 32)
-            for (uint32_t jj = 0; jj < 32; jj++) {
-                int64_t x = (int64_t)32 * k - jj + ln;
-                uint32_t v = 0;
-                if (r0 + jj < h && x >= 0 && x < (int64_t)w)
-                    v = load_px<BPP>(scan + (uint64_t)(r0 + jj) * stride + 1 + (uint64_t)x * BPP);
-                sm->tile[jj][ln] = v;
+    const uint32_t r0 = band * BAND_ROWS;
+    const uint32_t r = r0 + ln;
+    const bool row_ok = r < h;
+    const uint32_t ft = row_ok ? scan[(uint64_t)r * stride] : 0;
+    uint32_t prev_out = 0, prev_b = 0;
+    for (uint32_t k = 0; k < ntiles; k++) {
+        // stage the skewed tile: row jj holds pixels [32k - jj, 32k - jj + 32)
+        for (uint32_t jj = 0; jj < 32; jj++) {
+            int64_t x = (int64_t)32 * k - jj + ln;
+            uint32_t v = 0;
+            if (r0 + jj < h && x >= 0 && x < (int64_t)w)
+                v = load_px<BPP>(scan + (uint64_t)(r0 + jj) * stride + 1 + (uint64_t)x * BPP);
+            sm->tile[jj][ln] = v;
+        }
+        // the band above must have finished the tiles that hold pixels [32k, 32k+32) of its last row
+        uint32_t up_px = 0;
+        if (r0 > 0) {
+            if (prog) {
+                const uint64_t need = ((uint64_t)band << 32) | (k + 2 < ntiles ? k + 2 : ntiles);
+                const uint64_t *slot = prog + ((band - 1) & (BAND_SLOTS - 1));
+                while (simt::ld_acquire_u64(slot) < need) simt::backoff();
+                simt::syncwarp();
             }
-            // previous band's last row, pixels [32k, 32k+32), already reconstructed
-            uint32_t up_px = 0;
-            {
-                uint32_t x = 32 * k + ln;
-                if (r0 > 0 && x < w) {
-                    if (BPP == 4) up_px = out32[(uint64_t)(r0 - 1) * w + x];
-                    else up_px = load_px<BPP>(scan + (uint64_t)(r0 - 1) * stride + 1 + (uint64_t)x * BPP);
-                }
+            uint32_t x = 32 * k + ln;
+            if (x < w) {
+                if (BPP == 4) up_px = load_px_l2<4>((const uint8_t *)(out32 + (uint64_t)(r0 - 1) * w + x));
+                else up_px = load_px_l2<BPP>(scan + (uint64_t)(r0 - 1) * stride + 1 + (uint64_t)x * BPP);
             }
-            simt::syncwarp();
-            for (uint32_t i = 0; i < 32; i++) {
-                int64_t x = (int64_t)32 * k + i - ln;
-                uint32_t b_in = simt::shfl_up(prev_out, 1);
-                uint32_t b0 = simt::shfl(up_px, (int)i);
-                if (ln == 0) b_in = b0;
-                bool px_ok = row_ok && x >= 0 && x < (int64_t)w;
-                uint32_t cur = sm->tile[ln][i];
-                uint32_t a = x > 0 ? prev_out : 0;
-                uint32_t c = x > 0 ? prev_b : 0;
-                uint32_t b = b_in;
-                uint32_t o;
-                switch (ft) {  // undo_PNG_filter decode_png.c:497-541
-                    case 0: o = cur; break;
-                    case 1: o = swar_add4(cur, a); break;
-                    case 2: o = swar_add4(cur, b); break;
-                    case 3: o = swar_add4(cur, swar_havg4(a, b)); break;
-                    case 4: o = swar_add4(cur, paeth4(a, b, c)); break;
-                    default: o = 0; break;  // :528-540 unknown filter -> 0 in the no-assert build
-                }
-                o &= mask;
-                if (px_ok) {
-                    sm->tile[ln][i] = o;
-                    prev_out = o;
+        }
+        simt::syncwarp();
+        for (uint32_t i = 0; i < 32; i++) {
+            int64_t x = (int64_t)32 * k + i - ln;
+            uint32_t b_in = simt::shfl_up(prev_out, 1);
+            uint32_t b0 = simt::shfl(up_px, (int)i);
+            if (ln == 0) b_in = b0;
+            bool px_ok = row_ok && x >= 0 && x < (int64_t)w;
+            uint32_t cur = sm->tile[ln][i];
+            uint32_t a = x > 0 ? prev_out : 0;
+            uint32_t c = x > 0 ? prev_b : 0;
+            uint32_t b = b_in;
+            uint32_t o;
+            switch (ft) {  // undo_PNG_filter decode_png.c:497-541
+                case 0: o = cur; break;
+                case 1: o = swar_add4(cur, a); break;
+                case 2: o = swar_add4(cur, b); break;
+                case 3: o = swar_add4(cur, swar_havg4(a, b)); break;
+                case 4: o = swar_add4(cur, paeth4(a, b, c)); break;
+                default: o = 0; break;  // :528-540 unknown filter -> 0 in the no-assert build
+            }
+            o &= mask;
+            if (px_ok) {
+                sm->tile[ln][i] = o;
+                prev_out = o;
+            } else {
+                prev_out = 0;
+            }
+            prev_b = b_in;
+        }
+        simt::syncwarp();
+        for (uint32_t jj = 0; jj < 32; jj++) {
+            int64_t x = (int64_t)32 * k - jj + ln;
+            if (r0 + jj < h && x >= 0 && x < (int64_t)w) {
+                uint32_t v = sm->tile[jj][ln];
+                uint64_t pix = (uint64_t)(r0 + jj) * w + (uint64_t)x;
+                if (BPP == 4) {
+                    out32[pix] = v;
                 } else {
-                    prev_out = 0;
-                }
-                prev_b = b_in;
-            }
-            simt::syncwarp();
-            for (uint32_t jj = 0; jj < 32; jj++) {
-                int64_t x = (int64_t)32 * k - jj + ln;
-                if (r0 + jj < h && x >= 0 && x < (int64_t)w) {
-                    uint32_t v = sm->tile[jj][ln];
-                    uint64_t pix = (uint64_t)(r0 + jj) * w + (uint64_t)x;
-                    if (BPP == 4) {
-                        out32[pix] = v;
-                    } else {
-                        uint8_t *q = scan + (uint64_t)(r0 + jj) * stride + 1 + (uint64_t)x * BPP;
-                        for (int kk = 0; kk < BPP; kk++) q[kk] = (uint8_t)(v >> (8 * kk));
-                        if (BPP == 3) {
-                            out32[pix] = v | 0xff000000u;
-                        } else {  // palette, alpha forced to 255 (decode_png.c:1552-1560)
-                            uint32_t rgb = 0;
-                            if (v < plte_size) {
-                                const uint8_t *e = plte + 3 * v;
-                                rgb = (uint32_t)e[0] | ((uint32_t)e[1] << 8) | ((uint32_t)e[2] << 16);
-                            }
-                            out32[pix] = rgb | 0xff000000u;
+                    uint8_t *q = scan + (uint64_t)(r0 + jj) * stride + 1 + (uint64_t)x * BPP;
+                    for (int kk = 0; kk < BPP; kk++) q[kk] = (uint8_t)(v >> (8 * kk));
+                    if (BPP == 3) {
+                        out32[pix] = v | 0xff000000u;
+                    } else {  // palette, alpha forced to 255 (decode_png.c:1552-1560)
+                        uint32_t rgb = 0;
+                        if (v < plte_size) {
+                            const uint8_t *e = plte + 3 * v;
+                            rgb = (uint32_t)e[0] | ((uint32_t)e[1] << 8) | ((uint32_t)e[2] << 16);
                         }
+                        out32[pix] = rgb | 0xff000000u;
                     }
                 }
             }
-            simt::syncwarp();
+        }
+        simt::syncwarp();  // every lane's rows of this tile are written ...
+        if (prog && ln == 0) {  // ... and published to the band below
+            simt::threadfence();
+            simt::st_release_u64(prog + (band & (BAND_SLOTS - 1)), ((uint64_t)(band + 1) << 32) | (k + 1));
         }
     }
+}
+
+// Whole image by one warp (bands in order, no hand-off needed).
+template <int BPP>
+DBG_DEV void png_unfilter_warp(UnfilterSmem *sm, uint8_t *scan, uint32_t w, uint32_t h, uint8_t *out, const uint8_t *plte,
+                               uint32_t plte_size)
+{
+    for (uint32_t band = 0; band * BAND_ROWS < h; band++)
+        png_unfilter_band<BPP>(sm, scan, w, h, out, plte, plte_size, band, nullptr);
 }
 
 }  // namespace dbg

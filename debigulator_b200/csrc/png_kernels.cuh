@@ -13,6 +13,9 @@ struct PngLayout {
     uint64_t *s_off, *s_cap, *s_size;  // per image: filtered scanline buffer (offset into scan, capacity, inflated size)
     uint32_t *inf_status, *pre_status;
     PngInfo *info;
+    uint32_t *band_base;  // n + 1: first un-filter work item (32-row band) of every image
+    uint64_t *band_prog;  // BAND_SLOTS per image: band pipeline hand-off
+    uint32_t *band_counter;
     uint8_t *idat;  // compacted IDAT payloads
     uint8_t *scan;  // inflated, still filtered scanlines
     uint64_t idat_bytes, scan_bytes;
@@ -36,7 +39,10 @@ static inline uint64_t png_scan_bytes(uint64_t n, uint64_t total_rgba)
 {
     return png_align(total_rgba + total_rgba / 4 + 48 * n + 64, 256);
 }
-static inline uint64_t png_meta_bytes(uint64_t n) { return png_align(n * (5 * 8 + 2 * 4 + sizeof(PngInfo)) + 64, 256); }
+static inline uint64_t png_meta_bytes(uint64_t n)
+{
+    return png_align(n * (5 * 8 + 2 * 4 + sizeof(PngInfo) + 4 + 8 * BAND_SLOTS) + 256, 256);
+}
 static inline uint64_t png_scratch_bytes(uint64_t n, uint64_t total_in, uint64_t total_rgba)
 {
     return png_meta_bytes(n) + png_idat_bytes(n, total_in) + png_scan_bytes(n, total_rgba);
@@ -51,8 +57,11 @@ static inline PngLayout png_layout(uint8_t *base, uint64_t n, uint64_t total_in,
     l.s_cap = u + 3 * n;
     l.s_size = u + 4 * n;
     l.info = (PngInfo *)(u + 5 * n);
-    l.inf_status = (uint32_t *)(l.info + n);
+    l.band_prog = (uint64_t *)(l.info + n);
+    l.inf_status = (uint32_t *)(l.band_prog + n * BAND_SLOTS);
     l.pre_status = l.inf_status + n;
+    l.band_base = l.pre_status + n;
+    l.band_counter = l.band_base + n + 1;
     l.idat = base + png_meta_bytes(n);
     l.idat_bytes = png_idat_bytes(n, total_in);
     l.scan = l.idat + l.idat_bytes;
@@ -145,33 +154,86 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) png_scan_kernel(PngBatch b)
     }
 }
 
-// Pass D: one warp per image -- scanline reconstruction into RGBA.
+// Pass C2 (one CTA): un-filter work items. An image that decoded so far gets one item per 32-row
+// band, any other image a single item (which only reports its status).
+__global__ void __launch_bounds__(PLAN_THREADS) png_bands_kernel(PngBatch b)
+{
+    __shared__ uint32_t sh[PLAN_THREADS];
+    __shared__ uint32_t carry;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        carry = 0;
+        *b.lay.band_counter = 0;
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < b.n; base += PLAN_THREADS) {
+        uint32_t i = base + t, nb = 0;
+        if (i < b.n) {
+            bool ok = b.lay.pre_status[i] == ST_OK && b.lay.inf_status[i] == ST_OK;
+            nb = ok ? (b.lay.info[i].h + BAND_ROWS - 1) / BAND_ROWS : 1;
+            for (int k = 0; k < BAND_SLOTS; k += 8)  // reset this image's hand-off ring (8 words per step)
+                for (int j = 0; j < 8; j++) b.lay.band_prog[(uint64_t)i * BAND_SLOTS + k + j] = 0;
+        }
+        sh[t] = nb;
+        __syncthreads();
+        for (int d = 1; d < PLAN_THREADS; d <<= 1) {
+            uint32_t v = t >= d ? sh[t - d] : 0;
+            __syncthreads();
+            sh[t] += v;
+            __syncthreads();
+        }
+        if (i < b.n) b.lay.band_base[i] = carry + sh[t] - nb;
+        __syncthreads();
+        if (t == PLAN_THREADS - 1) carry += sh[t];
+        __syncthreads();
+    }
+    if (t == 0) b.lay.band_base[b.n] = carry;
+}
+
+// Pass D: scanline reconstruction into RGBA. Persistent warps take (image, band) items in order from a
+// global counter; the bands of one image form a pipeline (png_unfilter_band), so a single large image
+// keeps hundreds of warps busy instead of one.
 constexpr int UNF_WARPS = 4;
-__global__ void __launch_bounds__(UNF_WARPS * 32) png_unfilter_kernel(PngBatch b, uint8_t *out_base, const uint64_t *out_off,
+__global__ void __launch_bounds__(UNF_WARPS * 32, 6) png_unfilter_kernel(PngBatch b, uint8_t *out_base, const uint64_t *out_off,
                                                                      uint32_t *status)
 {
     __shared__ UnfilterSmem sm_all[UNF_WARPS];
     UnfilterSmem *sm = &sm_all[threadIdx.x >> 5];
     const uint32_t ln = (uint32_t)simt::lane();
-    const uint32_t warps = gridDim.x * UNF_WARPS;
-    for (uint32_t i = blockIdx.x * UNF_WARPS + (threadIdx.x >> 5); i < b.n; i += warps) {
+    const uint32_t total = b.lay.band_base[b.n];
+    for (;;) {
+        uint32_t t = 0;
+        if (ln == 0) t = atomicAdd(b.lay.band_counter, 1u);
+        t = simt::shfl(t, 0);
+        if (t >= total) break;
+        // image of work item t: last i with band_base[i] <= t
+        uint32_t lo = 0, hi = b.n;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (b.lay.band_base[mid] <= t) lo = mid;
+            else hi = mid;
+        }
+        const uint32_t i = lo, band = t - b.lay.band_base[i];
         uint32_t st = b.lay.pre_status[i];
         if (st == ST_OK) st = b.lay.inf_status[i];
         if (st == ST_OK) {
             PngInfo info = b.lay.info[i];
             uint8_t *scan = b.lay.scan + b.lay.s_off[i];
             uint64_t need = (uint64_t)info.h * ((uint64_t)info.w * info.bpp + 1);
-            if (scan[0] > 4) st = ST_PNG_FILTER;                      // decode_png.c:847-858
+            // the first filter byte is read through L2: band 0 of a palette / RGB image rewrites nothing
+            // at offset 0, but keep every band's verdict identical and cache-independent
+            if (simt::ldcg_u8(scan) > 4) st = ST_PNG_FILTER;          // decode_png.c:847-858
             else if (b.lay.s_size[i] < need) st = ST_PNG_SHORT;       // Q13: the reference reads stale memory here
             else {
                 uint8_t *out = out_base + out_off[i];
                 const uint8_t *file = b.in_base + b.in_off[i];
-                if (info.bpp == 4) png_unfilter_warp<4>(sm, scan, info.w, info.h, out, nullptr, 0);
-                else if (info.bpp == 3) png_unfilter_warp<3>(sm, scan, info.w, info.h, out, nullptr, 0);
-                else png_unfilter_warp<1>(sm, scan, info.w, info.h, out, file + info.plte_off, info.plte_size);
+                uint64_t *prog = b.lay.band_prog + (uint64_t)i * BAND_SLOTS;
+                if (info.bpp == 4) png_unfilter_band<4>(sm, scan, info.w, info.h, out, nullptr, 0, band, prog);
+                else if (info.bpp == 3) png_unfilter_band<3>(sm, scan, info.w, info.h, out, nullptr, 0, band, prog);
+                else png_unfilter_band<1>(sm, scan, info.w, info.h, out, file + info.plte_off, info.plte_size, band, prog);
             }
         }
-        if (ln == 0) status[i] = st;
+        if (ln == 0 && band == 0) status[i] = st;
         simt::syncwarp();
     }
 }
@@ -193,9 +255,12 @@ static inline int png_launch_scan(const PngBatch &b, int sm_count, cudaStream_t 
 static inline int png_launch_unfilter(const PngBatch &b, uint8_t *out_base, const uint64_t *out_off, uint32_t *status,
                                       int sm_count, cudaStream_t s)
 {
-    uint32_t ctas = (b.n + UNF_WARPS - 1) / UNF_WARPS;
-    uint32_t cap = (uint32_t)sm_count * 16;
-    png_unfilter_kernel<<<ctas < cap ? ctas : cap, UNF_WARPS * 32, 0, s>>>(b, out_base, out_off, status);
+    png_bands_kernel<<<1, PLAN_THREADS, 0, s>>>(b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    // persistent grid: every CTA must be resident (bands wait for the band above, which is always
+    // an earlier work item): 80 registers x 128 threads and 17 KB of shared memory allow 6 per SM
+    png_unfilter_kernel<<<(uint32_t)sm_count * 6, UNF_WARPS * 32, 0, s>>>(b, out_base, out_off, status);
     return (int)cudaGetLastError();
 }
 

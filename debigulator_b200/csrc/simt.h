@@ -46,6 +46,22 @@ DBG_DEV void cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes)
                  : "memory");
 }
+// cross-warp hand-off through global memory (band pipeline of the PNG un-filter)
+DBG_DEV uint64_t ld_acquire_u64(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+DBG_DEV void st_release_u64(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+DBG_DEV void threadfence() { __threadfence(); }
+DBG_DEV void backoff() { __nanosleep(64); }
+DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return __ldcg(p); }
+DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return __ldcg(p); }
+
 DBG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 DBG_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
@@ -146,6 +162,13 @@ DBG_DEV void cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
     else
         memset(smem_dst, 0, 16);
 }
+DBG_DEV uint64_t ld_acquire_u64(const uint64_t *p) { return *p; }
+DBG_DEV void st_release_u64(uint64_t *p, uint64_t v) { *p = v; }
+DBG_DEV void threadfence() {}
+DBG_DEV void backoff() {}
+DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return *p; }
+DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return *p; }
+
 DBG_DEV void cp_async_commit() {}
 DBG_DEV void cp_async_wait_all() {}
 
