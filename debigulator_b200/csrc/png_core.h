@@ -321,7 +321,7 @@ DBG_DEV uint32_t load_px_l2(const uint8_t *p)
     return v;
 }
 
-enum { BAND_ROWS = 32, BAND_SLOTS = 64 };
+enum { BAND_ROWS = 32, BAND_SLOTS = 128 };
 
 // Reconstructs band `band` (rows 32*band .. 32*band+31) of one image. `scan`
 // holds h rows of (1 filter byte + w*BPP bytes); it is overwritten in place
@@ -333,7 +333,10 @@ enum { BAND_ROWS = 32, BAND_SLOTS = 64 };
 // band's `b`/`c` input). Progress is handed over through `prog`, a ring of
 // BAND_SLOTS 64-bit words per image: slot (b % BAND_SLOTS) = (b+1) << 32 | tiles
 // done. Work items are issued in (image, band) order, so the band above is
-// always already running when a band waits for it.
+// always already running when a band waits for it. A slot is shared by bands b
+// and b + BAND_SLOTS; band b therefore starts only after band b - (BAND_SLOTS-1)
+// -- the last reader of the slot it is about to overwrite -- has finished, which
+// bounds the pipeline depth at BAND_SLOTS - 1 bands.
 template <int BPP>
 DBG_DEV void png_unfilter_band(UnfilterSmem *sm, uint8_t *scan, uint32_t w, uint32_t h, uint8_t *out, const uint8_t *plte,
                                uint32_t plte_size, uint32_t band, uint64_t *prog)
@@ -348,6 +351,13 @@ DBG_DEV void png_unfilter_band(UnfilterSmem *sm, uint8_t *scan, uint32_t w, uint
     const bool row_ok = r < h;
     const uint32_t ft = row_ok ? scan[(uint64_t)r * stride] : 0;
     uint32_t prev_out = 0, prev_b = 0;
+    if (prog && band >= BAND_SLOTS - 1) {
+        const uint32_t q = band - (BAND_SLOTS - 1);
+        const uint64_t done = ((uint64_t)(q + 1) << 32) | ntiles;
+        const uint64_t *slot = prog + (q & (BAND_SLOTS - 1));
+        while (simt::ld_acquire_u64(slot) < done) simt::backoff();
+        simt::syncwarp();
+    }
     for (uint32_t k = 0; k < ntiles; k++) {
         // stage the skewed tile: row jj holds pixels [32k - jj, 32k - jj + 32)
         for (uint32_t jj = 0; jj < 32; jj++) {
