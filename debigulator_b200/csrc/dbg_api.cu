@@ -400,16 +400,17 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
     // 1. container walk + CRC-32 + IDAT gather (one warp per image)
     dbg::PngBatch pb{d_in, d_in_off, d_in_size, d_out_cap, (uint32_t)n, lay};
     int rc = dbg::png_launch_scan(pb, ctx->sm_count, s);
-    ctx->launches += 2;
+    ctx->launches += 4;
     if (rc) CU((cudaError_t)rc);
     // 2. inflate the compacted zlib payloads into the filtered-scanline buffers
-    dbg::InflateBatch a{lay.idat, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
+    // z_off holds absolute addresses: a single-IDAT image is inflated straight from the file
+    dbg::InflateBatch a{nullptr, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
                         lay.pre_status, nullptr, nullptr, nullptr, (uint32_t)n};
     rc = launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
     if (rc) return rc;
     // 3. un-filter (+ palette / RGB expansion) straight into the caller's RGBA
     rc = dbg::png_launch_unfilter(pb, d_out, d_out_off, d_status, ctx->sm_count, s);
-    ctx->launches++;
+    ctx->launches += 2;
     if (rc) CU((cudaError_t)rc);
     return DBG_OK;
 }

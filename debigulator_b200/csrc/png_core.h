@@ -26,6 +26,10 @@
 #include "inflate_core.h"
 #include "simt.h"
 
+#ifdef DBG_SIMT_EMU
+static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+#endif
+
 namespace dbg {
 
 enum : uint32_t {
@@ -124,11 +128,13 @@ DBG_DEV uint32_t crc_slice(const CrcTables *T, uint32_t c, const uint8_t *p, uin
 // computed by the whole warp. `lane_k` must hold x^(8*CRC_SLICE*(31-lane)).
 // The region is cut into 8 KiB tiles counted from its END, so only the first
 // tile is partial and every lane's "bytes after my slice" count is a constant.
-DBG_DEV uint32_t crc32_warp(const CrcTables *T, uint32_t lane_k, const uint8_t *p, uint64_t n)
+// Raw CRC register after feeding p[0..n) to a register that starts at `init` (no final xor): the
+// building block for regions that are split over several warps.
+DBG_DEV uint32_t crc_state_warp(const CrcTables *T, uint32_t lane_k, const uint8_t *p, uint64_t n, uint32_t init)
 {
     const uint32_t ln = (uint32_t)simt::lane();
     uint32_t head = (uint32_t)(n % CRC_TILE);
-    uint32_t running = 0;
+    uint32_t running = init;
     bool first = true;
     uint64_t done = 0;
     while (done < n) {
@@ -139,7 +145,7 @@ DBG_DEV uint32_t crc32_warp(const CrcTables *T, uint32_t lane_k, const uint8_t *
         if (s1 > vstart) {
             uint32_t b0 = s0 > vstart ? s0 : vstart;
             bool has_first = (b0 == vstart);
-            if (has_first) c = first ? 0xffffffffu : running;
+            if (has_first) c = running;
             c = crc_slice(T, c, p + done + (b0 - vstart), s1 - b0);
             c = gf2_mulmod(lane_k, c);
         }
@@ -148,7 +154,61 @@ DBG_DEV uint32_t crc32_warp(const CrcTables *T, uint32_t lane_k, const uint8_t *
         done += tlen;
         first = false;
     }
-    return running ^ 0xffffffffu;
+    return running;
+}
+
+DBG_DEV uint32_t crc32_warp(const CrcTables *T, uint32_t lane_k, const uint8_t *p, uint64_t n)
+{
+    return crc_state_warp(T, lane_k, p, n, 0xffffffffu) ^ 0xffffffffu;
+}
+
+// Work that one warp per image would serialise (a 150 MB IDAT chunk) is handed to a second
+// kernel as 64 KiB segment tasks: CRC-32 segments (recombined in GF(2): the contribution of a
+// segment is its raw register times x^(8 * bytes after it), XOR-accumulated per chunk) and
+// IDAT copy segments.
+constexpr uint32_t SCAN_SEG = 65536;
+constexpr uint32_t SCAN_NONE = 0xffffffffu;
+struct ScanTask {
+    const uint8_t *src;
+    uint8_t *dst;          // nullptr: CRC only
+    uint32_t len;
+    uint32_t bytes_after;  // bytes of the CRC region after this segment
+    uint32_t big;          // accumulator index, SCAN_NONE: copy only
+    uint32_t first;        // 1: the register starts at 0xFFFFFFFF
+};
+struct BigChunk {
+    uint32_t img, expected, acc, armed;  // armed: `expected` is valid (the walk got as far as the stored CRC)
+};
+struct ScanQueues {
+    ScanTask *tasks;
+    uint32_t *ntasks;
+    uint32_t task_cap;
+    BigChunk *big;
+    uint32_t *nbig;
+    uint32_t big_cap;
+};
+
+// Enqueues segment tasks for region p[0..n) (uniform call). Returns false when the queue is full.
+DBG_DEV bool scan_enqueue(ScanQueues *q, const uint8_t *p, uint64_t n, uint8_t *dst, uint32_t big)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint32_t nseg = (uint32_t)((n + SCAN_SEG - 1) / SCAN_SEG);
+    uint32_t base = 0;
+    if (ln == 0) base = atomicAdd(q->ntasks, nseg);
+    base = simt::shfl(base, 0);
+    if (base + nseg > q->task_cap) return false;  // the slots stay unused (len 0)
+    for (uint32_t k = ln; k < nseg; k += 32) {
+        ScanTask t;
+        uint64_t o = (uint64_t)k * SCAN_SEG;
+        t.src = p + o;
+        t.dst = dst ? dst + o : nullptr;
+        t.len = (uint32_t)(n - o < SCAN_SEG ? n - o : SCAN_SEG);
+        t.bytes_after = (uint32_t)(n - o - t.len);
+        t.big = big;
+        t.first = k == 0;
+        q->tasks[base + k] = t;
+    }
+    return true;
 }
 
 // --------------------------------------------------------------- chunk walk ----
@@ -165,11 +225,17 @@ DBG_DEV bool tag_is(const uint8_t *p, char a, char b, char c, char d)
 // `info`, and has copied the concatenated IDAT payload (minus the 2-byte zlib
 // header) to `zdst`; *z_size is the deflate size handed to inflate
 // (payload - 4, decode_png.c:816).
+// With a single IDAT chunk (every stb-written PNG) nothing is copied: *z_ptr points into the file.
+// `q` (may be null) receives the CRC / copy work of chunks larger than SCAN_SEG.
 DBG_DEV uint32_t png_scan_warp(const CrcTables *T, uint32_t lane_k, const uint8_t *file, uint64_t size,
-                               uint64_t rgba_size, uint8_t *zdst, uint64_t zcap, PngInfo *info, uint64_t *z_size)
+                               uint64_t rgba_size, uint8_t *zdst, uint64_t zcap, PngInfo *info, uint64_t *z_size,
+                               const uint8_t **z_ptr, ScanQueues *q, uint32_t img)
 {
     const uint32_t ln = (uint32_t)simt::lane();
     *z_size = 0;
+    *z_ptr = zdst;
+    uint64_t first_off = 0, first_len = 0;  // the first IDAT payload, not copied until a second one shows up
+    uint32_t n_idat = 0;
     if (size < 8 || size >= (1ull << 32)) return ST_CONTAINER;
     if (!(file[1] == 'P' && file[2] == 'N' && file[3] == 'G')) return ST_CONTAINER;  // decode_png.c:730-753
     uint64_t pos = 8;
@@ -193,7 +259,25 @@ DBG_DEV uint32_t png_scan_warp(const CrcTables *T, uint32_t lane_k, const uint8_
         }
         if (length >= left) return ST_CONTAINER;            // decode_png.c:886
         if (pos + length + 4 > size) return ST_CONTAINER;   // real bounds (Q11 makes `left` optimistic)
-        uint32_t crc = crc32_warp(T, lane_k, type, 4 + length);  // decode_png.c:862-874
+        uint32_t crc = 0, big = SCAN_NONE;                      // decode_png.c:862-874
+        if (q && 4 + length > SCAN_SEG) {
+            uint32_t bi = 0;
+            if (ln == 0) bi = atomicAdd(q->nbig, 1u);
+            bi = simt::shfl(bi, 0);
+            if (bi < q->big_cap) {
+                if (ln == 0) {
+                    BigChunk bc;
+                    bc.img = img;
+                    bc.expected = 0;
+                    bc.acc = 0;
+                    bc.armed = 0;
+                    q->big[bi] = bc;
+                }
+                simt::syncwarp();
+                if (scan_enqueue(q, type, 4 + length, nullptr, bi)) big = bi;
+            }
+        }
+        if (big == SCAN_NONE) crc = crc32_warp(T, lane_k, type, 4 + length);
         if (tag_is(type, 'P', 'L', 'T', 'E')) {             // decode_png.c:900-950
             if (!found_ihdr) return ST_CONTAINER;
             if (length % 3 != 0) return ST_CONTAINER;
@@ -232,9 +316,19 @@ DBG_DEV uint32_t png_scan_warp(const CrcTables *T, uint32_t lane_k, const uint8_
                 if ((flg >> 5) & 1) return ST_CONTAINER;                     // FDICT :1262-1265
             }
             if (zlen + data_len > zcap) return ST_CONTAINER;
-            const uint8_t *src = file + pos;
-            uint8_t *dst = zdst + zlen;
-            for (uint64_t i = ln; i < data_len; i += 32) dst[i] = src[i];    // :1285-1291
+            n_idat++;
+            if (n_idat == 1) {
+                first_off = pos;
+                first_len = data_len;
+            } else {                                                         // :1285-1291
+                for (int pass = n_idat == 2 ? 0 : 1; pass < 2; pass++) {     // second IDAT: the first one moves too
+                    const uint8_t *src = pass == 0 ? file + first_off : file + pos;
+                    uint8_t *dst = pass == 0 ? zdst : zdst + zlen;
+                    uint64_t cl = pass == 0 ? first_len : data_len;
+                    if (!(q && cl > SCAN_SEG && scan_enqueue(q, src, cl, dst, SCAN_NONE)))
+                        for (uint64_t i = ln; i < cl; i += 32) dst[i] = src[i];
+                }
+            }
             zlen += data_len;
             pos += data_len;
             left -= data_len;
@@ -251,7 +345,12 @@ DBG_DEV uint32_t png_scan_warp(const CrcTables *T, uint32_t lane_k, const uint8_
         uint32_t stored = be32(file + pos);
         pos += 4;
         left -= 4;
-        if (stored != crc) return ST_PNG_CRC;               // :1341-1348
+        if (big != SCAN_NONE) {                             // verified once the segment tasks have run
+            if (ln == 0) {
+                q->big[big].expected = stored;
+                q->big[big].armed = 1;
+            }
+        } else if (stored != crc) return ST_PNG_CRC;        // :1341-1348
     }
     if (!ran_inflate) return ST_CONTAINER;                  // :1357
     if (zlen_at_run < 4 + 5) {
@@ -262,6 +361,7 @@ DBG_DEV uint32_t png_scan_warp(const CrcTables *T, uint32_t lane_k, const uint8_
     info->w = w;
     info->h = h;
     info->bpp = ct == 6 ? 4 : ct == 2 ? 3 : 1;              // :1401-1414
+    if (n_idat == 1) *z_ptr = file + first_off;
     *z_size = zlen_at_run - 4;
     return ST_OK;
 }

@@ -16,6 +16,8 @@ struct PngLayout {
     uint32_t *band_base;  // n + 1: first un-filter work item (32-row band) of every image
     uint64_t *band_prog;  // BAND_SLOTS per image: band pipeline hand-off
     uint32_t *band_counter;
+    ScanQueues queues;     // deferred CRC / copy segments of large chunks
+    uint32_t *task_counter;
     uint8_t *idat;  // compacted IDAT payloads
     uint8_t *scan;  // inflated, still filtered scanlines
     uint64_t idat_bytes, scan_bytes;
@@ -43,9 +45,17 @@ static inline uint64_t png_meta_bytes(uint64_t n)
 {
     return png_align(n * (5 * 8 + 2 * 4 + sizeof(PngInfo) + 4 + 8 * BAND_SLOTS) + 256, 256);
 }
+// at most total_in / SCAN_SEG chunks exceed SCAN_SEG, each cut into ceil(len / SCAN_SEG) segments,
+// CRC and copy counted separately
+static inline uint64_t png_task_cap(uint64_t n, uint64_t total_in) { return 4 * (total_in / SCAN_SEG) + 64; }
+static inline uint64_t png_big_cap(uint64_t n, uint64_t total_in) { return total_in / SCAN_SEG + 16; }
+static inline uint64_t png_queue_bytes(uint64_t n, uint64_t total_in)
+{
+    return png_align(png_task_cap(n, total_in) * sizeof(ScanTask) + png_big_cap(n, total_in) * sizeof(BigChunk) + 256, 256);
+}
 static inline uint64_t png_scratch_bytes(uint64_t n, uint64_t total_in, uint64_t total_rgba)
 {
-    return png_meta_bytes(n) + png_idat_bytes(n, total_in) + png_scan_bytes(n, total_rgba);
+    return png_meta_bytes(n) + png_queue_bytes(n, total_in) + png_idat_bytes(n, total_in) + png_scan_bytes(n, total_rgba);
 }
 static inline PngLayout png_layout(uint8_t *base, uint64_t n, uint64_t total_in, uint64_t total_rgba)
 {
@@ -62,7 +72,15 @@ static inline PngLayout png_layout(uint8_t *base, uint64_t n, uint64_t total_in,
     l.pre_status = l.inf_status + n;
     l.band_base = l.pre_status + n;
     l.band_counter = l.band_base + n + 1;
-    l.idat = base + png_meta_bytes(n);
+    uint8_t *qb = base + png_meta_bytes(n);
+    l.queues.tasks = (ScanTask *)(qb + 256);
+    l.queues.task_cap = (uint32_t)png_task_cap(n, total_in);
+    l.queues.big = (BigChunk *)(l.queues.tasks + l.queues.task_cap);
+    l.queues.big_cap = (uint32_t)png_big_cap(n, total_in);
+    l.queues.ntasks = (uint32_t *)qb;
+    l.queues.nbig = l.queues.ntasks + 1;
+    l.task_counter = l.queues.ntasks + 2;
+    l.idat = qb + png_queue_bytes(n, total_in);
     l.idat_bytes = png_idat_bytes(n, total_in);
     l.scan = l.idat + l.idat_bytes;
     l.scan_bytes = png_scan_bytes(n, total_rgba);
@@ -82,6 +100,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) png_plan_kernel(PngBatch b)
     if (t == 0) {
         carry_z = 0;
         carry_s = 0;
+        *b.lay.queues.ntasks = 0;
+        *b.lay.queues.nbig = 0;
+        *b.lay.task_counter = 0;
     }
     __syncthreads();
     for (uint32_t base = 0; base < b.n; base += PLAN_THREADS) {
@@ -111,7 +132,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) png_plan_kernel(PngBatch b)
             __syncthreads();
         }
         if (i < b.n) {
-            b.lay.z_off[i] = carry_z + sh_z[t] - zc;
+            b.lay.z_off[i] = (uint64_t)(uintptr_t)(b.lay.idat + (carry_z + sh_z[t] - zc));  // absolute address
             b.lay.s_off[i] = carry_s + sh_s[t] - sc;
             b.lay.s_cap[i] = est;  // inflate's recipient_size, decode_png.c:803-804
             b.lay.z_size[i] = 0;
@@ -138,20 +159,70 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) png_scan_kernel(PngBatch b)
     const uint32_t lane_k = gf2_xpow_bytes(CRC_SLICE * (31 - ln));
     const uint32_t warps = gridDim.x * SCAN_WARPS;
     for (uint32_t i = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5); i < b.n; i += warps) {
-        uint64_t zoff = b.lay.z_off[i];
+        uint8_t *zdst = (uint8_t *)(uintptr_t)b.lay.z_off[i];
         uint64_t zcap = png_align(b.in_size[i] + 16, 16);
         uint64_t zs = 0;
+        const uint8_t *zp = zdst;
         PngInfo info;
         info.w = info.h = info.bpp = 0;
-        uint32_t st = png_scan_warp(&tables, lane_k, b.in_base + b.in_off[i], b.in_size[i], b.rgba_size[i],
-                                    b.lay.idat + zoff, zcap, &info, &zs);
+        ScanQueues q = b.lay.queues;
+        uint32_t st = png_scan_warp(&tables, lane_k, b.in_base + b.in_off[i], b.in_size[i], b.rgba_size[i], zdst, zcap, &info,
+                                    &zs, &zp, &q, i);
         if (ln == 0) {
+            b.lay.z_off[i] = (uint64_t)(uintptr_t)zp;
             b.lay.z_size[i] = zs;
             b.lay.pre_status[i] = st;
             b.lay.info[i] = info;
         }
         simt::syncwarp();
     }
+}
+
+// Pass B2: the deferred segments (persistent warps, queue filled by pass B).
+__global__ void __launch_bounds__(SCAN_WARPS * 32) png_tasks_kernel(PngBatch b)
+{
+    __shared__ CrcTables tables;
+    crc_tables_init(&tables, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint32_t lane_k = gf2_xpow_bytes(CRC_SLICE * (31 - ln));
+    uint32_t total = *b.lay.queues.ntasks;
+    if (total > b.lay.queues.task_cap) total = b.lay.queues.task_cap;
+    for (;;) {
+        uint32_t t = 0;
+        if (ln == 0) t = atomicAdd(b.lay.task_counter, 1u);
+        t = simt::shfl(t, 0);
+        if (t >= total) break;
+        const ScanTask k = b.lay.queues.tasks[t];
+        if (k.len == 0) continue;
+        if (k.big != SCAN_NONE) {
+            uint32_t st = crc_state_warp(&tables, lane_k, k.src, k.len, k.first ? 0xffffffffu : 0u);
+            st = gf2_mulmod(gf2_xpow_bytes(k.bytes_after), st);
+            if (ln == 0) atomicXor(&b.lay.queues.big[k.big].acc, st);
+        }
+        if (k.dst) {
+            if ((((uintptr_t)k.src | (uintptr_t)k.dst) & 15) == 0) {
+                const uint4 *s4 = (const uint4 *)k.src;
+                uint4 *d4 = (uint4 *)k.dst;
+                for (uint32_t i = ln; i < k.len / 16; i += 32) d4[i] = s4[i];
+                for (uint32_t i = (k.len & ~15u) + ln; i < k.len; i += 32) k.dst[i] = k.src[i];
+            } else {
+                for (uint32_t i = ln; i < k.len; i += 32) k.dst[i] = k.src[i];
+            }
+        }
+        simt::syncwarp();
+    }
+}
+
+// Pass B3: compare the recombined CRCs of the large chunks with the stored ones (decode_png.c:1341-1348).
+__global__ void png_verify_kernel(PngBatch b)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nbig = *b.lay.queues.nbig;
+    if (nbig > b.lay.queues.big_cap) nbig = b.lay.queues.big_cap;
+    if (i >= nbig) return;
+    const BigChunk c = b.lay.queues.big[i];
+    if (c.armed && (c.acc ^ 0xffffffffu) != c.expected) atomicMax(&b.lay.pre_status[c.img], (uint32_t)ST_PNG_CRC);
 }
 
 // Pass C2 (one CTA): un-filter work items. An image that decoded so far gets one item per 32-row
@@ -249,6 +320,11 @@ static inline int png_launch_scan(const PngBatch &b, int sm_count, cudaStream_t 
     uint32_t ctas = (b.n + SCAN_WARPS - 1) / SCAN_WARPS;
     uint32_t cap = (uint32_t)sm_count * 8;
     png_scan_kernel<<<ctas < cap ? ctas : cap, SCAN_WARPS * 32, 0, s>>>(b);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    png_tasks_kernel<<<(uint32_t)sm_count * 4, SCAN_WARPS * 32, 0, s>>>(b);
+    uint32_t big_cap = b.lay.queues.big_cap;
+    png_verify_kernel<<<(big_cap + 255) / 256, 256, 0, s>>>(b);
     return (int)cudaGetLastError();
 }
 

@@ -247,10 +247,12 @@ static void png_body(void *p)
     dbg::PngInfo info;
     info.w = info.h = info.bpp = 0;
     uint64_t zs = 0;
-    uint32_t st = dbg::png_scan_warp(a->tables, lane_k, a->file, a->size, a->rgba_size, a->zbuf, a->zcap, &info, &zs);
+    const uint8_t *zp = a->zbuf;
+    uint32_t st = dbg::png_scan_warp(a->tables, lane_k, a->file, a->size, a->rgba_size, a->zbuf, a->zcap, &info, &zs, &zp,
+                                     nullptr, 0);
     if (st == dbg::ST_OK) {
         uint64_t est = (uint64_t)info.w * info.h * 4 + info.h + 1, ssize = 0;
-        st = dbg::inflate_warp(a->ism, a->zbuf, zs, a->scan, est, &ssize);
+        st = dbg::inflate_warp(a->ism, zp, zs, a->scan, est, &ssize);
         if (st == dbg::ST_OK) {
             uint64_t need = (uint64_t)info.h * ((uint64_t)info.w * info.bpp + 1);
             if (a->scan[0] > 4) st = dbg::ST_PNG_FILTER;
