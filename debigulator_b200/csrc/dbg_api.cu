@@ -295,8 +295,9 @@ static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, c
     dbg::split_transfer_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b, T);
     dbg::split_chain_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);
     dbg::split_decode_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b, T);
-    dbg::split_resolve_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(b);
-    ctx->launches += 5;
+    dbg::split_resolve_tails_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(b);
+    dbg::split_resolve_body_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(b, T);
+    ctx->launches += 6;
     CU(cudaGetLastError());
     *skip_out = b.split_flag;
     return DBG_OK;

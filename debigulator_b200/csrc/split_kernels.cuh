@@ -146,9 +146,16 @@ __global__ void __launch_bounds__(SPLIT_WARPS_PER_CTA * 32) split_decode_kernel(
     }
 }
 
-// Cells -> bytes, chunk after chunk: one CTA per split stream.
+// Cells -> bytes. A marker in chunk c points into the 32 KiB of output that precede the chunk,
+// i.e. into the TAIL (last 32 KiB) of the chunks before it. Only the tails therefore form a serial
+// chain; they are resolved chunk after chunk by one CTA per stream (32 cells per thread, the next
+// chunk's cells are already in flight while the current one is resolved). Everything else -- the
+// body of every chunk -- is then resolved by all CTAs at once against the finished tails.
 constexpr int RESOLVE_THREADS = 1024;
-__global__ void __launch_bounds__(RESOLVE_THREADS) split_resolve_kernel(SplitBatch b)
+constexpr uint32_t TAIL_BYTES = 32768;
+constexpr int TAIL_PER_THREAD = TAIL_BYTES / RESOLVE_THREADS;
+
+__global__ void __launch_bounds__(RESOLVE_THREADS) split_resolve_tails_kernel(SplitBatch b)
 {
     const uint32_t s = blockIdx.x;
     if (!b.split_flag[s] || b.status[s] != ST_OK) {
@@ -158,15 +165,58 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) split_resolve_kernel(SplitBat
     const uint32_t nch = split_nchunks(b.in_size[s]), base = b.chunk_base[s];
     uint8_t *out = b.out_base + b.out_off[s];
     const uint16_t *cells = b.cells + b.cell_base[s];
+    uint32_t v[TAIL_PER_THREAD / 2], nv[TAIL_PER_THREAD / 2];  // two 16-bit cells per register
+    uint64_t o = 0, t0 = 0;
+    uint32_t tl = 0;
+    auto fetch = [&](uint32_t c, uint32_t *dst, uint64_t &co, uint64_t &cs, uint32_t &cl) {
+        co = b.c_out_off[base + c];
+        const uint32_t len = b.c_out_len[base + c];
+        cl = len < TAIL_BYTES ? len : TAIL_BYTES;
+        cs = co + len - cl;
+#pragma unroll
+        for (int k = 0; k < TAIL_PER_THREAD / 2; k++) {
+            uint32_t i0 = threadIdx.x + (2 * k) * RESOLVE_THREADS, i1 = i0 + RESOLVE_THREADS;
+            uint32_t lo = i0 < cl ? cells[cs + i0] : 0, hi = i1 < cl ? cells[cs + i1] : 0;
+            dst[k] = lo | (hi << 16);
+        }
+    };
+    fetch(0, v, o, t0, tl);
     for (uint32_t c = 0; c < nch; c++) {
-        const uint32_t t = base + c;
-        const uint64_t o = b.c_out_off[t];
-        const uint32_t len = b.c_out_len[t];
-        for (uint32_t i = threadIdx.x; i < len; i += RESOLVE_THREADS) {
-            uint32_t v = cells[o + i];
-            out[o + i] = v < 256 ? (uint8_t)v : out[o + v - 33024];  // marker: 256 + 32768 + (negative source index)
+        uint64_t no = 0, nt0 = 0;
+        uint32_t ntl = 0;
+        if (c + 1 < nch) fetch(c + 1, nv, no, nt0, ntl);
+#pragma unroll
+        for (int k = 0; k < TAIL_PER_THREAD; k++) {
+            uint32_t i = threadIdx.x + k * RESOLVE_THREADS;
+            if (i < tl) {
+                uint32_t x = (v[k >> 1] >> (16 * (k & 1))) & 0xffff;
+                out[t0 + i] = x < 256 ? (uint8_t)x : out[o + x - 33024];  // marker: 256 + 32768 + (negative source index)
+            }
         }
         __syncthreads();  // the next chunk's markers may point at these bytes
+#pragma unroll
+        for (int k = 0; k < TAIL_PER_THREAD / 2; k++) v[k] = nv[k];
+        o = no;
+        t0 = nt0;
+        tl = ntl;
+    }
+}
+
+__global__ void __launch_bounds__(256) split_resolve_body_kernel(SplitBatch b, uint32_t total_chunks)
+{
+    for (uint32_t t = blockIdx.x; t < total_chunks; t += gridDim.x) {
+        const uint32_t s = b.chunk_stream[t];
+        if (b.status[s] != ST_OK) continue;
+        const uint32_t len = b.c_out_len[t];
+        if (len <= TAIL_BYTES) continue;
+        const uint64_t o = b.c_out_off[t];
+        const uint32_t body = len - TAIL_BYTES;
+        uint8_t *out = b.out_base + b.out_off[s];
+        const uint16_t *cells = b.cells + b.cell_base[s];
+        for (uint32_t i = threadIdx.x; i < body; i += 256) {
+            uint32_t x = cells[o + i];
+            out[o + i] = x < 256 ? (uint8_t)x : out[o + x - 33024];
+        }
     }
 }
 
