@@ -62,3 +62,19 @@ def test_sass_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_corpus_single_block_encoder_roundtrip():
+    """The corpus tool that writes stb-shaped streams (one final fixed-Huffman block) is a valid DEFLATE encoder."""
+    import zlib
+    from debigulator_b200 import corpus
+    for seed, n in ((1, 0), (2, 1), (3, 70000), (4, 300000)):
+        data = corpus.word_salad(n, seed) if n else b""
+        z = corpus.fixed_block_deflate(data)
+        assert (z[0] & 7) == 3                      # BFINAL=1, BTYPE=01
+        assert zlib.decompress(z, -15) == data
+    img = corpus.gradient_noise_rgba(64, 48, 9)
+    png = corpus.write_png(img, 4, single_block=True)
+    from PIL import Image
+    import io
+    assert Image.open(io.BytesIO(png)).convert("RGBA").tobytes() == img.tobytes()
