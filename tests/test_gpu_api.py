@@ -207,3 +207,25 @@ def test_failed_items_do_not_poison_batch(ctx):
     assert [r[0] for r in res] == [1, 0, 1, res[3][0], 0, 1]
     for k in (0, 2, 5):
         assert res[k][1] == good[1]
+
+
+def test_example_mains_print_the_readme_golden(golden_dir, tmp_path):
+    """examples/hellopng.c and hellogz.c (the roles of the reference's stale examples) build with gcc against
+    include/*.h and print the reference README's golden for gimp_test.png (README.md:41-47)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "debigulator_b200")
+    outs = {}
+    for name in ("hellopng", "hellogz"):
+        exe = str(tmp_path / name)
+        subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", name + ".c"),
+                               "-L" + lib, "-ldebigulator_b200", "-Wl,-rpath," + lib, "-o", exe])
+        arg = os.path.join(golden_dir, "gimp_test.png" if name == "hellopng" else "gzipsample.gz")
+        outs[name] = subprocess.run([exe, arg], capture_output=True, text=True, timeout=300)
+        assert outs[name].returncode == 0, outs[name].stdout + outs[name].stderr
+    p = outs["hellopng"].stdout
+    for line in ("bytes read from raw file: 30522", "result was: SUCCESS", "rgba values in image: 4194304",
+                 "pixels in image (info from image header): 1048576", "image width: 1024", "image height: 1024",
+                 "average pixel: [248,249,251,158]"):
+        assert line in p, p
+    assert "decompressed bytes: 561872" in outs["hellogz"].stdout
