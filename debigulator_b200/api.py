@@ -11,7 +11,7 @@ _lib = None
 STATUS_NAMES = {
     0: "ok", 1: "cap_lt_input", 2: "input_too_small", 3: "too_large", 4: "stored_len", 5: "bad_table",
     6: "bad_code", 7: "bad_symbol", 8: "bad_distance", 9: "out_overflow", 10: "truncated", 11: "bad_repeat",
-    12: "container", 13: "crc", 14: "filter", 15: "short_stream",
+    12: "container", 13: "crc", 14: "filter", 15: "short_stream", 16: "checksum",
 }
 KIND_INFLATE, KIND_GZ, KIND_PNG = 0, 1, 2
 
@@ -47,6 +47,8 @@ def load_library():
     L.dbg_ctx_device.restype = i32
     L.dbg_kernel_launches.argtypes = [vp]
     L.dbg_kernel_launches.restype = u64
+    L.dbg_set_verify.argtypes = [vp, i32]
+    L.dbg_set_verify.restype = i32
     L.dbg_profile_enable.argtypes = [vp, i32]
     L.dbg_profile_enable.restype = i32
     L.dbg_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
@@ -122,6 +124,10 @@ class Context:
     @property
     def kernel_launches(self):
         return int(self.L.dbg_kernel_launches(self.h))
+
+    def set_verify(self, on=True):
+        """Opt-in gzip CRC32 / ISIZE verification (dbg_set_verify)."""
+        self._check(self.L.dbg_set_verify(self.h, 1 if on else 0), "dbg_set_verify")
 
     def profile_enable(self, on=True):
         self._check(self.L.dbg_profile_enable(self.h, 1 if on else 0), "dbg_profile_enable")

@@ -72,6 +72,7 @@ struct dbg_ctx {
     Buf d_png_scratch;             // compacted IDAT + filtered scanlines
     Buf d_split, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
     uint32_t split_max_streams = 1024;  // batches with fewer streams may use the split-stream path
+    bool verify = false;                // opt-in: check gzip CRC32 / ISIZE trailers
     // host-API staging
     Buf d_in, d_out, d_desc;       // arenas + descriptor tables
     Buf h_in, h_out, h_desc;       // pinned mirrors
@@ -171,6 +172,13 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
     if (ctx->wave_ready) cudaEventDestroy(ctx->wave_ready);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int dbg_set_verify(dbg_ctx *ctx, int on)
+{
+    if (!ctx) return DBG_ERR_ARG;
+    ctx->verify = on != 0;
+    return DBG_OK;
 }
 
 extern "C" int dbg_profile_enable(dbg_ctx *ctx, int on)
@@ -330,7 +338,14 @@ static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t
         ctx->launches++;
         CU(cudaGetLastError());
         dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, d_order, nullptr, (uint32_t)n};
-        return launch_inflate(ctx, a, counter, s);
+        int rc = launch_inflate(ctx, a, counter, s);
+        if (rc || !ctx->verify) return rc;
+        uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
+        dbg::gz_verify_kernel<<<ctas, dbg::SCAN_WARPS * 32, 0, s>>>(d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_size, d_status,
+                                                                    (uint32_t)n);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        return DBG_OK;
     }
     dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
     return launch_inflate(ctx, a, counter, s);

@@ -296,7 +296,7 @@ DBG_DEV_NOINLINE uint32_t slow_decode(uint32_t bits, int root, uint32_t maxlen, 
 // stream) needs them, so the global-load latency overlaps the decode of the
 // following symbols instead of stalling the warp.
 struct PendingStore {
-    uint8_t *ptr;
+    uint8_t *ptr;   // byte sink: destination byte; 16-bit sink: destination cell
     uint32_t val;
     bool on;
 };
@@ -304,6 +304,11 @@ struct PendingStore {
 DBG_DEV void flush_pending(PendingStore &pd)
 {
     if (pd.on) *pd.ptr = (uint8_t)pd.val;
+    pd.on = false;
+}
+DBG_DEV void flush_pending16(PendingStore &pd)
+{
+    if (pd.on) *reinterpret_cast<uint16_t *>(pd.ptr) = (uint16_t)pd.val;
     pd.on = false;
 }
 
@@ -461,7 +466,18 @@ DBG_DEV uint32_t emit_match(Sink &k, uint32_t len, uint32_t dist)
         copy_match(k.out, k.pos, len, dist, k.pd);
     } else {
         if (dist > 32768 || dist > k.abs_base + k.pos) return ST_BAD_DISTANCE;
-        copy_match_u16(k.out16, k.pos, len, dist);
+        flush_pending16(k.pd);
+        if ((len <= 32) & (dist >= len)) {
+            // same deferred load/store pair as the byte sink; a source before the chunk's own output is a marker
+            simt::syncwarp();
+            const uint32_t ln = (uint32_t)simt::lane();
+            const int32_t si = (int32_t)k.pos - (int32_t)dist + (int32_t)ln;
+            k.pd.on = ln < len;
+            if (k.pd.on) k.pd.val = si < 0 ? (uint32_t)(256 + 32768 + si) : k.out16[si];
+            k.pd.ptr = reinterpret_cast<uint8_t *>(k.out16 + k.pos + ln);
+        } else {
+            copy_match_u16(k.out16, k.pos, len, dist);
+        }
     }
     k.pos += len;
     return ST_OK;
@@ -895,6 +911,7 @@ DBG_DEV ChunkResult decode_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in
     k.pd.on = false;
     uint32_t why = END_EOB;
     uint32_t st = decode_symbols<SINK>(w, sm, bt, k, why);
+    if (SINK == SINK_U16) flush_pending16(k.pd);
     r.exit_bits = w.abs_bits() - off;
     r.out_bytes = k.pos;
     if (st) r.flag = CH_ERR + st;

@@ -309,6 +309,33 @@ __global__ void __launch_bounds__(UNF_WARPS * 32, 6) png_unfilter_kernel(PngBatc
     }
 }
 
+// Opt-in integrity check for gzip members (the reference reads the trailer but never
+// checks it, decode_gz.c:281-297): CRC-32 of the decoded payload and ISIZE against the 8-byte trailer.
+// One warp per member, same slicing / GF(2) recombination as the PNG chunk CRCs.
+constexpr uint32_t ST_CHECKSUM = 16;
+__global__ void __launch_bounds__(SCAN_WARPS * 32) gz_verify_kernel(const uint8_t *in_base, const uint64_t *in_off,
+                                                                   const uint64_t *in_size, const uint8_t *out_base,
+                                                                   const uint64_t *out_off, const uint64_t *out_size,
+                                                                   uint32_t *status, uint32_t n)
+{
+    __shared__ CrcTables tables;
+    crc_tables_init(&tables, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint32_t lane_k = gf2_xpow_bytes(CRC_SLICE * (31 - ln));
+    const uint32_t warps = gridDim.x * SCAN_WARPS;
+    for (uint32_t i = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5); i < n; i += warps) {
+        if (status[i] != ST_OK) continue;
+        const uint8_t *t = in_base + in_off[i] + in_size[i] - 8;
+        const uint32_t want_crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        const uint32_t want_size = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+        const uint64_t len = out_size[i];
+        uint32_t crc = len ? crc32_warp(&tables, lane_k, out_base + out_off[i], len) : 0u;
+        if (ln == 0 && (crc != want_crc || (uint32_t)len != want_size)) status[i] = ST_CHECKSUM;
+        simt::syncwarp();
+    }
+}
+
 static inline void png_configure_kernels() {}
 
 // returns 0 or a cudaError_t value

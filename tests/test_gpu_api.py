@@ -229,3 +229,24 @@ def test_example_mains_print_the_readme_golden(golden_dir, tmp_path):
                  "average pixel: [248,249,251,158]"):
         assert line in p, p
     assert "decompressed bytes: 561872" in outs["hellogz"].stdout
+
+
+def test_optin_gzip_trailer_verification(ctx):
+    """dbg_set_verify: CRC32 / ISIZE are checked on the device only when asked; by default `good` follows the
+    reference, which ignores the trailer (decode_gz.c:281-297)."""
+    import struct
+    import zlib
+    data = corpus.word_salad(200000, 21)
+    ok = corpus.gzip_frame(corpus.raw_deflate(data), data)
+    bad_crc = ok[:-8] + struct.pack("<II", (zlib.crc32(data) ^ 1) & 0xFFFFFFFF, len(data))
+    bad_size = ok[:-8] + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data) + 1)
+    items = [ok, bad_crc, bad_size]
+    caps = [len(data) + len(ok)] * 3
+    assert [g for g, _ in ctx.decode_gz_batch(items, caps)] == [1, 1, 1]
+    ctx.set_verify(True)
+    try:
+        res = ctx.decode_gz_batch(items, caps)
+        assert [g for g, _ in res] == [1, 0, 0]
+        assert res[0][1] == data
+    finally:
+        ctx.set_verify(False)
