@@ -418,11 +418,12 @@ struct Sink {
     PendingStore pd;
 };
 
-template <int SINK>
+// CHECK = false: the caller has verified that the output has room for everything one window can produce.
+template <int SINK, bool CHECK>
 DBG_DEV uint32_t emit_literal(Sink &k, uint32_t byte)
 {
     if (SINK != SINK_COUNT) {
-        if (k.pos >= k.cap) return ST_OUT_OVERFLOW;
+        if (CHECK && k.pos >= k.cap) return ST_OUT_OVERFLOW;
         if (simt::lane() == 0) {
             if (SINK == SINK_BYTES) k.out[k.pos] = (uint8_t)byte;
             else k.out16[k.pos] = (uint16_t)byte;
@@ -453,14 +454,14 @@ DBG_DEV_NOINLINE void copy_match_u16(uint16_t *o, uint32_t pos, uint32_t len, ui
     simt::syncwarp();
 }
 
-template <int SINK>
+template <int SINK, bool CHECK>
 DBG_DEV uint32_t emit_match(Sink &k, uint32_t len, uint32_t dist)
 {
     if (SINK == SINK_COUNT) {
         k.pos += len;
         return ST_OK;
     }
-    if (k.pos + len > k.cap) return ST_OUT_OVERFLOW;
+    if (CHECK && k.pos + len > k.cap) return ST_OUT_OVERFLOW;
     if (SINK == SINK_BYTES) {
         if (dist > k.pos) return ST_BAD_DISTANCE;  // inflate.c:1843
         copy_match(k.out, k.pos, len, dist, k.pd);
@@ -587,25 +588,32 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
         const uint32_t cand = decode_candidate(sm, lo, mid, ln);
         uint32_t p = w.s, cur, err = 0;
         bool eob = false, slow = false;
-        do {
-            cur = p;
-            const uint32_t info = simt::shfl(cand, (int)p);
-            const uint32_t lf = (info >> 7) & 511;
-            p = info & 127;
-            if (lf == 0) {
-                err = emit_literal<SINK>(k, info >> 16);
-                if (err) break;
-            } else if (lf >= 3) {
-                err = emit_match<SINK>(k, lf, (info >> 16) + 1);
-                if (err) break;
-            } else {
-                const uint32_t code = info >> 16;
-                if (code == CAND_EOB) eob = true;
-                else if (code == CAND_ERR) err = ST_BAD_SYMBOL;
-                else slow = true;  // a code longer than the primary LUT index starts at `cur`
-                break;
-            }
-        } while (p < lim);
+        // one window yields at most 32 symbols of at most 258 bytes: with that much room left the
+        // per-symbol capacity checks are dropped
+        const bool roomy = SINK == SINK_COUNT || k.cap - k.pos >= 32 * 258;
+#define DBG_WALK(CHECK)                                                                        \
+        do {                                                                                   \
+            cur = p;                                                                           \
+            const uint32_t info = simt::shfl(cand, (int)p);                                    \
+            const uint32_t lf = (info >> 7) & 511;                                             \
+            p = info & 127;                                                                    \
+            if (lf == 0) {                                                                     \
+                err = emit_literal<SINK, CHECK>(k, info >> 16);                                \
+                if (CHECK && err) break;                                                       \
+            } else if (lf >= 3) {                                                              \
+                err = emit_match<SINK, CHECK>(k, lf, (info >> 16) + 1);                        \
+                if (err) break;                                                                \
+            } else {                                                                           \
+                const uint32_t code = info >> 16;                                              \
+                if (code == CAND_EOB) eob = true;                                              \
+                else if (code == CAND_ERR) err = ST_BAD_SYMBOL;                                \
+                else slow = true; /* a code longer than the primary LUT index starts at cur */ \
+                break;                                                                         \
+            }                                                                                  \
+        } while (p < lim)
+        if (roomy) DBG_WALK(false);
+        else DBG_WALK(true);
+#undef DBG_WALK
         if (err) return err;
         if (slow) {
             // rare: decode this one symbol serially (uniform), then rebuild the window candidates
@@ -619,7 +627,7 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
             }
             w.consume(e & 15);
             if (e & E_LIT) {
-                err = emit_literal<SINK>(k, e >> 16);
+                err = emit_literal<SINK, true>(k, e >> 16);
                 if (err) return err;
                 continue;
             }
@@ -644,7 +652,7 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
             uint32_t l2 = e & 15;
             uint32_t dist = (e >> 16) + ((bits >> l2) & ((1u << xb) - 1));
             w.consume(l2 + xb);
-            err = emit_match<SINK>(k, len, dist);
+            err = emit_match<SINK, true>(k, len, dist);
             if (err) return err;
             continue;
         }
