@@ -194,3 +194,17 @@ def test_split_stream_path_vs_reference(ctx, ref):
     for s, c, (good, out) in zip(streams, caps, got):
         rgood, rout = ref.inflate(s, c)
         assert good == rgood and out == rout
+
+
+def test_cfg5_extremes_vs_reference(ctx, ref):
+    """BASELINE config 5 extremes at full member size (16 MiB): stored random data, period-32000 data (matches
+    at the window limit, ratio ~100), long runs and zeros (ratio ~1000), plus small members of every class."""
+    big = 16 << 20
+    members = [corpus.gz_member_cfg5(i, big) for i in (0, 5, 6, 7)]
+    members += [corpus.gz_member_cfg5(i, 65536 + 4099 * i) for i in range(8)]
+    caps = [len(d) + len(g) + 64 for g, d in members]
+    res = ctx.decode_gz_batch([g for g, _ in members], caps)
+    for i, ((g, d), (good, out)) in enumerate(zip(members, res)):
+        rgood, rout = ref.decode_gz(g, caps[i])
+        assert good == rgood, i
+        assert len(out) == len(rout) and sha(out) == sha(rout), i
