@@ -73,6 +73,7 @@ struct dbg_ctx {
     Buf d_split, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
     uint32_t split_max_streams = 1024;  // batches with fewer streams may use the split-stream path
     bool verify = false;                // opt-in: check gzip CRC32 / ISIZE trailers
+    uint32_t inflate_ctas_per_sm = dbg::INFLATE_CTAS_PER_SM;  // resident streams per SM = 4x this (tunable: L2 footprint)
     // host-API staging
     Buf d_in, d_out, d_desc;       // arenas + descriptor tables
     Buf h_in, h_out, h_desc;       // pinned mirrors
@@ -156,6 +157,10 @@ extern "C" dbg_ctx *dbg_create(int device)
     cudaFuncSetAttribute(dbg::split_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA));
     if (const char *e = getenv("DBG_SPLIT_MAX_STREAMS")) ctx->split_max_streams = (uint32_t)atoi(e);
+    if (const char *e = getenv("DBG_INFLATE_CTAS_PER_SM")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= dbg::INFLATE_CTAS_PER_SM) ctx->inflate_ctas_per_sm = (uint32_t)v;
+    }
     return ctx;
 }
 
@@ -222,7 +227,7 @@ static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_c
     a.counter = d_counter;
     CU(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), s));
     uint32_t ctas_needed = (a.n + dbg::INFLATE_WARPS_PER_CTA - 1) / dbg::INFLATE_WARPS_PER_CTA;
-    uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);
+    uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)ctx->sm_count * ctx->inflate_ctas_per_sm);
     size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->profiling) {
@@ -424,6 +429,12 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
                         lay.pre_status, nullptr, nullptr, nullptr, (uint32_t)n};
     rc = launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
     if (rc) return rc;
+    if (ctx->verify) {
+        uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
+        dbg::png_adler_kernel<<<ctas, dbg::SCAN_WARPS * 32, 0, s>>>(pb);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
     // 3. un-filter (+ palette / RGB expansion) straight into the caller's RGBA
     rc = dbg::png_launch_unfilter(pb, d_out, d_out_off, d_status, ctx->sm_count, s);
     ctx->launches += 2;

@@ -6,18 +6,24 @@
 // :565-706 + huffman_to_hashmap :494-557), symbol decode (:421-474) and the
 // LZ77 copy (:1861-1897). It is a new design, not a translation:
 //
-//   * one warp owns one stream. Symbol decode is executed redundantly and
-//     uniformly by all 32 lanes (same registers, broadcast shared-memory LUT
-//     reads), so there is no divergence and no shuffle on the serial path;
-//     the lanes fan out only where there is parallel work: Huffman table
-//     construction (match_any/ballot ranking, warp scans) and LZ77 / stored
-//     copies (one byte per lane, pattern replication for short distances).
+//   * one warp owns one stream. Headers are read uniformly (every lane holds the
+//     same window registers); symbols are decoded a 32-bit window at a time:
+//     lane k decodes the candidate symbol that would start at bit k (litlen
+//     lookup, extra bits, distance lookup -- 32 offsets in parallel) and the
+//     warp then walks the chain of real symbol starts with one shuffle per
+//     symbol. The lanes also fan out for Huffman table construction
+//     (match_any ranking, warp scans), LZ77 copies (one byte per lane, stores
+//     deferred behind the next symbols, pattern replication for short
+//     distances) and stored-block copies.
 //   * compressed bytes are staged global -> shared with 16-byte cp.async
 //     (LDGSTS) into a 2 x 512 B per-warp ring, requested one chunk ahead.
-//   * decode tables are two-level: a 9-bit (litlen) / 7-bit (distance) primary
+//   * decode tables are two-level: a 9-bit (litlen) / 8-bit (distance) primary
 //     LUT with pre-baked base/extra-bit fields, and a canonical first-code
-//     walk for the rare longer codes -- 4.7 KB of shared memory per warp
+//     walk for the rare longer codes -- 5.2 KB of shared memory per warp
 //     instead of the reference's 3 x 792 KB hash maps (inflate.c:112-118).
+//   * streams that are one fixed-Huffman block can also be decoded chunk-
+//     parallel ("split stream", end of this file): exact chunk boundaries from
+//     32-hypothesis transfer tables, 16-bit cells with markers, resolve pass.
 //
 // Behavioural parity with the reference's silent, no-assert build is kept where
 // the reference has defined behaviour: the premature
@@ -130,10 +136,6 @@ struct Window {
         wleft--;
         if ((wb & 63) == 0) maintain();
         w3 = ring[(wb + 3) & 255];
-    }
-    DBG_DEVM void shift_n(uint32_t n)
-    {
-        for (; n; n--) shift();
     }
     DBG_DEVM uint32_t peek32() const { return simt::funnel_r(w0, w1, s); }
     DBG_DEVM void consume(uint32_t n)  // n <= 64

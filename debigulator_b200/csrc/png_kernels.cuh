@@ -336,6 +336,40 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) gz_verify_kernel(const uint8_
     }
 }
 
+// Opt-in: Adler-32 of the inflated scanline stream against the zlib trailer (the reference drops those four
+// bytes unread, decode_png.c:816). One warp per image; 2 KiB tiles, 64 bytes per lane, warp reductions.
+__global__ void __launch_bounds__(SCAN_WARPS * 32) png_adler_kernel(PngBatch b)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint32_t warps = gridDim.x * SCAN_WARPS;
+    for (uint32_t i = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5); i < b.n; i += warps) {
+        if (b.lay.pre_status[i] != ST_OK || b.lay.inf_status[i] != ST_OK) continue;
+        const uint8_t *p = b.lay.scan + b.lay.s_off[i];
+        const uint64_t n = b.lay.s_size[i];
+        uint64_t s1 = 1, s2 = 0;
+        for (uint64_t t0 = 0; t0 < n; t0 += 2048) {
+            const uint32_t tl = (uint32_t)(n - t0 < 2048 ? n - t0 : 2048);
+            uint32_t a = 0, w = 0;
+            const uint32_t lo = ln * 64;
+            for (uint32_t j = lo; j < lo + 64 && j < tl; j++) {
+                uint32_t v = p[t0 + j];
+                a += v;
+                w += (tl - j) * v;
+            }
+            for (int d = 16; d; d >>= 1) {
+                a += simt::shfl_xor(a, d);
+                w += simt::shfl_xor(w, d);
+            }
+            s2 = (s2 + (uint64_t)tl * s1 + w) % 65521u;
+            s1 = (s1 + a) % 65521u;
+        }
+        const uint8_t *z = (const uint8_t *)(uintptr_t)b.lay.z_off[i] + b.lay.z_size[i];
+        const uint32_t want = ((uint32_t)z[0] << 24) | ((uint32_t)z[1] << 16) | ((uint32_t)z[2] << 8) | z[3];
+        if (ln == 0 && want != (uint32_t)((s2 << 16) | s1)) b.lay.inf_status[i] = ST_CHECKSUM;
+        simt::syncwarp();
+    }
+}
+
 static inline void png_configure_kernels() {}
 
 // returns 0 or a cudaError_t value

@@ -67,7 +67,7 @@ enum {
     DBG_ST_CRC = 13,        /* PNG chunk CRC mismatch (decode_png.c:1341-1348) */
     DBG_ST_FILTER = 14,     /* first filter byte > 4 (decode_png.c:847-858) */
     DBG_ST_SHORT_STREAM = 15, /* inflated PNG stream shorter than h*(w*bpp+1) */
-    DBG_ST_CHECKSUM = 16     /* only with dbg_set_verify(): gzip CRC32 / ISIZE trailer mismatch */
+    DBG_ST_CHECKSUM = 16     /* only with dbg_set_verify(): gzip CRC32 / ISIZE or zlib Adler-32 mismatch */
 };
 
 int dbg_version(void);
@@ -132,10 +132,11 @@ int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, c
                                 const uint64_t *d_out_cap, uint32_t *d_status, uint64_t total_in_bytes,
                                 uint64_t total_rgba_bytes, void *stream);
 
-/* Opt-in strictness the reference does not have (it reads the gzip trailer but never checks it,
- * decode_gz.c:281-297): when on, gzip batches also compare CRC-32 and ISIZE of every decoded member with its
- * trailer (on the device) and report DBG_ST_CHECKSUM / good = 0 on mismatch. Off by default, so that `good`
- * matches the reference. */
+/* Opt-in strictness the reference does not have: when on, gzip batches also compare CRC-32 and ISIZE of every
+ * decoded member with its trailer (the reference reads the trailer but never checks it, decode_gz.c:281-297) and
+ * PNG batches compare the Adler-32 of the inflated scanlines with the zlib trailer (the reference drops those
+ * four bytes unread, decode_png.c:816); a mismatch reports DBG_ST_CHECKSUM / good = 0. Computed on the device.
+ * Off by default, so that `good` matches the reference. */
 int dbg_set_verify(dbg_ctx *ctx, int on);
 
 /* Optional timing of the dominant kernel (inflate): after dbg_profile_enable(ctx, 1)

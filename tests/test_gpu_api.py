@@ -250,3 +250,35 @@ def test_optin_gzip_trailer_verification(ctx):
         assert res[0][1] == data
     finally:
         ctx.set_verify(False)
+
+
+def test_optin_png_adler_verification(ctx):
+    """With dbg_set_verify the zlib Adler-32 of the scanline stream is checked (single- and multi-IDAT files)."""
+    import struct
+    import zlib
+    img = corpus.gradient_noise_rgba(200, 150, 31)
+    ok1 = corpus.write_png(img, 4, single_block=True)
+    ok2 = corpus.write_png(img, -1, idat_split=4000, strategy=zlib.Z_DEFAULT_STRATEGY)
+
+    def break_adler(png):
+        # flip a bit in the last 4 bytes of the (last) IDAT payload and fix that chunk's CRC
+        pos, last = 8, None
+        while pos < len(png):
+            (ln,) = struct.unpack(">I", png[pos:pos + 4])
+            if png[pos + 4:pos + 8] == b"IDAT":
+                last = (pos, ln)
+            pos += 12 + ln
+        p, ln = last
+        body = bytearray(png[p + 4:p + 8 + ln])
+        body[-1] ^= 1
+        return png[:p + 4] + bytes(body) + struct.pack(">I", zlib.crc32(bytes(body)) & 0xFFFFFFFF) + png[p + 12 + ln:]
+
+    files = [ok1, ok2, break_adler(ok1), break_adler(ok2)]
+    assert [r[0] for r in ctx.decode_png_batch(files)] == [1, 1, 1, 1]      # the reference ignores Adler-32
+    ctx.set_verify(True)
+    try:
+        res = ctx.decode_png_batch(files)
+        assert [r[0] for r in res] == [1, 1, 0, 0]
+        assert res[0][3] == img.tobytes() and res[1][3] == img.tobytes()
+    finally:
+        ctx.set_verify(False)
