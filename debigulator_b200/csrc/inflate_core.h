@@ -114,7 +114,7 @@ struct Window {
     {
         uint32_t off = (c << 9) + ((uint32_t)simt::lane() << 4);
         bool in = off < end16;
-        simt::cp_async16(&ring[((c & 1) << 7) + ((uint32_t)simt::lane() << 2)], base + (in ? off : 0), in ? 16 : 0);
+        simt::cp_async16_stream(&ring[((c & 1) << 7) + ((uint32_t)simt::lane() << 2)], base + (in ? off : 0), in ? 16 : 0);
     }
     DBG_DEVM void maintain()
     {

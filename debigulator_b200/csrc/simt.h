@@ -62,6 +62,16 @@ DBG_DEV void backoff() { __nanosleep(64); }
 DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return __ldcg(p); }
 DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return __ldcg(p); }
 
+// Same, for data that is read exactly once (the compressed input): the L2 line is marked evict-first so
+// that the stream does not push the recently written output -- which LZ77 matches read back -- out of L2.
+DBG_DEV void cp_async16_stream(void *smem_dst, const void *gsrc, int src_bytes)
+{
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes), "l"(pol)
+                 : "memory");
+}
 DBG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 DBG_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
@@ -169,6 +179,7 @@ DBG_DEV void backoff() {}
 DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return *p; }
 DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return *p; }
 
+DBG_DEV void cp_async16_stream(void *smem_dst, const void *gsrc, int src_bytes) { cp_async16(smem_dst, gsrc, src_bytes); }
 DBG_DEV void cp_async_commit() {}
 DBG_DEV void cp_async_wait_all() {}
 
