@@ -254,7 +254,11 @@ def run_ours(args):
     d_in_off, d_in_size, d_out_off, d_out_cap = t_i64(in_off), t_i64(in_size), t_i64(out_off), t_i64(out_cap)
     d_out_size = torch.zeros(n, dtype=torch.int64, device=dev)
     d_status = torch.zeros(n, dtype=torch.int32, device=dev)
-    order = np.argsort(-in_size.astype(np.int64), kind="stable").astype(np.uint32)
+    # scheduling hint (any caller can compute it from the first deflate byte): longest-processing-time first,
+    # where a member that starts with a stored block counts as 1/16 of its size
+    first = np.array([uniq[i % N_UNIQUE][0][10] & 6 for i in range(n)])
+    weight = np.where(first == 0, in_size // 16, in_size).astype(np.int64)
+    order = np.argsort(-weight, kind="stable").astype(np.uint32)
     d_order = torch.from_numpy(order.view(np.int32)).to(dev)
     stream = torch.cuda.current_stream().cuda_stream
 

@@ -445,6 +445,23 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
 // -------------------------------------------------------------- host batches --
 static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
+// Scheduling weight of an item for the largest-first work queue: its compressed size, except that a
+// stream whose first block is stored (a plain copy, ~16x cheaper per byte than Huffman decode) counts less.
+static inline uint64_t sched_weight(int kind, const uint8_t *p, uint64_t size)
+{
+    uint64_t at = 0;
+    if (kind == 1) {  // gzip: skip the header the way gz_scan_kernel does
+        if (size < 18) return size;
+        at = 10;
+        if ((p[3] >> 3) & 1) {
+            while (at < size && p[at] != 0) at++;
+            at++;
+        }
+    }
+    if (kind == 2 || at >= size) return size;
+    return ((p[at] >> 1) & 3) == 0 ? size / 16 : size;
+}
+
 extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
                                        const uint64_t *in_size, uint8_t *h_out, const uint64_t *out_off,
                                        const uint64_t *out_cap, uint64_t *out_size, uint32_t *status)
@@ -495,8 +512,10 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
     uint64_t *gz_size = gz_off ? gz_off + n : nullptr;
     uint32_t *gz_pre = gz_off ? (uint32_t *)(gz_size + n) : nullptr;
     if (nw == 1) {
+        std::vector<uint64_t> wt(n);
+        for (uint64_t i = 0; i < n; i++) wt[i] = sched_weight(kind, h_in + in_off[i], in_size[i]);
         std::iota(h_order, h_order + n, 0u);
-        std::stable_sort(h_order, h_order + n, [&](uint32_t a, uint32_t b) { return in_size[a] > in_size[b]; });
+        std::stable_sort(h_order, h_order + n, [&](uint32_t a, uint32_t b) { return wt[a] > wt[b]; });
         CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(ctx->d_in.p, h_in, in_span, cudaMemcpyHostToDevice, s));
         CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
@@ -516,8 +535,10 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
         for (int k = 0; k < nw; k++) {
             uint32_t *o = h_order + cut[k];
             uint64_t m = cut[k + 1] - cut[k], b = cut[k];
+            std::vector<uint64_t> wt(m);
+            for (uint64_t i = 0; i < m; i++) wt[i] = sched_weight(kind, h_in + in_off[b + i], in_size[b + i]);
             std::iota(o, o + m, 0u);
-            std::stable_sort(o, o + m, [&](uint32_t x, uint32_t y) { return in_size[b + x] > in_size[b + y]; });
+            std::stable_sort(o, o + m, [&](uint32_t x, uint32_t y) { return wt[x] > wt[y]; });
         }
         CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
         CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
