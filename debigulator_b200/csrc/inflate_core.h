@@ -345,6 +345,31 @@ DBG_DEV_NOINLINE void copy_match_slow(uint8_t *out, uint32_t pos, uint32_t len, 
     }
 }
 
+// Stored block payload (inflate.c:958-989): a plain copy with arbitrary source and destination alignment.
+// Head bytes bring the destination to a 4-byte boundary, then every lane moves one word per step, built
+// from two aligned source words with a funnel shift.
+DBG_DEV void copy_stored(uint8_t *dst, const uint8_t *src, uint32_t len)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (head > len) head = len;
+    if (ln < head) dst[ln] = src[ln];
+    dst += head;
+    src += head;
+    len -= head;
+    const uint32_t words = len >> 2;
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 3) * 8;
+    const uint32_t *s4 = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
+    uint32_t *d4 = (uint32_t *)dst;
+    for (uint32_t i = ln; i < words; i += 32) {
+        uint32_t lo = s4[i];
+        uint32_t v = sh ? simt::funnel_r(lo, s4[i + 1], sh) : lo;  // s4[i + 1] still overlaps the source when sh != 0
+        d4[i] = v;
+    }
+    const uint32_t done = words << 2;
+    if (ln < len - done) dst[done + ln] = src[done + ln];
+}
+
 // Match dispatch: the common short non-overlapping match becomes a deferred
 // load/store pair; everything else goes through copy_match_slow.
 DBG_DEV void copy_match(uint8_t *out, uint32_t pos, uint32_t len, uint32_t dist, PendingStore &pd)
@@ -710,7 +735,6 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     if (in_size < 5) return ST_INPUT_TOO_SMALL;
     if (in_size >= (1ull << 31) || cap >= (1ull << 32) - 1024) return ST_TOO_LARGE;  // keeps pos + len in 32 bits
 
-    const uint32_t ln = (uint32_t)simt::lane();
     Window w;
     const StreamIn g = open_stream(w, sm, in, in_size);
     w.seek(g.mis);
@@ -743,9 +767,7 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
                 uint64_t bytepos = w.abs_bits() >> 3;
                 if (bytepos + len > g.end_byte) return ST_TRUNCATED;
                 if ((uint64_t)k.pos + len > k.cap) return ST_OUT_OVERFLOW;
-                const uint8_t *src = w.base + bytepos;
-                uint8_t *dst = out + k.pos;
-                for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
+                copy_stored(out + k.pos, w.base + bytepos, len);
                 k.pos += len;
                 w.seek(bytepos + len);
             }
