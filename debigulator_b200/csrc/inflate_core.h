@@ -602,7 +602,10 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
 {
     const uint32_t ln = (uint32_t)simt::lane();
     for (;;) {
-        uint32_t lim = 32;
+        // Two words (64 start offsets) per pass when the limit is not in sight, otherwise one word
+        // with the limit applied. Candidate k of the second word carries offsets relative to the first.
+        const bool two = w.wleft >= 2;
+        uint32_t lim = two ? 64u : 32u;
         if (w.wleft <= 0) {
             lim = w.wleft == 0 ? w.lim_b : 0u;
             if (w.s >= lim) {
@@ -612,16 +615,18 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
         }
         const uint32_t lo = simt::funnel_r(w.w0, w.w1, ln);
         const uint32_t mid = simt::funnel_r(w.w1, w.w2, ln);
-        const uint32_t cand = decode_candidate(sm, lo, mid, ln);
+        const uint32_t hi = simt::funnel_r(w.w2, w.w3, ln);
+        const uint32_t cand0 = decode_candidate(sm, lo, mid, ln);
+        const uint32_t cand1 = two ? decode_candidate(sm, mid, hi, ln + 32) : 0u;
         uint32_t p = w.s, cur, err = 0;
         bool eob = false, slow = false;
-        // one window yields at most 32 symbols of at most 258 bytes: with that much room left the
+        // one pass yields at most 64 symbols of at most 258 bytes: with that much room left the
         // per-symbol capacity checks are dropped
-        const bool roomy = SINK == SINK_COUNT || k.cap - k.pos >= 32 * 258;
+        const bool roomy = SINK == SINK_COUNT || k.cap - k.pos >= 64 * 258;
 #define DBG_WALK(CHECK)                                                                        \
         do {                                                                                   \
             cur = p;                                                                           \
-            const uint32_t info = simt::shfl(cand, (int)p);                                    \
+            const uint32_t info = simt::shfl(p < 32 ? cand0 : cand1, (int)p);                  \
             const uint32_t lf = (info >> 7) & 511;                                             \
             p = info & 127;                                                                    \
             if (lf == 0) {                                                                     \
@@ -644,6 +649,10 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
         if (err) return err;
         if (slow) {
             // rare: decode this one symbol serially (uniform), then rebuild the window candidates
+            if (cur >= 32) {
+                w.shift();
+                cur -= 32;
+            }
             w.s = cur;
             uint32_t bits = w.peek32();
             uint32_t e = sm->lit_lut[bits & ((1u << LIT_ROOT) - 1)];
@@ -685,15 +694,12 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
         }
         // the window now sits exactly on the next symbol start (the chunk prober relies on it)
         w.s = p & 31;
-        if (p >= 32) {
-            w.shift();
-            if (p >= 64) w.shift();
-        }
+        for (uint32_t n = p >> 5; n; n--) w.shift();
         if (eob) {
             end_reason = END_EOB;
             return ST_OK;
         }
-        if (lim < 32) {  // the walk ran into the limit
+        if (!two && lim < 32) {  // the walk ran into the limit
             end_reason = END_LIMIT;
             return ST_OK;
         }
