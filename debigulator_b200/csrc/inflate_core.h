@@ -65,6 +65,7 @@ struct InflateSmem {
     uint16_t dist_first[16], dist_offs[16], dist_cnt[16];
     uint8_t dist_sorted[32];
     uint8_t lens[320];       // HLIT (<=288) + HDIST (<=32) code lengths
+    uint32_t cand[2][64];    // candidate symbols of the current / previous decode pass, one per start offset
 };
 
 // LUT entry: [3:0] code length (0 = not in the primary table), bit4 literal /
@@ -601,6 +602,7 @@ template <int SINK>
 DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &bt, Sink &k, uint32_t &end_reason)
 {
     const uint32_t ln = (uint32_t)simt::lane();
+    uint32_t flip = 0;
     for (;;) {
         // Two words (64 start offsets) per pass when the limit is not in sight, otherwise one word
         // with the limit applied. Candidate k of the second word carries offsets relative to the first.
@@ -616,8 +618,15 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
         const uint32_t lo = simt::funnel_r(w.w0, w.w1, ln);
         const uint32_t mid = simt::funnel_r(w.w1, w.w2, ln);
         const uint32_t hi = simt::funnel_r(w.w2, w.w3, ln);
-        const uint32_t cand0 = decode_candidate(sm, lo, mid, ln);
-        const uint32_t cand1 = two ? decode_candidate(sm, mid, hi, ln + 32) : 0u;
+        // candidates go through shared memory: the chain walk below reads them with a uniform
+        // (broadcast) address, which needs no warp-convergence point per symbol the way a shuffle does
+        // (double buffered: a lane that is already in the next pass must not overwrite what a slower
+        // lane is still walking; the barrier below keeps lanes at most one pass apart)
+        uint32_t *cand = sm->cand[flip];
+        flip ^= 1;
+        cand[ln] = decode_candidate(sm, lo, mid, ln);
+        if (two) cand[ln + 32] = decode_candidate(sm, mid, hi, ln + 32);
+        simt::syncwarp();
         uint32_t p = w.s, cur, err = 0;
         bool eob = false, slow = false;
         // one pass yields at most 64 symbols of at most 258 bytes: with that much room left the
@@ -626,7 +635,7 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
 #define DBG_WALK(CHECK)                                                                        \
         do {                                                                                   \
             cur = p;                                                                           \
-            const uint32_t info = simt::shfl(p < 32 ? cand0 : cand1, (int)p);                  \
+            const uint32_t info = cand[p];                                                     \
             const uint32_t lf = (info >> 7) & 511;                                             \
             p = info & 127;                                                                    \
             if (lf == 0) {                                                                     \
