@@ -350,6 +350,13 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = comp_bytes + out_total  # C + U per launch
+        traffic = None  # dram read + write of one inflate launch from the committed `ncu --set full` capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_inflate_traffic.json")))
+            if n == N_MEMBERS and int(tj["algorithmic_bytes_per_launch"]) == int(alg_bytes):
+                traffic = float(tj["traffic_bytes_per_launch"])
+        except Exception:
+            pass
         avg_kern_ms = kern_ms / max(kern_n, 1)
         achieved = alg_bytes / (avg_kern_ms / 1e3) / 1e9
         line = {
@@ -364,7 +371,8 @@ def run_ours(args):
                     "steps": e2e_steps, "api": "dbg_decode_batch_packed(kind=gzip), pinned host arenas"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "inflate_batch_kernel", "avg_launch_ms": avg_kern_ms, "launches": kern_n,
+                         "traffic": traffic, "traffic_source": "profiles/r01_inflate_traffic.json (ncu --set full)" if traffic else None,
+                         "kernel": "inflate_batch_kernel", "avg_launch_ms": avg_kern_ms, "launches": kern_n,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "cpu_baseline": cpu, "clocks": clocks,
