@@ -71,7 +71,7 @@ struct dbg_ctx {
     Buf d_meta;                    // derived descriptors (gzip payloads, PNG streams)
     Buf d_png_scratch;             // compacted IDAT + filtered scanlines
     Buf d_split, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
-    uint32_t split_max_streams = 1024;  // batches with fewer streams may use the split-stream path
+    uint32_t split_max_streams = 1536;  // batches with fewer streams may use the split-stream path (measured crossover ~1,500 images of 1024^2)
     bool verify = false;                // opt-in: check gzip CRC32 / ISIZE trailers
     uint32_t inflate_ctas_per_sm = dbg::INFLATE_CTAS_PER_SM;  // resident streams per SM = 4x this (tunable: L2 footprint)
     // host-API staging

@@ -73,7 +73,8 @@ enum {
 int dbg_version(void);
 int dbg_device_count(void); /* >= 0, or a DBG_ERR_* code */
 
-/* One context per GPU (one process per GPU in multi-GPU runs). */
+/* One context per GPU (one process per GPU in multi-GPU runs). A context owns its device scratch, pinned
+ * staging buffers and streams; it is not thread-safe -- use one context per host thread. */
 dbg_ctx *dbg_create(int device);
 void dbg_destroy(dbg_ctx *ctx);
 const char *dbg_last_error(const dbg_ctx *ctx); /* ctx may be NULL */
