@@ -327,6 +327,9 @@ def run_ours(args):
     png_large = None
     if args.png_large and rank == 0 and world == 1:
         png_large = bench_png(ctx, dev, torch, args.png_large, 8192, 8192, 1)
+    bmp = None
+    if args.bmp and rank == 0 and world == 1:
+        bmp = bench_bmp(ctx, dev, torch, args.bmp)
 
     # ---- CPU baseline: the reference C on this box's host cores (rank 0, N=1 only)
     cpu = None
@@ -381,6 +384,10 @@ def run_ours(args):
             line["png"] = png
         if png_large:
             line["png_cfg4_shape"] = png_large
+        if bmp:
+            bmp["roofline"]["peak"] = peak
+            bmp["roofline"]["frac"] = bmp["roofline"]["achieved"] / peak
+            line["bmp"] = bmp
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -439,6 +446,69 @@ def bench_png(ctx, dev, torch, n=PNG_N, w=PNG_W, h=PNG_H, n_unique=PNG_UNIQUE):
                        "unique_images": PNG_UNIQUE_, "png_bytes": tot_in}}
 
 
+def bench_bmp(ctx, dev, torch, n, w=2048, h=2048):
+    """decode_BMP / encode_BMP on n bottom-up w x h files: the one kernel of the
+    library that is plain HBM traffic (every pixel read once, written once)."""
+    from debigulator_b200 import corpus
+    from oracle import checker
+    rng = np.random.default_rng(7)
+    rgba = rng.integers(0, 256, w * h * 4, dtype=np.uint8).tobytes()
+    file = corpus.bmp_file(rgba, w, h, bottom_up=True)
+    fsz, osz = len(file), w * h * 4
+    stride = (fsz + 255) // 256 * 256
+    one = torch.from_numpy(np.frombuffer(file + bytes(stride - fsz), np.uint8).copy()).to(dev)
+    d_in = one.repeat(n)
+    d_out = torch.zeros(n * osz, dtype=torch.uint8, device=dev)
+    i64 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.uint64).view(np.int64)).to(dev)
+    in_off, in_size = i64(np.arange(n, dtype=np.uint64) * np.uint64(stride)), i64(np.full(n, fsz, dtype=np.uint64))
+    out_off, out_cap = i64(np.arange(n, dtype=np.uint64) * np.uint64(osz)), i64(np.full(n, osz, dtype=np.uint64))
+    out_size = torch.zeros(n, dtype=torch.int64, device=dev)
+    st = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    # encode target: the decoded images back into BMP files
+    estride = (54 + osz + 1 + 255) // 256 * 256
+    d_enc = torch.zeros(n * estride, dtype=torch.uint8, device=dev)
+    e_off, e_cap = i64(np.arange(n, dtype=np.uint64) * np.uint64(estride)), i64(np.full(n, estride, dtype=np.uint64))
+    e_size = torch.zeros(n, dtype=torch.int64, device=dev)
+    e_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    wd = torch.full((n,), w, dtype=torch.int32, device=dev)
+    ht = torch.full((n,), h, dtype=torch.int32, device=dev)
+
+    def dec():
+        ctx.bmp_decode_device(d_in, in_off, in_size, d_out, out_off, out_cap, out_size, st, stream=stream)
+
+    def enc():
+        ctx.bmp_encode_device(d_out, out_off, out_cap, wd, ht, d_enc, e_off, e_cap, e_size, e_st, stream=stream)
+
+    res = {}
+    for name, fn in (("decode", dec), ("encode", enc)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 10
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / steps
+    assert int(st.abs().sum().item()) == 0 and int(e_st.abs().sum().item()) == 0, "bmp failures"
+    exp = torch.from_numpy(np.frombuffer(rgba, np.uint8).copy()).to(dev)
+    assert torch.equal(d_out.view(n, osz)[0], exp) and torch.equal(d_out.view(n, osz)[n - 1], exp), "bmp pixel mismatch"
+    size, want = checker.encode_bmp(rgba, w, h)
+    got = d_enc.view(n, estride)[n - 1][: size - 1].cpu().numpy().tobytes()
+    assert got == want and int(e_size[0].item()) == size, "bmp encode mismatch"
+    alg = 2 * n * osz  # pixels read once + written once
+    ach = alg / (res["decode"] / 1e3) / 1e9
+    return {"metric": "bmp_decode_Mpixels_per_s", "value": n * w * h / (res["decode"] / 1e3) / 1e6, "unit": "Mpix/s",
+            "ms_per_step": res["decode"], "encode_Mpixels_per_s": n * w * h / (res["encode"] / 1e3) / 1e6,
+            "encode_ms_per_step": res["encode"],
+            "config": {"workload": f"{n} x {w}x{h} 32-bit bottom-up BMP files (rows flipped), then re-encoded", "unique_images": 1},
+            "roofline": {"bound": "hbm", "achieved": ach, "unit": "GB/s", "kernel": "bmp_swizzle_kernel",
+                         "algorithmic_bytes_per_launch": alg, "encode_achieved": alg / (res["encode"] / 1e3) / 1e9}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -451,6 +521,7 @@ def main():
     ap.add_argument("--png-only", action="store_true")
     ap.add_argument("--png-images", type=int, default=PNG_N)
     ap.add_argument("--png-large", type=int, default=4, help="number of 8192x8192 images in the config-4-shape line (0 = skip)")
+    ap.add_argument("--bmp", type=int, default=64, help="number of 2048x2048 BMP files in the BMP line (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

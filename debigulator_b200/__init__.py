@@ -7,7 +7,8 @@ its own and no CPU fallback: loading fails loudly if the library is missing and
 `Context()` raises if no CUDA device is usable.
 """
 from .api import (Context, DebigulatorError, STATUS_NAMES, load_library, library_path,
-                  png_get_width_height)
+                  png_get_width_height, bmp_get_width_height)
+from . import api
 
 __all__ = ["Context", "DebigulatorError", "STATUS_NAMES", "load_library", "library_path",
-           "png_get_width_height"]
+           "png_get_width_height", "bmp_get_width_height", "api"]

@@ -71,6 +71,16 @@ def load_library():
     L.dbg_png_scratch_bytes.restype = u64
     L.dbg_decode_png_batch_device.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, u64, u64, vp]
     L.dbg_decode_png_batch_device.restype = i32
+    L.dbg_decode_bmp_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp]
+    L.dbg_decode_bmp_batch.restype = i32
+    L.dbg_encode_bmp_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dbg_encode_bmp_batch.restype = i32
+    L.dbg_decode_bmp_batch_device.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dbg_decode_bmp_batch_device.restype = i32
+    L.dbg_encode_bmp_batch_device.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dbg_encode_bmp_batch_device.restype = i32
+    L.get_BMP_width_height.argtypes = [vp, u64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
+    L.get_BMP_width_height.restype = None
     L.decode_png_get_width_height.argtypes = [vp, u64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                               C.POINTER(C.c_uint8)]
     L.decode_png_get_width_height.restype = None
@@ -84,6 +94,15 @@ def png_get_width_height(data: bytes):
     w, h, g = C.c_uint32(0), C.c_uint32(0), C.c_uint8(0)
     buf = C.create_string_buffer(bytes(data), len(data))
     L.decode_png_get_width_height(buf, len(data), C.byref(w), C.byref(h), C.byref(g))
+    return int(g.value), int(w.value), int(h.value)
+
+
+def bmp_get_width_height(data: bytes):
+    """get_BMP_width_height (decode_bmp.h:14-19): returns (good, w, h). Host only."""
+    L = load_library()
+    w, h, g = C.c_uint32(0), C.c_uint32(0), C.c_uint8(0)
+    buf = C.create_string_buffer(bytes(data), max(len(data), 1))
+    L.get_BMP_width_height(buf, len(data), C.byref(w), C.byref(h), C.byref(g))
     return int(g.value), int(w.value), int(h.value)
 
 
@@ -175,6 +194,29 @@ class Context:
         self._check(self.L.dbg_decode_png_batch(self.h, n, in_p, in_sz, out_p, cap, good), "dbg_decode_png_batch")
         return [(int(good[i]), dims[i][1], dims[i][2], outs[i].raw[: caps[i]] if good[i] else b"") for i in range(n)]
 
+    def decode_bmp_batch(self, files, caps=None):
+        """dbg_decode_bmp_batch: returns [(good, w, h, rgba bytes)]. caps default to w*h*4 from the header."""
+        if caps is None:
+            dims = [bmp_get_width_height(f) for f in files]
+            caps = [(w * h * 4 if g and w * h * 4 < 1 << 32 else 0) for g, w, h in dims]
+        n, bufs, outs, in_p, out_p, in_sz, cap, _ = self._pointer_batch(None, files, caps)
+        good = (C.c_uint8 * n)()
+        w, h = (C.c_uint32 * n)(), (C.c_uint32 * n)()
+        self._check(self.L.dbg_decode_bmp_batch(self.h, n, in_p, in_sz, out_p, cap, w, h, good), "dbg_decode_bmp_batch")
+        return [(int(good[i]), int(w[i]), int(h[i]), outs[i].raw[: w[i] * h[i] * 4] if good[i] else b"") for i in range(n)]
+
+    def encode_bmp_batch(self, images, caps=None):
+        """dbg_encode_bmp_batch: images = [(rgba bytes, w, h)]; returns [(status, reported size, bytes written)]."""
+        rgba = [im[0] for im in images]
+        if caps is None:
+            caps = [54 + len(r) + 1 for r in rgba]
+        n, bufs, outs, in_p, out_p, in_sz, cap, out_sz = self._pointer_batch(None, rgba, caps)
+        w = (C.c_uint32 * n)(*[int(im[1]) for im in images])
+        h = (C.c_uint32 * n)(*[int(im[2]) for im in images])
+        st = (C.c_uint32 * n)()
+        self._check(self.L.dbg_encode_bmp_batch(self.h, n, in_p, in_sz, w, h, out_p, cap, out_sz, st), "dbg_encode_bmp_batch")
+        return [(int(st[i]), int(out_sz[i]), outs[i].raw[: max(int(out_sz[i]) - 1, 0)] if st[i] == 0 else b"") for i in range(n)]
+
     # ---- packed host arenas (numpy uint8 arrays, ideally pinned) --------------
     def decode_packed(self, kind, h_in, in_off, in_size, h_out, out_off, out_cap):
         n = len(in_off)
@@ -202,3 +244,17 @@ class Context:
                                                        _ptr(d_out), _ptr(out_off), _ptr(out_cap), _ptr(status),
                                                        int(total_in), int(total_rgba), stream),
                     "dbg_decode_png_batch_device")
+
+    def bmp_decode_device(self, d_in, in_off, in_size, d_out, out_off, out_cap, out_size, status, width=None,
+                          height=None, stream=None):
+        self._check(self.L.dbg_decode_bmp_batch_device(self.h, in_off.numel(), _ptr(d_in), _ptr(in_off), _ptr(in_size),
+                                                       _ptr(d_out), _ptr(out_off), _ptr(out_cap), _ptr(out_size),
+                                                       _ptr(width), _ptr(height), _ptr(status), stream),
+                    "dbg_decode_bmp_batch_device")
+
+    def bmp_encode_device(self, d_rgba, rgba_off, rgba_size, width, height, d_out, out_off, out_cap, out_size, status,
+                          stream=None):
+        self._check(self.L.dbg_encode_bmp_batch_device(self.h, rgba_off.numel(), _ptr(d_rgba), _ptr(rgba_off),
+                                                       _ptr(rgba_size), _ptr(width), _ptr(height), _ptr(d_out),
+                                                       _ptr(out_off), _ptr(out_cap), _ptr(out_size), _ptr(status), stream),
+                    "dbg_encode_bmp_batch_device")

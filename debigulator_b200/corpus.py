@@ -236,3 +236,26 @@ def png_cfg3(i, w=1024, h=1024):
     """BASELINE config 3 image i: forced filter i%6-1 (-1 = adaptive). Returns (png bytes, rgba bytes)."""
     img = gradient_noise_rgba(w, h, 0x706E6700 + i)
     return write_png(img, filt=i % 6 - 1, single_block=True), img.tobytes()
+
+
+def bmp_file(rgba: bytes, w: int, h: int, bottom_up: bool = False, v4: bool = False, pad: int = 0,
+             bf_size: int = None, planes: int = 1, bpp: int = 32, dib_size: int = None, magic: bytes = b"BM") -> bytes:
+    """A 32-bit BMP holding the RGBA image `rgba` (w*h*4 bytes, top row first). `pad` extra bytes sit between the
+    headers and the pixels (moves image_offset, e.g. to an odd address); the remaining arguments let tests break
+    individual header fields (decode_bmp.c:120-221)."""
+    import struct
+    assert len(rgba) == w * h * 4
+    px = np.frombuffer(rgba, np.uint8).reshape(h, w, 4) if w * h else np.zeros((0, 0, 4), np.uint8)
+    bgra = px[:, :, [2, 1, 0, 3]]
+    if bottom_up:
+        bgra = bgra[::-1]
+    dib = 108 if v4 else 40
+    offset = 14 + dib + pad
+    body = bgra.tobytes()
+    total = offset + len(body)
+    hdr = magic + struct.pack("<IHHI", total if bf_size is None else bf_size, 0, 0, offset)
+    info = struct.pack("<IiiHHIIIIII", dib if dib_size is None else dib_size, w, h if bottom_up else -h, planes, bpp,
+                       3 if v4 else 0, len(body), 0, 0, 0, 0)
+    if v4:
+        info += struct.pack("<IIII", 0x00ff0000, 0x0000ff00, 0x000000ff, 0xff000000) + b"BGRs" + bytes(48)
+    return hdr + info + bytes(pad) + body

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/debigulator_b200.h"
+#include "bmp_kernels.cuh"
 #include "kernels.cuh"
 #include "png_kernels.cuh"
 #include "split_kernels.cuh"
@@ -638,4 +639,153 @@ extern "C" int dbg_decode_png_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *con
     if (rc == DBG_OK)
         for (uint64_t i = 0; i < n; i++) good[i] = st[i] == 0 ? 1 : 0;
     return rc;
+}
+
+// ----------------------------------------------------------------------- BMP --
+// decode_bmp.c:105-372: header checks + BGRA <-> RGBA swizzle (bmp_kernels.cuh).
+static int bmp_launch(dbg_ctx *ctx, bool encode, dbg::BmpBatch b, cudaStream_t s)
+{
+    const uint64_t n = b.n;
+    CU(ctx->d_meta.reserve(n * sizeof(dbg::BmpItem) + (n + 1) * sizeof(uint32_t) + 64));
+    b.items = (dbg::BmpItem *)ctx->d_meta.p;
+    b.tile_base = (uint32_t *)(b.items + n);
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (encode) dbg::bmp_encode_plan_kernel<<<blocks, 128, 0, s>>>(b);
+    else dbg::bmp_decode_plan_kernel<<<blocks, 128, 0, s>>>(b);
+    dbg::bmp_scan_kernel<<<1, 1024, 0, s>>>(b.tile_base, b.n);
+    dbg::bmp_swizzle_kernel<<<(unsigned)ctx->sm_count * 8, dbg::BMP_THREADS, 0, s>>>(b);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return DBG_OK;
+}
+
+extern "C" int dbg_decode_bmp_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                           const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                                           const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_width,
+                                           uint32_t *d_height, uint32_t *d_status, void *stream)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!d_in || !d_in_off || !d_in_size || !d_out || !d_out_off || !d_out_cap || !d_out_size || !d_status ||
+        n > 0x7fffffffull) {
+        set_err(ctx, "dbg_decode_bmp_batch_device: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    dbg::BmpBatch b{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, d_width, d_height,
+                    (uint32_t)n, nullptr, nullptr};
+    return bmp_launch(ctx, false, b, s);
+}
+
+extern "C" int dbg_encode_bmp_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_rgba, const uint64_t *d_rgba_off,
+                                           const uint64_t *d_rgba_size, const uint32_t *d_width, const uint32_t *d_height,
+                                           uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_out_cap,
+                                           uint64_t *d_out_size, uint32_t *d_status, void *stream)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!d_rgba || !d_rgba_off || !d_rgba_size || !d_width || !d_height || !d_out || !d_out_off || !d_out_cap || !d_out_size ||
+        !d_status || n > 0x7fffffffull) {
+        set_err(ctx, "dbg_encode_bmp_batch_device: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    dbg::BmpBatch b{d_rgba, d_rgba_off, d_rgba_size, d_out, d_out_off, d_out_cap, d_out_size, d_status,
+                    const_cast<uint32_t *>(d_width), const_cast<uint32_t *>(d_height), (uint32_t)n, nullptr, nullptr};
+    return bmp_launch(ctx, true, b, s);
+}
+
+// Host-pointer front end shared by decode and encode: stage, run, scatter.
+static int bmp_host_batch(dbg_ctx *ctx, bool encode, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                          uint32_t *width, uint32_t *height, uint8_t *const *out, const uint64_t *out_cap,
+                          uint64_t *out_size, uint32_t *status)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!in || !in_size || !out || !out_cap || !status || (encode && (!width || !height)) || n > 0x7fffffffull) {
+        set_err(ctx, "BMP batch call: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    std::vector<uint64_t> in_off(n), out_off(n);
+    uint64_t ti = 0, to = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (in_size[i] && !in[i]) {
+            set_err(ctx, "BMP batch call: item %llu has a NULL input", (unsigned long long)i);
+            return DBG_ERR_ARG;
+        }
+        in_off[i] = ti;
+        ti += align_up(in_size[i] + 16, 16);
+        out_off[i] = to;
+        to += align_up(out_cap[i], 16);
+    }
+    // descriptors: in_off, in_size, out_off, out_cap, out_size (u64) | status, width, height (u32)
+    const size_t desc_bytes = n * (5 * 8 + 3 * 4);
+    CU(ctx->h_desc.reserve(desc_bytes));
+    CU(ctx->d_desc.reserve(desc_bytes));
+    CU(ctx->h_in.reserve(ti + 64));
+    CU(ctx->d_in.reserve(ti + 64));
+    CU(ctx->h_out.reserve(to + 64));
+    CU(ctx->d_out.reserve(to + 64));
+    uint64_t *hd = (uint64_t *)ctx->h_desc.p, *dd = (uint64_t *)ctx->d_desc.p;
+    uint32_t *h32 = (uint32_t *)(hd + 5 * n), *d32 = (uint32_t *)(dd + 5 * n);
+    memcpy(hd, in_off.data(), n * 8);
+    memcpy(hd + n, in_size, n * 8);
+    memcpy(hd + 2 * n, out_off.data(), n * 8);
+    memcpy(hd + 3 * n, out_cap, n * 8);
+    if (encode) {
+        memcpy(h32 + n, width, n * 4);
+        memcpy(h32 + 2 * n, height, n * 4);
+    }
+    uint8_t *hi = (uint8_t *)ctx->h_in.p;
+    for (uint64_t i = 0; i < n; i++) memcpy(hi + in_off[i], in[i], in_size[i]);
+    CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_in.p, hi, ti, cudaMemcpyHostToDevice, s));
+    int rc;
+    if (encode)
+        rc = dbg_encode_bmp_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, d32 + n, d32 + 2 * n,
+                                         (uint8_t *)ctx->d_out.p, dd + 2 * n, dd + 3 * n, dd + 4 * n, d32, s);
+    else
+        rc = dbg_decode_bmp_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p, dd + 2 * n,
+                                         dd + 3 * n, dd + 4 * n, d32 + n, d32 + 2 * n, d32, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hd + 4 * n, dd + 4 * n, n * 8 + 3 * n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, to, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (uint64_t i = 0; i < n; i++) {
+        status[i] = h32[i];
+        const uint64_t sz = hd[4 * n + i];
+        // encode reports one byte more than it writes (decode_bmp.c:311)
+        const uint64_t written = encode && sz ? sz - 1 : sz;
+        if (status[i] == 0 && out[i]) memcpy(out[i], (uint8_t *)ctx->h_out.p + out_off[i], written);
+        if (out_size) out_size[i] = sz;
+        if (!encode) {
+            if (width) width[i] = h32[n + i];
+            if (height) height[i] = h32[2 * n + i];
+        }
+    }
+    return DBG_OK;
+}
+
+extern "C" int dbg_decode_bmp_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                                    uint8_t *const *out_rgba, const uint64_t *rgba_cap, uint32_t *width, uint32_t *height,
+                                    uint8_t *good)
+{
+    if (!good) return DBG_ERR_ARG;
+    std::vector<uint32_t> st(n);
+    int rc = bmp_host_batch(ctx, false, n, in, in_size, width, height, out_rgba, rgba_cap, nullptr, st.data());
+    if (rc == DBG_OK)
+        for (uint64_t i = 0; i < n; i++) good[i] = st[i] == 0 ? 1 : 0;
+    return rc;
+}
+
+extern "C" int dbg_encode_bmp_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *rgba, const uint64_t *rgba_size,
+                                    const uint32_t *width, const uint32_t *height, uint8_t *const *out, const uint64_t *out_cap,
+                                    uint64_t *out_size, uint32_t *status)
+{
+    return bmp_host_batch(ctx, true, n, rgba, rgba_size, const_cast<uint32_t *>(width), const_cast<uint32_t *>(height), out,
+                          out_cap, out_size, status);
 }

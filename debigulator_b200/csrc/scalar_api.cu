@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "../../include/debigulator_b200.h"
+#include "../../include/decode_bmp.h"
 #include "../../include/decode_gz.h"
 #include "../../include/decode_png.h"
 #include "../../include/inflate.h"
@@ -179,4 +180,51 @@ extern "C" DecodedData *decode_gz(uint8_t *compressed_bytes, uint32_t compressed
     r->data_size = (uint32_t)sz[0];
     r->good = 1;
     return r;
+}
+
+// ----------------------------------------------------------------------- BMP --
+extern "C" void get_BMP_width_height(const uint8_t *raw_input, const uint64_t raw_input_size, uint32_t *out_width,
+                                     uint32_t *out_height, uint8_t *out_good)
+{
+    *out_good = 0;
+    if (!raw_input || raw_input_size < 54) return;  // the reference asserts (decode_bmp.c:69-80)
+    if (raw_input[0] != 'B' || raw_input[1] != 'M') return;  // :84-99 (width / height left untouched)
+    int32_t w, h;
+    memcpy(&w, raw_input + 18, 4);
+    memcpy(&h, raw_input + 22, 4);
+    *out_height = (uint32_t)(h < 0 ? -(int64_t)h : h);  // :101-105
+    *out_width = (uint32_t)w;
+    *out_good = *out_width > 0 && *out_height > 0;
+}
+
+extern "C" void decode_BMP(const uint8_t *raw_input, const uint64_t raw_input_size, uint8_t *out_rgba_values,
+                           const int64_t out_rgba_values_size, uint8_t *out_good)
+{
+    if (!out_good) return;
+    *out_good = 0;
+    if (!raw_input || !out_rgba_values || out_rgba_values_size < 0) return;
+    dbg_ctx *ctx = slot_ctx(0);
+    if (!ctx) return;
+    const uint8_t *in[1] = {raw_input};
+    uint8_t *out[1] = {out_rgba_values};
+    uint64_t in_size[1] = {raw_input_size}, cap[1] = {(uint64_t)out_rgba_values_size};
+    uint8_t good[1] = {0};
+    if (dbg_decode_bmp_batch(ctx, 1, in, in_size, out, cap, nullptr, nullptr, good) != DBG_OK) return;
+    *out_good = good[0];
+}
+
+extern "C" void encode_BMP(const uint8_t *rgba, const uint64_t rgba_size, const uint32_t width, const uint32_t height,
+                           char *recipient, uint32_t *recipient_size, const int64_t recipient_capacity)
+{
+    if (!recipient_size) return;
+    *recipient_size = 0;
+    if (!rgba || !recipient || recipient_capacity < 0) return;
+    dbg_ctx *ctx = slot_ctx(0);
+    if (!ctx) return;
+    const uint8_t *in[1] = {rgba};
+    uint8_t *out[1] = {(uint8_t *)recipient};
+    uint64_t in_size[1] = {rgba_size}, cap[1] = {(uint64_t)recipient_capacity}, sz[1] = {0};
+    uint32_t w[1] = {width}, h[1] = {height}, st[1] = {0};
+    if (dbg_encode_bmp_batch(ctx, 1, in, in_size, w, h, out, cap, sz, st) != DBG_OK || st[0]) return;
+    *recipient_size = (uint32_t)sz[0];
 }

@@ -147,6 +147,30 @@ int dbg_set_verify(dbg_ctx *ctx, int on);
 int dbg_profile_enable(dbg_ctx *ctx, int on);
 int dbg_profile_read(dbg_ctx *ctx, double *total_ms, uint64_t *launches);
 
+/* ---- BMP (decode_bmp.h:14-36; decode_bmp.c:105-372) --------------------------
+ * 32-bit BGRA BMP <-> RGBA8, the reference's decode_BMP / encode_BMP batched. Decode accepts what the
+ * reference accepts ('BM', 40- or 108-byte DIB header, 1 plane, 32 bpp, either row order) and writes
+ * w*h*4 bytes (out_size); inputs the reference would read or write out of bounds on are rejected
+ * instead (DBG_ST_TRUNCATED / DBG_ST_OUT_OVERFLOW / DBG_ST_TOO_LARGE). Encode writes the 54 header
+ * bytes + swizzled pixels and reports 54 + rgba_size + 1 like the reference (the last byte is never
+ * written); rgba_size must be a multiple of 4 and out_cap at least the reported size.
+ * width / height of dbg_decode_bmp_batch may be NULL. */
+int dbg_decode_bmp_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *in, const uint64_t *in_size,
+                         uint8_t *const *out_rgba, const uint64_t *rgba_cap, uint32_t *width, uint32_t *height,
+                         uint8_t *good);
+int dbg_encode_bmp_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *const *rgba, const uint64_t *rgba_size,
+                         const uint32_t *width, const uint32_t *height, uint8_t *const *out, const uint64_t *out_cap,
+                         uint64_t *out_size, uint32_t *status);
+/* Device-resident forms (d_width / d_height of the decode may be NULL). */
+int dbg_decode_bmp_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
+                                const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_width,
+                                uint32_t *d_height, uint32_t *d_status, void *stream);
+int dbg_encode_bmp_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_rgba, const uint64_t *d_rgba_off,
+                                const uint64_t *d_rgba_size, const uint32_t *d_width, const uint32_t *d_height,
+                                uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_out_cap,
+                                uint64_t *d_out_size, uint32_t *d_status, void *stream);
+
 /* Blocks until everything the context enqueued on its own stream is done. */
 int dbg_synchronize(dbg_ctx *ctx);
 

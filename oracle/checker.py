@@ -34,3 +34,11 @@ def decode_gz(data: bytes, cap: int):
 
 def decode_png(data: bytes):
     return _impl().decode_png(data)
+
+
+def decode_bmp(data: bytes, out_size: int = None):
+    return _impl().decode_bmp(data, out_size)
+
+
+def encode_bmp(rgba: bytes, w: int, h: int):
+    return _impl().encode_bmp(rgba, w, h)

@@ -456,3 +456,89 @@ done:
     free(z);
     free(scan);
 }
+
+/* ------------------------------------------------------------------- BMP --
+ * decode_bmp.c:53-103 (get_BMP_width_height), :105-295 (decode_BMP), :297-372
+ * (encode_BMP), release semantics (asserts off). Where the reference reads or
+ * writes out of bounds (undefined behaviour) this restatement reports good = 0,
+ * exactly like the product; those inputs are outside the parity domain. */
+static uint32_t bmp_u32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint32_t bmp_u16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+void oracle_bmp_dims(const uint8_t *in, uint64_t size, uint32_t *w, uint32_t *h, uint8_t *good)
+{
+    *good = 0;
+    if (size < 54) return;                      /* asserted in the reference (:69-80) */
+    if (in[0] != 'B' || in[1] != 'M') return;   /* :84-99 */
+    int32_t width = (int32_t)bmp_u32(in + 18), height = (int32_t)bmp_u32(in + 22);
+    *h = (uint32_t)(height < 0 ? -(int64_t)height : height); /* :101-105 */
+    *w = (uint32_t)width;
+    *good = *w > 0 && *h > 0;
+}
+
+void oracle_decode_bmp(const uint8_t *in, uint64_t size, uint8_t *out, int64_t out_size, uint8_t *good)
+{
+    *good = 0;
+    if (size < 54 || out_size < 0) return;
+    if (in[0] != 'B' || in[1] != 'M') return;                                /* :120-133 */
+    uint32_t bf_size = bmp_u32(in + 2), image_offset = bmp_u32(in + 10);
+    if ((uint64_t)(uint32_t)(image_offset + bf_size) + 14 < size) return;    /* :135-150: file longer than declared */
+    uint32_t dib = bmp_u32(in + 14);
+    if (dib != 40 && dib != 108) return;                                     /* :158-178 */
+    int32_t width = (int32_t)bmp_u32(in + 18), height = (int32_t)bmp_u32(in + 22);
+    int bottom_first = 1;
+    if (height < 0) {                                                        /* :180-186 */
+        bottom_first = 0;
+        if (height == INT32_MIN) return;
+        height = -height;
+    }
+    /* :188-202 compares w*h*4 with out_size but the verdict is overwritten by :293 */
+    if (bmp_u16(in + 26) != 1) return;                                       /* :204-211 */
+    if (bmp_u16(in + 28) != 32) return;                                      /* :213-221 */
+    /* :223-258 compression / resolution / palette counts: no effect (see :293) */
+    if (width < 0) return;                                                   /* UB domain */
+    uint64_t need = (uint64_t)(uint32_t)width * (uint32_t)height * 4;
+    if (need > 0xffffffffull || need > (uint64_t)out_size || (uint64_t)image_offset + need > size) return; /* UB domain */
+    uint32_t w = (uint32_t)width, h = (uint32_t)height;
+    for (uint32_t y = 0; y < h; y++) {                                       /* :260-291 */
+        uint32_t ty = bottom_first ? h - y - 1 : y;
+        const uint8_t *s = in + image_offset + (uint64_t)y * 4 * w;
+        uint8_t *d = out + (uint64_t)ty * 4 * w;
+        for (uint32_t x = 0; x < w; x++) {
+            d[4 * x + 0] = s[4 * x + 2];
+            d[4 * x + 1] = s[4 * x + 1];
+            d[4 * x + 2] = s[4 * x + 0];
+            d[4 * x + 3] = s[4 * x + 3];
+        }
+    }
+    *good = 1;                                                               /* :293 */
+}
+
+void oracle_encode_bmp(const uint8_t *rgba, uint64_t rgba_size, uint32_t w, uint32_t h, uint8_t *out,
+                       uint32_t *out_size, int64_t cap)
+{
+    *out_size = 0;
+    uint64_t total = 14 + 40 + rgba_size + 1;                                /* :311 */
+    if ((rgba_size & 3) || cap < 0 || total > (uint64_t)cap || total > 0xffffffffull) return; /* UB domain */
+    *out_size = (uint32_t)total;
+    uint8_t hd[54];
+    memset(hd, 0, sizeof hd);
+#define PUT32(at, v) do { uint32_t v_ = (v); hd[at] = (uint8_t)v_; hd[(at) + 1] = (uint8_t)(v_ >> 8); hd[(at) + 2] = (uint8_t)(v_ >> 16); hd[(at) + 3] = (uint8_t)(v_ >> 24); } while (0)
+    hd[0] = 'B'; hd[1] = 'M';                                                /* :315-326 */
+    PUT32(2, w * h * 4 + 54);
+    PUT32(10, 54);
+    PUT32(14, 40);                                                           /* :333-347 */
+    PUT32(18, w);
+    PUT32(22, (uint32_t)(-(int32_t)h));
+    hd[26] = 1;
+    hd[28] = 32;
+    PUT32(34, w * h * 4);
+#undef PUT32
+    memcpy(out, hd, 54);
+    for (uint64_t i = 0; i < rgba_size; i += 4) {                            /* :354-364 */
+        out[54 + i + 0] = rgba[i + 2];
+        out[54 + i + 1] = rgba[i + 1];
+        out[54 + i + 2] = rgba[i + 0];
+        out[54 + i + 3] = rgba[i + 3];
+    }
+}
