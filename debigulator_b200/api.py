@@ -53,6 +53,8 @@ def load_library():
     L.dbg_profile_enable.restype = i32
     L.dbg_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     L.dbg_profile_read.restype = i32
+    L.dbg_bsplit_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.dbg_bsplit_stats.restype = i32
     L.dbg_synchronize.argtypes = [vp]
     L.dbg_synchronize.restype = i32
     for name in ("dbg_inflate_batch", "dbg_decode_gz_batch"):
@@ -156,6 +158,12 @@ class Context:
         ms, n = C.c_double(0), C.c_uint64(0)
         self._check(self.L.dbg_profile_read(self.h, C.byref(ms), C.byref(n)), "dbg_profile_read")
         return float(ms.value), int(n.value)
+
+    def bsplit_stats(self):
+        """(streams decoded by the block-split path, streams handed back to the warp-per-stream kernel)."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.L.dbg_bsplit_stats(self.h, C.byref(a), C.byref(b)), "dbg_bsplit_stats")
+        return int(a.value), int(b.value)
 
     def synchronize(self):
         self._check(self.L.dbg_synchronize(self.h), "dbg_synchronize")

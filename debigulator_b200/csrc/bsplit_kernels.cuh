@@ -1,0 +1,222 @@
+// bsplit_kernels.cuh -- __global__ wrappers of the block-split path (bsplit_core.h): chunk-parallel
+// decode of long multi-block DEFLATE streams. Shares the cell -> byte resolve kernels with the
+// split-stream path (split_kernels.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bsplit_core.h"
+#include "split_kernels.cuh"
+
+namespace dbg {
+
+constexpr uint64_t BS_MIN_BYTES = 4 * (uint64_t)REGION_BYTES;  // shorter streams never take this path
+constexpr int BS_WARPS_PER_CTA = 4;
+
+struct BsSummary {         // device -> host after classify, and again after chain
+    uint32_t n_split;
+    uint32_t total_regions;
+    uint64_t total_in;     // compressed bytes of the whole batch
+    uint64_t cells_used;   // exact number of 16-bit cells (bs_chain_kernel)
+    uint32_t n_fallback;   // streams whose chain did not close
+    uint32_t pad;
+};
+
+struct BsBatch {
+    const uint8_t *in_base;
+    const uint64_t *in_off;
+    const uint64_t *in_size;
+    uint8_t *out_base;
+    const uint64_t *out_off;
+    const uint64_t *out_cap;
+    uint64_t *out_size;
+    uint32_t *status;
+    const uint32_t *pre_status;  // optional
+    const uint32_t *taken;       // optional: streams already handled by the split-stream path
+    uint32_t n;
+    uint32_t resident_warps;     // streams the warp-per-stream kernel keeps in flight
+    uint64_t min_bytes;          // lower bound of the split threshold
+    BsSummary *summary;
+    uint32_t *flag;         // per stream: 1 = block-split path
+    uint32_t *chunk_base;   // per stream: first region index
+    uint32_t *nchunks;      // per stream: regions
+    uint64_t *cell_base;    // per stream
+    uint32_t *chunk_stream; // per region
+    uint64_t *cand;         // per region: hinted block start (stream bit) or BS_NONE
+    uint64_t *exit_bits;    // per region: where its decode ended (count pass)
+    uint64_t *c_out_off;    // per region: output offset inside the stream
+    uint32_t *c_out_len;    // per region
+    uint32_t *c_flag;       // per region
+    uint16_t *cells;
+};
+
+__global__ void bs_sum_kernel(BsBatch b)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t v = s < b.n ? b.in_size[s] : 0;
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd((unsigned long long *)&b.summary->total_in, (unsigned long long)v);
+}
+
+// A stream is split when one warp would need clearly longer for it than the whole batch needs when
+// it is spread evenly over the resident warps: compressed size > 2 x (batch bytes / resident warps).
+__global__ void bs_classify_kernel(BsBatch b)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n) return;
+    const uint64_t size = b.in_size[s], cap = b.out_cap[s];
+    uint64_t thr = 2 * (b.summary->total_in / b.resident_warps);
+    if (thr < b.min_bytes) thr = b.min_bytes;
+    uint32_t flag = 0;
+    const bool ok = (!b.pre_status || b.pre_status[s] == 0) && (!b.taken || b.taken[s] == 0) && size >= thr && cap >= size &&
+                    size < (1ull << 31) && cap < (1ull << 32) - 1024;
+    if (ok) {
+        flag = 1;
+        const uint32_t nreg = (uint32_t)((size + REGION_BYTES - 1) / REGION_BYTES);
+        b.chunk_base[s] = atomicAdd(&b.summary->total_regions, nreg);
+        b.nchunks[s] = nreg;
+        atomicAdd(&b.summary->n_split, 1u);
+    }
+    b.flag[s] = flag;
+}
+
+__global__ void bs_fill_kernel(BsBatch b)
+{
+    const uint32_t s = blockIdx.x;
+    if (!b.flag[s]) return;
+    const uint32_t nch = b.nchunks[s], base = b.chunk_base[s];
+    for (uint32_t c = threadIdx.x; c < nch; c += blockDim.x) b.chunk_stream[base + c] = s;
+}
+
+// Hints: one warp per region.
+__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_search_kernel(BsBatch b, uint32_t total_regions)
+{
+    __shared__ uint16_t kraft12[4096];
+    __shared__ SearchSmem qs[BS_WARPS_PER_CTA];
+    build_kraft12(kraft12, threadIdx.x, blockDim.x);
+    __syncthreads();
+    SearchSmem *q = &qs[threadIdx.x >> 5];
+    const uint32_t warps = gridDim.x * BS_WARPS_PER_CTA;
+    for (uint32_t t = blockIdx.x * BS_WARPS_PER_CTA + (threadIdx.x >> 5); t < total_regions; t += warps) {
+        const uint32_t s = b.chunk_stream[t], c = t - b.chunk_base[s];
+        uint64_t cand = 0;
+        if (c) cand = find_block_start(q, kraft12, b.in_base + b.in_off[s], b.in_size[s], (uint64_t)c * REGION_BYTES * 8,
+                                       (uint64_t)(c + 1) * REGION_BYTES * 8);
+        if (simt::lane() == 0) b.cand[t] = cand;
+        simt::syncwarp();
+    }
+}
+
+__device__ __forceinline__ uint64_t bs_next_hint(const BsBatch &b, uint32_t s, uint32_t t)
+{
+    const uint32_t end = b.chunk_base[s] + b.nchunks[s];
+    for (uint32_t u = t + 1; u < end; u++)
+        if (b.cand[u] != BS_NONE) return b.cand[u];
+    return BS_NONE;
+}
+
+// Sizes: one warp per hinted region decodes to the first block boundary at or past the next hint.
+__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_count_kernel(BsBatch b, uint32_t total_regions)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
+    const uint32_t warps = gridDim.x * BS_WARPS_PER_CTA;
+    for (uint32_t t = blockIdx.x * BS_WARPS_PER_CTA + (threadIdx.x >> 5); t < total_regions; t += warps) {
+        const uint64_t start = b.cand[t];
+        if (start == BS_NONE) continue;
+        const uint32_t s = b.chunk_stream[t];
+        const ChunkResult r = decode_block_chunk<SINK_COUNT>(sm, b.in_base + b.in_off[s], b.in_size[s], start, bs_next_hint(b, s, t),
+                                                             nullptr, 0, 0);
+        if (simt::lane() == 0) {
+            b.exit_bits[t] = r.exit_bits;
+            b.c_out_len[t] = r.out_bytes;
+            b.c_flag[t] = r.flag;
+        }
+        simt::syncwarp();
+    }
+}
+
+// One thread per stream: does every chunk end exactly on the next hint?
+__global__ void bs_chain_kernel(BsBatch b)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n || !b.flag[s]) return;
+    const uint32_t nch = b.nchunks[s], base = b.chunk_base[s];
+    const uint64_t cap = b.out_cap[s];
+    uint64_t pos = 0, expected = 0;
+    uint32_t st = ST_OK;
+    bool ended = false, fail = false;
+    for (uint32_t c = 0; c < nch; c++) {
+        const uint32_t t = base + c;
+        const uint64_t cand = b.cand[t];
+        const uint32_t len = b.c_out_len[t], flag = b.c_flag[t];
+        b.c_out_off[t] = pos;
+        if (cand == BS_NONE || ended || fail) {
+            b.c_flag[t] = CH_IDLE;
+            b.c_out_len[t] = 0;
+            continue;
+        }
+        if (cand != expected) {  // the previous chunk stepped over this hint: not a block boundary
+            fail = true;
+            b.c_flag[t] = CH_IDLE;
+            b.c_out_len[t] = 0;
+            continue;
+        }
+        if (flag >= CH_ERR) {
+            // the sequential decoder reports whichever comes first: the overflow or the error
+            st = pos + len > cap ? (uint32_t)ST_OUT_OVERFLOW : flag - CH_ERR;
+            ended = true;
+            b.c_flag[t] = CH_IDLE;
+            b.c_out_len[t] = 0;
+            continue;
+        }
+        pos += len;
+        if (pos > cap) {
+            st = ST_OUT_OVERFLOW;
+            ended = true;
+        } else if (flag != CH_RUN) {
+            ended = true;
+        } else {
+            expected = b.exit_bits[t];
+        }
+    }
+    if (!ended) fail = true;  // cannot happen: the last hinted chunk runs to the end of the stream
+    if (fail) {
+        // hand the stream back to the warp-per-stream kernel
+        for (uint32_t c = 0; c < nch; c++) {
+            b.c_flag[base + c] = CH_IDLE;
+            b.c_out_len[base + c] = 0;
+        }
+        b.flag[s] = 0;
+        b.cell_base[s] = 0;
+        atomicAdd(&b.summary->n_fallback, 1u);
+        return;
+    }
+    b.status[s] = st;
+    b.out_size[s] = st == ST_OK ? pos : 0;
+    b.cell_base[s] = st == ST_OK ? atomicAdd((unsigned long long *)&b.summary->cells_used, (unsigned long long)pos) : 0;
+}
+
+// Chunk decode into 16-bit cells: one warp per hinted region.
+__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_decode_kernel(BsBatch b, uint32_t total_regions)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
+    const uint32_t warps = gridDim.x * BS_WARPS_PER_CTA;
+    for (uint32_t t = blockIdx.x * BS_WARPS_PER_CTA + (threadIdx.x >> 5); t < total_regions; t += warps) {
+        const uint32_t s = b.chunk_stream[t];
+        if (!b.flag[s] || b.status[s] != ST_OK || b.c_flag[t] == CH_IDLE) continue;
+        const uint64_t stop = b.c_flag[t] == CH_RUN ? b.exit_bits[t] : BS_NONE;
+        const ChunkResult r = decode_block_chunk<SINK_U16>(sm, b.in_base + b.in_off[s], b.in_size[s], b.cand[t], stop,
+                                                           b.cells + b.cell_base[s] + b.c_out_off[t], b.c_out_len[t], b.c_out_off[t]);
+        if (simt::lane() == 0) {
+            uint32_t st = ST_OK;
+            if (r.flag >= CH_ERR) st = r.flag - CH_ERR;  // e.g. a distance reaching before the stream start
+            else if (r.out_bytes != b.c_out_len[t] || r.flag != b.c_flag[t]) st = ST_BAD_CODE;  // cannot happen: same decode twice
+            if (st) atomicMax(&b.status[s], st);
+        }
+        simt::syncwarp();
+    }
+}
+
+}  // namespace dbg

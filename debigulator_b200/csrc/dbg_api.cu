@@ -16,6 +16,7 @@
 
 #include "../../include/debigulator_b200.h"
 #include "bmp_kernels.cuh"
+#include "bsplit_kernels.cuh"
 #include "kernels.cuh"
 #include "png_kernels.cuh"
 #include "split_kernels.cuh"
@@ -72,6 +73,11 @@ struct dbg_ctx {
     Buf d_meta;                    // derived descriptors (gzip payloads, PNG streams)
     Buf d_png_scratch;             // compacted IDAT + filtered scanlines
     Buf d_split, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
+    // block-split path (long multi-block streams): per wave slot, since waves run concurrently
+    Buf d_bs_stream[MAX_WAVES], d_bs_region[MAX_WAVES], d_bs_cells[MAX_WAVES], h_bs_summary[MAX_WAVES];
+    bool bsplit = true;
+    uint64_t bsplit_min_bytes = dbg::BS_MIN_BYTES;
+    uint64_t bs_streams = 0, bs_fallbacks = 0;  // counters: streams that took the block-split path / were handed back
     uint32_t split_max_streams = 1536;  // batches with fewer streams may use the split-stream path (measured crossover ~1,500 images of 1024^2)
     bool verify = false;                // opt-in: check gzip CRC32 / ISIZE trailers
     uint32_t inflate_ctas_per_sm = dbg::INFLATE_CTAS_PER_SM;  // resident streams per SM = 4x this (tunable: L2 footprint)
@@ -81,6 +87,7 @@ struct dbg_ctx {
     dbg_ctx()
     {
         h_in.pinned_host = h_out.pinned_host = h_desc.pinned_host = h_summary.pinned_host = true;
+        for (int k = 0; k < MAX_WAVES; k++) h_bs_summary[k].pinned_host = true;
     }
 };
 
@@ -158,6 +165,8 @@ extern "C" dbg_ctx *dbg_create(int device)
     cudaFuncSetAttribute(dbg::split_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA));
     if (const char *e = getenv("DBG_SPLIT_MAX_STREAMS")) ctx->split_max_streams = (uint32_t)atoi(e);
+    if (const char *e = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(e) != 0;
+    if (const char *e = getenv("DBG_BSPLIT_MIN_BYTES")) ctx->bsplit_min_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 2 * dbg::REGION_BYTES);
     if (const char *e = getenv("DBG_INFLATE_CTAS_PER_SM")) {
         int v = atoi(e);
         if (v >= 1 && v <= dbg::INFLATE_CTAS_PER_SM) ctx->inflate_ctas_per_sm = (uint32_t)v;
@@ -173,11 +182,24 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
     Buf *all[] = {&ctx->d_counter, &ctx->d_meta, &ctx->d_png_scratch, &ctx->d_in,    &ctx->d_out,    &ctx->d_desc,
                   &ctx->h_in,      &ctx->h_out,  &ctx->h_desc,        &ctx->d_split, &ctx->d_cells, &ctx->h_summary};
     for (Buf *b : all) b->release();
-    for (int i = 0; i < dbg_ctx::MAX_WAVES; i++)
+    for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) {
+        ctx->d_bs_stream[i].release();
+        ctx->d_bs_region[i].release();
+        ctx->d_bs_cells[i].release();
+        ctx->h_bs_summary[i].release();
         if (ctx->wave_stream[i]) cudaStreamDestroy(ctx->wave_stream[i]);
+    }
     if (ctx->wave_ready) cudaEventDestroy(ctx->wave_ready);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int dbg_bsplit_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *fallbacks)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (streams) *streams = ctx->bs_streams;
+    if (fallbacks) *fallbacks = ctx->bs_fallbacks;
+    return DBG_OK;
 }
 
 extern "C" int dbg_set_verify(dbg_ctx *ctx, int on)
@@ -258,7 +280,7 @@ static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, c
     const uint32_t n = a.n;
     CU(ctx->h_summary.reserve(sizeof(dbg::SplitSummary)));
     // per-stream scratch first; per-chunk scratch once the chunk count is known
-    size_t per_stream = (size_t)n * (4 + 4 + 8) + 256;
+    size_t per_stream = (size_t)n * (4 + 4 + 4 + 8) + 256;
     CU(ctx->d_split.reserve(per_stream + sizeof(dbg::SplitSummary) + 256));
     uint8_t *p = (uint8_t *)ctx->d_split.p;
     dbg::SplitBatch b{};
@@ -269,6 +291,7 @@ static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, c
     b.cell_base = (uint64_t *)(p + 256);
     b.split_flag = (uint32_t *)(b.cell_base + n);
     b.chunk_base = b.split_flag + n;
+    b.nchunks = b.chunk_base + n;
     CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::SplitSummary), s));
     dbg::split_classify_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);
     ctx->launches++;
@@ -288,6 +311,7 @@ static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, c
         b.cell_base = (uint64_t *)(p + 256);
         b.split_flag = (uint32_t *)(b.cell_base + n);
         b.chunk_base = b.split_flag + n;
+        b.nchunks = b.chunk_base + n;
         CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::SplitSummary), s));
         dbg::split_classify_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);  // same inputs, same decisions
         ctx->launches++;
@@ -317,20 +341,96 @@ static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, c
     return DBG_OK;
 }
 
-static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s)
+// Block-split path for the long streams of a batch (bsplit_kernels.cuh). Two small device->host reads:
+// how many regions, then how many cells. `taken` marks streams the split-stream path already owns.
+static int run_bsplit(dbg_ctx *ctx, int slot, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t *taken,
+                      const uint32_t **skip_out)
+{
+    *skip_out = nullptr;
+    const uint32_t n = a.n;
+    Buf &bs = ctx->d_bs_stream[slot], &br = ctx->d_bs_region[slot], &bc = ctx->d_bs_cells[slot], &hsb = ctx->h_bs_summary[slot];
+    CU(hsb.reserve(sizeof(dbg::BsSummary)));
+    CU(bs.reserve(256 + (size_t)n * (8 + 4 + 4 + 4) + 256));
+    uint8_t *p = (uint8_t *)bs.p;
+    dbg::BsBatch b{};
+    b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
+    b.out_base = a.out_base; b.out_off = a.out_off; b.out_cap = a.out_cap;
+    b.out_size = a.out_size; b.status = a.status; b.pre_status = a.pre_status; b.taken = taken; b.n = n;
+    b.resident_warps = (uint32_t)ctx->sm_count * ctx->inflate_ctas_per_sm * dbg::INFLATE_WARPS_PER_CTA;
+    b.min_bytes = ctx->bsplit_min_bytes;
+    b.summary = (dbg::BsSummary *)p;
+    b.cell_base = (uint64_t *)(p + 256);
+    b.flag = (uint32_t *)(b.cell_base + n);
+    b.chunk_base = b.flag + n;
+    b.nchunks = b.chunk_base + n;
+    const unsigned sb = (n + 127) / 128;
+    CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::BsSummary), s));
+    dbg::bs_sum_kernel<<<sb, 128, 0, s>>>(b);
+    dbg::bs_classify_kernel<<<sb, 128, 0, s>>>(b);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    dbg::BsSummary *hs = (dbg::BsSummary *)hsb.p;
+    CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::BsSummary), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (hs->n_split == 0) return DBG_OK;
+    const uint32_t T = hs->total_regions;
+    CU(br.reserve((size_t)T * (4 + 8 + 8 + 8 + 4 + 4) + 256));
+    b.cand = (uint64_t *)br.p;
+    b.exit_bits = b.cand + T;
+    b.c_out_off = b.exit_bits + T;
+    b.chunk_stream = (uint32_t *)(b.c_out_off + T);
+    b.c_out_len = b.chunk_stream + T;
+    b.c_flag = b.c_out_len + T;
+    const size_t smem = sizeof(dbg::InflateSmem) * dbg::BS_WARPS_PER_CTA;
+    const uint32_t grid = std::min<uint32_t>((T + dbg::BS_WARPS_PER_CTA - 1) / dbg::BS_WARPS_PER_CTA,
+                                             (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);
+    dbg::bs_fill_kernel<<<n, 128, 0, s>>>(b);
+    dbg::bs_search_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, 0, s>>>(b, T);
+    dbg::bs_count_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b, T);
+    dbg::bs_chain_kernel<<<sb, 128, 0, s>>>(b);
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::BsSummary), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    ctx->bs_streams += hs->n_split - hs->n_fallback;
+    ctx->bs_fallbacks += hs->n_fallback;
+    *skip_out = b.flag;
+    if (hs->cells_used == 0) return DBG_OK;
+    CU(bc.reserve((size_t)hs->cells_used * 2 + 256));
+    b.cells = (uint16_t *)bc.p;
+    dbg::bs_decode_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b, T);
+    // cells -> bytes with the split-stream path's resolve kernels
+    dbg::SplitBatch r{};
+    r.out_base = a.out_base; r.out_off = a.out_off; r.out_size = a.out_size; r.status = a.status; r.n = n;
+    r.split_flag = b.flag; r.chunk_base = b.chunk_base; r.nchunks = b.nchunks; r.cell_base = b.cell_base;
+    r.chunk_stream = b.chunk_stream; r.c_out_off = b.c_out_off; r.c_out_len = b.c_out_len; r.c_flag = b.c_flag;
+    r.cells = b.cells;
+    dbg::split_resolve_tails_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(r);
+    dbg::split_resolve_body_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(r, T);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return DBG_OK;
+}
+
+static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot = 0)
 {
     a.skip = nullptr;
-    if (a.n < ctx->split_max_streams) {
+    a.skip2 = nullptr;
+    if (a.n < ctx->split_max_streams && slot == 0) {
         const uint32_t *skip = nullptr;
         int rc = run_split(ctx, a, s, &skip);
         if (rc) return rc;
         a.skip = skip;
     }
+    if (ctx->bsplit) {
+        const uint32_t *skip2 = nullptr;
+        int rc = run_bsplit(ctx, slot, a, s, a.skip, &skip2);
+        if (rc) return rc;
+        a.skip2 = skip2;
+    }
     return launch_inflate_plain(ctx, a, d_counter, s);
 }
 
-// `slot` selects an independent work-queue counter / descriptor scratch so that
-// several waves of one host batch can be in flight on different streams.
 static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                                const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
                                const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
@@ -343,8 +443,8 @@ static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t
         dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, gz_off, gz_size, gz_pre);
         ctx->launches++;
         CU(cudaGetLastError());
-        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, d_order, nullptr, (uint32_t)n};
-        int rc = launch_inflate(ctx, a, counter, s);
+        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
+        int rc = launch_inflate(ctx, a, counter, s, slot);
         if (rc || !ctx->verify) return rc;
         uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
         dbg::gz_verify_kernel<<<ctas, dbg::SCAN_WARPS * 32, 0, s>>>(d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_size, d_status,
@@ -353,8 +453,8 @@ static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t
         CU(cudaGetLastError());
         return DBG_OK;
     }
-    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
-    return launch_inflate(ctx, a, counter, s);
+    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
+    return launch_inflate(ctx, a, counter, s, slot);
 }
 
 extern "C" int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -427,7 +527,7 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
     // 2. inflate the compacted zlib payloads into the filtered-scanline buffers
     // z_off holds absolute addresses: a single-IDAT image is inflated straight from the file
     dbg::InflateBatch a{nullptr, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
-                        lay.pre_status, nullptr, nullptr, nullptr, (uint32_t)n};
+                        lay.pre_status, nullptr, nullptr, nullptr, nullptr, (uint32_t)n};
     rc = launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
     if (rc) return rc;
     if (ctx->verify) {

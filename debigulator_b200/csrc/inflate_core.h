@@ -738,6 +738,70 @@ DBG_DEV StreamIn open_stream(Window &w, InflateSmem *sm, const uint8_t *in, uint
     return g;
 }
 
+// Stored block payload into 16-bit cells (split paths).
+DBG_DEV void copy_stored_u16(uint16_t *dst, const uint8_t *src, uint32_t len)
+{
+    for (uint32_t i = (uint32_t)simt::lane(); i < len; i += 32) dst[i] = src[i];
+}
+
+// The block loop of inflate() (inflate.c:896-1950): decodes blocks from the window position, which
+// must be a block header, until the final block has ended (BLK_FINAL), rule Q2 ended the stream
+// (BLK_Q2), or a block boundary at or past ring-coordinate bit `stop_bit` has been reached (BLK_STOP,
+// used by the block-split path; ~0 = never).
+enum { BLK_FINAL = 0, BLK_Q2 = 1, BLK_STOP = 2 };
+template <int SINK>
+DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, Sink &k, uint64_t stop_bit, uint32_t &end)
+{
+    BlockTables bt;
+    bt.lit_max = bt.dist_max = 0;
+    end = BLK_FINAL;
+    for (;;) {
+        if (w.abs_bits() >= stop_bit) {
+            end = BLK_STOP;
+            return ST_OK;
+        }
+        if (w.abs_bits() >= 8 * g.end_byte) return ST_TRUNCATED;
+        const uint32_t hdr = w.peek32() & 7;
+        w.consume(3);
+        const bool more = !(hdr & 1);
+        const uint32_t btype = hdr >> 1;
+        if (btype == 0) {
+            w.consume((0u - w.s) & 7);  // to the next byte boundary (32*wb is byte aligned)
+            const uint32_t v = w.peek32();
+            const uint32_t len = v & 0xffff, nlen = v >> 16;
+            w.consume(32);
+            if (len != (~nlen & 0xffff)) return ST_STORED_LEN;
+            if (len) {
+                const uint64_t bytepos = w.abs_bits() >> 3;
+                if (bytepos + len > g.end_byte) return ST_TRUNCATED;
+                if (SINK != SINK_COUNT) {
+                    if ((uint64_t)k.pos + len > k.cap) return ST_OUT_OVERFLOW;
+                    if (SINK == SINK_BYTES) {
+                        copy_stored(k.out + k.pos, w.base + bytepos, len);
+                    } else {
+                        flush_pending16(k.pd);
+                        copy_stored_u16(k.out16 + k.pos, w.base + bytepos, len);
+                        simt::syncwarp();
+                    }
+                }
+                k.pos += len;
+                w.seek(bytepos + len);
+            }
+        } else if (btype != 3) {  // btype 3: inflate.c:990-998, ignored in the no-assert build
+            uint32_t st = read_huffman_tables(w, sm, btype, bt);
+            if (st) return st;
+            uint32_t why = END_EOB;
+            st = decode_symbols<SINK>(w, sm, bt, k, why);
+            if (st) return st;
+            if (why == END_LIMIT) {  // rule Q2
+                end = BLK_Q2;
+                return ST_OK;
+            }
+        }
+        if (!more) return ST_OK;
+    }
+}
+
 // Decodes one raw DEFLATE stream of `in_size` bytes at `in` into out[0..cap).
 // Every lane of the warp must call it with identical arguments; the return
 // value and *final_size are uniform. `in` may have any alignment; bytes from
@@ -763,39 +827,9 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     k.pd.ptr = out;
     k.pd.val = 0;
     k.pd.on = false;
-    BlockTables bt;
-    bt.lit_max = bt.dist_max = 0;
-    bool more = true;
-    while (more) {
-        if (w.abs_bits() >= 8 * g.end_byte) return ST_TRUNCATED;
-        uint32_t hdr = w.peek32() & 7;
-        w.consume(3);
-        if (hdr & 1) more = false;
-        uint32_t btype = hdr >> 1;
-        if (btype == 0) {
-            w.consume((0u - w.s) & 7);  // to the next byte boundary (32*wb is byte aligned)
-            uint32_t v = w.peek32();
-            uint32_t len = v & 0xffff, nlen = v >> 16;
-            w.consume(32);
-            if (len != (~nlen & 0xffff)) return ST_STORED_LEN;
-            if (len) {
-                uint64_t bytepos = w.abs_bits() >> 3;
-                if (bytepos + len > g.end_byte) return ST_TRUNCATED;
-                if ((uint64_t)k.pos + len > k.cap) return ST_OUT_OVERFLOW;
-                copy_stored(out + k.pos, w.base + bytepos, len);
-                k.pos += len;
-                w.seek(bytepos + len);
-            }
-            continue;
-        }
-        if (btype == 3) continue;  // inflate.c:990-998: ignored in the no-assert build
-        uint32_t st = read_huffman_tables(w, sm, btype, bt);
-        if (st) return st;
-        uint32_t why = END_EOB;
-        st = decode_symbols<SINK_BYTES>(w, sm, bt, k, why);
-        if (st) return st;
-        if (why == END_LIMIT) more = false;  // rule Q2
-    }
+    uint32_t end;
+    const uint32_t st = inflate_blocks<SINK_BYTES>(w, g, sm, k, ~0ull, end);
+    if (st) return st;
     flush_pending(k.pd);
     *final_size = k.pos;
     return ST_OK;

@@ -59,6 +59,8 @@ DBG_DEV void st_release_u64(uint64_t *p, uint64_t v)
 }
 DBG_DEV void threadfence() { __threadfence(); }
 DBG_DEV void backoff() { __nanosleep(64); }
+DBG_DEV uint32_t ldg_u32(const uint32_t *p) { return __ldg(p); }
+DBG_DEV uint32_t atomic_inc_shared(uint32_t *p) { return atomicAdd(p, 1u); }
 DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return __ldcg(p); }
 DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return __ldcg(p); }
 
@@ -176,6 +178,8 @@ DBG_DEV uint64_t ld_acquire_u64(const uint64_t *p) { return *p; }
 DBG_DEV void st_release_u64(uint64_t *p, uint64_t v) { *p = v; }
 DBG_DEV void threadfence() {}
 DBG_DEV void backoff() {}
+DBG_DEV uint32_t ldg_u32(const uint32_t *p) { return *p; }
+DBG_DEV uint32_t atomic_inc_shared(uint32_t *p) { return (*p)++; }
 DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return *p; }
 DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return *p; }
 

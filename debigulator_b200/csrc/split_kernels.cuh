@@ -35,6 +35,7 @@ struct SplitBatch {
     SplitSummary *summary;
     uint32_t *split_flag;   // per stream: 1 = split path
     uint32_t *chunk_base;   // per stream: first global chunk index
+    uint32_t *nchunks;      // per stream: number of chunks
     uint64_t *cell_base;    // per stream: first cell
     uint32_t *chunk_stream; // per chunk
     uint64_t *entry_bits;   // per chunk: exact entry (stream-relative bit)
@@ -60,6 +61,7 @@ __global__ void split_classify_kernel(SplitBatch b)
         flag = 1;
         uint32_t nch = split_nchunks(size);
         b.chunk_base[s] = atomicAdd(&b.summary->total_chunks, nch);
+        b.nchunks[s] = nch;
         atomicAdd(&b.summary->n_split, 1u);
         atomicAdd((unsigned long long *)&b.summary->cells_cap, (unsigned long long)cap);
     }
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) split_resolve_tails_kernel(Sp
         if (b.split_flag[s] && threadIdx.x == 0) b.out_size[s] = 0;
         return;
     }
-    const uint32_t nch = split_nchunks(b.in_size[s]), base = b.chunk_base[s];
+    const uint32_t nch = b.nchunks[s], base = b.chunk_base[s];
     uint8_t *out = b.out_base + b.out_off[s];
     const uint16_t *cells = b.cells + b.cell_base[s];
     uint32_t v[TAIL_PER_THREAD / 2], nv[TAIL_PER_THREAD / 2];  // two 16-bit cells per register

@@ -140,6 +140,11 @@ int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, c
  * Off by default, so that `good` matches the reference. */
 int dbg_set_verify(dbg_ctx *ctx, int on);
 
+/* How many streams so far were decoded chunk-parallel by the block-split path (long multi-block streams,
+ * see DESIGN.md 4.3), and how many of those were handed back to the warp-per-stream kernel because a
+ * hinted block boundary turned out not to be one. Diagnostics only; either pointer may be NULL. */
+int dbg_bsplit_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *fallbacks);
+
 /* Optional timing of the dominant kernel (inflate): after dbg_profile_enable(ctx, 1)
  * every inflate launch is bracketed by CUDA events on its own stream;
  * dbg_profile_read() waits for them, returns the summed device time and the

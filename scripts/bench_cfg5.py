@@ -73,4 +73,5 @@ ms = e0.elapsed_time(e1) / 3
 out_bytes = int(got.sum())
 print(json.dumps({"workload": f"cfg5 shape: {N} gzip members, 64 KiB-16 MiB log-uniform, 8 compressibility classes, {U} unique",
                   "output_bytes": out_bytes, "compressed_bytes": int(sum(sizes)), "ms_per_step": ms,
-                  "GBps_out": out_bytes / ms / 1e6, "members_with_spec_size": exact, "members": N}))
+                  "GBps_out": out_bytes / ms / 1e6, "members_with_spec_size": exact, "members": N,
+                  "bsplit": os.environ.get("DBG_BSPLIT", "1"), "bsplit_streams_fallbacks": ctx.bsplit_stats()}))

@@ -215,6 +215,108 @@ extern "C" uint32_t emu_split_inflate(const uint8_t *in, uint64_t in_size, uint8
     return status;
 }
 
+// ------------------------------------------------------------ block split ----
+#include "../../debigulator_b200/csrc/bsplit_core.h"
+
+struct BsArgs {
+    dbg::InflateSmem *sm;
+    dbg::SearchSmem *q;
+    const uint16_t *kraft;
+    const uint8_t *in;
+    uint64_t in_size;
+    int mode;  // 0 search, 1 count, 2 decode
+    uint64_t lo, hi, start, stop;
+    uint16_t *cells;
+    uint32_t cell_cap;
+    uint64_t abs_base;
+    uint64_t found[32];
+    dbg::ChunkResult res[32];
+};
+static void bs_body(void *p)
+{
+    BsArgs *a = (BsArgs *)p;
+    int l = simt::lane();
+    if (a->mode == 0) a->found[l] = dbg::find_block_start(a->q, a->kraft, a->in, a->in_size, a->lo, a->hi);
+    else if (a->mode == 1) a->res[l] = dbg::decode_block_chunk<dbg::SINK_COUNT>(a->sm, a->in, a->in_size, a->start, a->stop, nullptr, 0, 0);
+    else a->res[l] = dbg::decode_block_chunk<dbg::SINK_U16>(a->sm, a->in, a->in_size, a->start, a->stop, a->cells, a->cell_cap, a->abs_base);
+}
+
+// The block-split pipeline (search, count, chain, 16-bit decode, resolve) of bsplit_kernels.cuh run
+// region by region through the emulator. Returns the status; 0x4000 = the chain did not close (the
+// product would hand the stream back to the warp-per-stream kernel). *n_chunks = hinted regions used.
+extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
+                                       int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks)
+{
+    size_t arena_sz = ((size_t)in_size + 64 + 32 + 15) & ~(size_t)15;
+    uint8_t *arena = (uint8_t *)aligned_alloc(16, arena_sz);
+    memset(arena, 0xA5, arena_sz);
+    uint8_t *src = arena + 16 + (misalign & 15);
+    memcpy(src, in, in_size);
+    dbg::InflateSmem *sm = (dbg::InflateSmem *)aligned_alloc(16, sizeof(dbg::InflateSmem));
+    dbg::SearchSmem q;
+    static uint16_t kraft[4096];
+    dbg::build_kraft12(kraft, 0, 1);
+    *final_size = 0;
+    *n_chunks = 0;
+    const uint32_t nreg = (uint32_t)((in_size + region_bytes - 1) / region_bytes);
+    uint64_t *cand = (uint64_t *)calloc(nreg, 8), *exitb = (uint64_t *)calloc(nreg, 8), *ooff = (uint64_t *)calloc(nreg, 8);
+    uint32_t *olen = (uint32_t *)calloc(nreg, 4), *flag = (uint32_t *)calloc(nreg, 4);
+    BsArgs a;
+    a.sm = sm; a.q = &q; a.kraft = kraft; a.in = src; a.in_size = in_size; a.cells = nullptr;
+    uint32_t status = 0;
+    for (uint32_t c = 0; c < nreg; c++) {
+        cand[c] = 0;
+        if (!c) continue;
+        a.mode = 0; a.lo = (uint64_t)c * region_bytes * 8; a.hi = (uint64_t)(c + 1) * region_bytes * 8;
+        simt::run_warp(bs_body, &a, reverse);
+        for (int i = 1; i < 32; i++) if (a.found[i] != a.found[0]) status = 0x1000 | i;
+        cand[c] = a.found[0];
+    }
+    auto next_hint = [&](uint32_t c) { for (uint32_t u = c + 1; u < nreg; u++) if (cand[u] != dbg::BS_NONE) return cand[u]; return dbg::BS_NONE; };
+    for (uint32_t c = 0; c < nreg && !status; c++) {
+        if (cand[c] == dbg::BS_NONE) continue;
+        a.mode = 1; a.start = cand[c]; a.stop = next_hint(c);
+        simt::run_warp(bs_body, &a, reverse);
+        exitb[c] = a.res[0].exit_bits; olen[c] = a.res[0].out_bytes; flag[c] = a.res[0].flag;
+    }
+    uint64_t pos = 0, expected = 0;
+    bool ended = false, fail = false;
+    for (uint32_t c = 0; c < nreg && !status; c++) {
+        ooff[c] = pos;
+        if (cand[c] == dbg::BS_NONE || ended || fail) { flag[c] = dbg::CH_IDLE; continue; }
+        if (cand[c] != expected) { fail = true; flag[c] = dbg::CH_IDLE; continue; }
+        (*n_chunks)++;
+        if (flag[c] >= dbg::CH_ERR) { status = pos + olen[c] > cap ? (uint32_t)dbg::ST_OUT_OVERFLOW : flag[c] - dbg::CH_ERR; ended = true; flag[c] = dbg::CH_IDLE; continue; }
+        pos += olen[c];
+        if (pos > cap) { status = dbg::ST_OUT_OVERFLOW; ended = true; }
+        else if (flag[c] != dbg::CH_RUN) ended = true;
+        else expected = exitb[c];
+    }
+    if (!status && (fail || !ended)) status = 0x4000;
+    if (!status) {
+        uint16_t *cells = (uint16_t *)malloc((pos + 16) * 2);
+        for (uint32_t c = 0; c < nreg && !status; c++) {
+            if (flag[c] == dbg::CH_IDLE) continue;
+            a.mode = 2; a.start = cand[c]; a.stop = flag[c] == dbg::CH_RUN ? exitb[c] : dbg::BS_NONE;
+            a.cells = cells + ooff[c]; a.cell_cap = olen[c]; a.abs_base = ooff[c];
+            simt::run_warp(bs_body, &a, reverse);
+            if (a.res[0].flag >= dbg::CH_ERR) status = a.res[0].flag - dbg::CH_ERR;
+            else if (a.res[0].out_bytes != olen[c] || a.res[0].flag != flag[c]) status = 0x3000;
+        }
+        for (uint32_t c = 0; c < nreg && !status; c++) {
+            if (flag[c] == dbg::CH_IDLE) continue;
+            for (uint32_t i = 0; i < olen[c]; i++) {
+                uint32_t v = cells[ooff[c] + i];
+                out[ooff[c] + i] = v < 256 ? (uint8_t)v : out[ooff[c] + (int64_t)v - 33024];
+            }
+        }
+        free(cells);
+        if (!status) *final_size = pos;
+    }
+    free(cand); free(exitb); free(ooff); free(olen); free(flag); free(sm); free(arena);
+    return status;
+}
+
 // ------------------------------------------------------------------- PNG -----
 #include "../../debigulator_b200/csrc/png_core.h"
 

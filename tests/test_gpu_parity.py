@@ -208,3 +208,34 @@ def test_cfg5_extremes_vs_reference(ctx, ref):
         rgood, rout = ref.decode_gz(g, caps[i])
         assert good == rgood, i
         assert len(out) == len(rout) and sha(out) == sha(rout), i
+
+
+def test_block_split_long_streams(ctx, ref):
+    """Long multi-block streams take the block-split path (chunk-parallel decode behind verified block
+    boundaries); results must equal the reference's sequential decode, errors included."""
+    rng = np.random.default_rng(77)
+    text = corpus.word_salad(5 << 20, 11)
+    items = [
+        corpus.raw_deflate(text, 6),                                               # ~2 MB, ~70 dynamic blocks
+        corpus.raw_deflate(text[: 3 << 20], 1),
+        corpus.raw_deflate(corpus.low_entropy(6 << 20, 12), 6),                    # Huffman-only, rule Q2 may end it early
+        corpus.raw_deflate(corpus.periodic(6 << 20, 13, 31000), 9),                # distances at the window limit
+        corpus.raw_deflate(corpus.runs(40 << 20, 14), 6),                          # ~1000:1
+        corpus.mixed_deflate(text[: 4 << 20], 15),                                 # stored + fixed + dynamic segments
+        corpus.raw_deflate(bytes(rng.integers(0, 256, 1 << 20, dtype=np.uint8)), 6),  # stored blocks only
+        corpus.raw_deflate(text, 6)[:-5000],                                       # truncated inside a block
+        corpus.raw_deflate(text[: 200000], 6),                                     # short: stays on the warp-per-stream path
+    ]
+    broken = bytearray(items[0])
+    broken[len(broken) // 2] ^= 0x55                                               # corrupt the middle of a long stream
+    items.append(bytes(broken))
+    caps = [48 << 20] * len(items)
+    before = ctx.bsplit_stats()
+    got = ctx.inflate_batch(items, caps)
+    after = ctx.bsplit_stats()
+    assert after[0] - before[0] >= 5, (before, after)
+    for k, (z, (good, out)) in enumerate(zip(items, got)):
+        rg, rout = ref.inflate(z, caps[k])
+        assert good == rg, k
+        if good:
+            assert out == rout, k

@@ -23,7 +23,7 @@ def sha(b):
 @pytest.fixture(scope="module")
 def emu():
     so = os.path.join(EMU_DIR, "libsimt_emu.so")
-    srcs = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("simt.h", "inflate_core.h", "png_core.h")]
+    srcs = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(CSRC, f) for f in ("simt.h", "inflate_core.h", "png_core.h", "bsplit_core.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", srcs[0], "-o", so])
     L = C.CDLL(so)
@@ -33,6 +33,9 @@ def emu():
     L.emu_png_decode.restype = C.c_uint32
     L.emu_split_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int]
     L.emu_split_inflate.restype = C.c_uint32
+    L.emu_bsplit_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int,
+                                     C.c_uint32, C.POINTER(C.c_uint32)]
+    L.emu_bsplit_inflate.restype = C.c_uint32
     L.emu_crc32.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
     L.emu_crc32.restype = C.c_uint32
     return L
@@ -120,3 +123,40 @@ def test_split_stream_kernel_source(emu):
         st = emu.emu_split_inflate(ib, len(z), ob, cap, C.byref(n), (3 * k) % 16, k & 1)
         assert st == 0, (k, st)
         assert ob.raw[: n.value] == zlib.decompress(z, -15), k
+
+
+def test_block_split_kernel_source(emu, ref):
+    """Block-split path (header search -> count -> chain -> 16-bit cells -> resolve) on multi-block streams,
+    against the reference. memLevel 1 makes zlib close a block every 128 symbols, so small inputs already
+    have hundreds of block boundaries; the mixed stream adds stored and fixed blocks between the dynamic ones."""
+    import zlib
+    import numpy as np
+    from debigulator_b200 import corpus
+    rng = np.random.default_rng(9)
+
+    def many_blocks(data, level=6, mem=1):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, mem)
+        return c.compress(data) + c.flush()
+
+    cases = [
+        (many_blocks(corpus.word_salad(60000, 1)), 2048),
+        (many_blocks(corpus.periodic(150000, 2, 30000), 9, 2), 1024),
+        (many_blocks(corpus.low_entropy(120000, 3)), 1500),
+        (corpus.mixed_deflate(corpus.word_salad(200000, 4), 4), 4096),
+        (many_blocks(corpus.runs(300000, 5)), 512),
+        (corpus.raw_deflate(bytes(rng.integers(0, 256, 70000, dtype=np.uint8)), 6), 4096),  # stored blocks only: no hints
+        (many_blocks(corpus.word_salad(60000, 6))[:-700], 2048),                             # truncated
+    ]
+    used = 0
+    for k, (z, region) in enumerate(cases):
+        want_good, want = ref.inflate(z, 400000)
+        ib = C.create_string_buffer(z, len(z))
+        ob = C.create_string_buffer(400000 + 64)
+        n, nch = C.c_uint64(0), C.c_uint32(0)
+        st = emu.emu_bsplit_inflate(ib, len(z), ob, 400000, C.byref(n), (5 * k) % 16, k & 1, region, C.byref(nch))
+        assert st != 0x4000 and st < 0x1000, (k, hex(st))
+        assert (st == 0) == bool(want_good), (k, st)
+        if want_good:
+            assert ob.raw[: n.value] == want, k
+        used += nch.value
+    assert used > 40  # the search really finds block boundaries
