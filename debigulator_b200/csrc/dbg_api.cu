@@ -74,9 +74,12 @@ struct dbg_ctx {
     Buf d_png_scratch;             // compacted IDAT + filtered scanlines
     Buf d_split, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
     // block-split path (long multi-block streams): per wave slot, since waves run concurrently
+    Buf d_sched[MAX_WAVES];        // work-queue order computed on the device when the caller brings none
+    bool bsplit_allowed = true;    // cleared while the packed API runs several waves at once
     Buf d_bs_stream[MAX_WAVES], d_bs_region[MAX_WAVES], d_bs_cells[MAX_WAVES], h_bs_summary[MAX_WAVES];
     bool bsplit = true;
     uint64_t bsplit_min_bytes = dbg::BS_MIN_BYTES;
+    uint32_t bsplit_factor_q = 8;
     uint64_t bs_streams = 0, bs_fallbacks = 0;  // counters: streams that took the block-split path / were handed back
     uint32_t split_max_streams = 1536;  // batches with fewer streams may use the split-stream path (measured crossover ~1,500 images of 1024^2)
     bool verify = false;                // opt-in: check gzip CRC32 / ISIZE trailers
@@ -166,6 +169,7 @@ extern "C" dbg_ctx *dbg_create(int device)
                          (int)(sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA));
     if (const char *e = getenv("DBG_SPLIT_MAX_STREAMS")) ctx->split_max_streams = (uint32_t)atoi(e);
     if (const char *e = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(e) != 0;
+    if (const char *e = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(e));
     if (const char *e = getenv("DBG_BSPLIT_MIN_BYTES")) ctx->bsplit_min_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 2 * dbg::REGION_BYTES);
     if (const char *e = getenv("DBG_INFLATE_CTAS_PER_SM")) {
         int v = atoi(e);
@@ -183,6 +187,7 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
                   &ctx->h_in,      &ctx->h_out,  &ctx->h_desc,        &ctx->d_split, &ctx->d_cells, &ctx->h_summary};
     for (Buf *b : all) b->release();
     for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) {
+        ctx->d_sched[i].release();
         ctx->d_bs_stream[i].release();
         ctx->d_bs_region[i].release();
         ctx->d_bs_cells[i].release();
@@ -245,9 +250,15 @@ extern "C" int dbg_synchronize(dbg_ctx *ctx)
 }
 
 // ------------------------------------------------------------------ launches --
-static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s)
+static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot = 0)
 {
     a.counter = d_counter;
+    if (!a.order && a.n > (uint32_t)ctx->sm_count) {  // heaviest first, so that the longest streams do not start last
+        CU(ctx->d_sched[slot].reserve((size_t)a.n * 4));
+        dbg::sched_order_kernel<<<1, 1024, 0, s>>>(a, (uint32_t *)ctx->d_sched[slot].p);
+        ctx->launches++;
+        a.order = (const uint32_t *)ctx->d_sched[slot].p;
+    }
     CU(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), s));
     uint32_t ctas_needed = (a.n + dbg::INFLATE_WARPS_PER_CTA - 1) / dbg::INFLATE_WARPS_PER_CTA;
     uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)ctx->sm_count * ctx->inflate_ctas_per_sm);
@@ -358,6 +369,7 @@ static int run_bsplit(dbg_ctx *ctx, int slot, const dbg::InflateBatch &a, cudaSt
     b.out_size = a.out_size; b.status = a.status; b.pre_status = a.pre_status; b.taken = taken; b.n = n;
     b.resident_warps = (uint32_t)ctx->sm_count * ctx->inflate_ctas_per_sm * dbg::INFLATE_WARPS_PER_CTA;
     b.min_bytes = ctx->bsplit_min_bytes;
+    b.factor_q = ctx->bsplit_factor_q;
     b.summary = (dbg::BsSummary *)p;
     b.cell_base = (uint64_t *)(p + 256);
     b.flag = (uint32_t *)(b.cell_base + n);
@@ -422,13 +434,13 @@ static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter
         if (rc) return rc;
         a.skip = skip;
     }
-    if (ctx->bsplit) {
+    if (ctx->bsplit && ctx->bsplit_allowed) {
         const uint32_t *skip2 = nullptr;
         int rc = run_bsplit(ctx, slot, a, s, a.skip, &skip2);
         if (rc) return rc;
         a.skip2 = skip2;
     }
-    return launch_inflate_plain(ctx, a, d_counter, s);
+    return launch_inflate_plain(ctx, a, d_counter, s, slot);
 }
 
 static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -469,6 +481,7 @@ extern "C" int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t 
         set_err(ctx, "dbg_inflate_batch_device: bad arguments");
         return DBG_ERR_ARG;
     }
+    ctx->bsplit_allowed = true;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     return inflate_device_slot(ctx, 0, n, d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, d_order,
@@ -487,6 +500,7 @@ extern "C" int dbg_decode_gz_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_
         set_err(ctx, "dbg_decode_gz_batch_device: bad arguments");
         return DBG_ERR_ARG;
     }
+    ctx->bsplit_allowed = true;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     CU(ctx->d_meta.reserve(n * 20 + 64));
@@ -560,7 +574,7 @@ static inline uint64_t sched_weight(int kind, const uint8_t *p, uint64_t size)
         }
     }
     if (kind == 2 || at >= size) return size;
-    return ((p[at] >> 1) & 3) == 0 ? size / 16 : size;
+    return ((p[at] >> 1) & 3) == 0 ? size / 64 : size;
 }
 
 extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
@@ -607,6 +621,15 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
         mono = in_off[i] >= in_off[i - 1] + in_size[i - 1] && out_off[i] >= out_off[i - 1] + out_cap[i - 1];
     int nw = mono ? (int)std::min<uint64_t>(dbg_ctx::MAX_WAVES, std::max<uint64_t>(1, n / 256)) : 1;
     if (n < ctx->split_max_streams) nw = 1;  // small batches may take the split-stream path, which owns per-context scratch
+    if (nw > 1 && ctx->bsplit) {
+        // a batch with streams long enough for the block-split path (same rule as bs_classify_kernel) runs
+        // as one wave: that path synchronises the host twice, which would serialise concurrent waves
+        const uint64_t resident = (uint64_t)ctx->sm_count * ctx->inflate_ctas_per_sm * dbg::INFLATE_WARPS_PER_CTA;
+        const uint64_t thr = std::max<uint64_t>(ctx->bsplit_min_bytes, tot_in / resident * ctx->bsplit_factor_q / 4);
+        for (uint64_t i = 0; i < n && nw > 1; i++)
+            if (in_size[i] >= thr) nw = 1;
+    }
+    ctx->bsplit_allowed = nw == 1;
     CU(cudaMemcpyAsync(dd, hd, 4 * n * 8, cudaMemcpyHostToDevice, s));
     if (kind == 1) CU(ctx->d_meta.reserve(n * 20 + 64));
     uint64_t *gz_off = kind == 1 ? (uint64_t *)ctx->d_meta.p : nullptr;
@@ -614,7 +637,7 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
     uint32_t *gz_pre = gz_off ? (uint32_t *)(gz_size + n) : nullptr;
     if (nw == 1) {
         std::vector<uint64_t> wt(n);
-        for (uint64_t i = 0; i < n; i++) wt[i] = sched_weight(kind, h_in + in_off[i], in_size[i]);
+        for (uint64_t i = 0; i < n; i++) wt[i] = sched_weight(kind, h_in + in_off[i], in_size[i]) + out_cap[i] / 32;
         std::iota(h_order, h_order + n, 0u);
         std::stable_sort(h_order, h_order + n, [&](uint32_t a, uint32_t b) { return wt[a] > wt[b]; });
         CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
@@ -637,7 +660,7 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
             uint32_t *o = h_order + cut[k];
             uint64_t m = cut[k + 1] - cut[k], b = cut[k];
             std::vector<uint64_t> wt(m);
-            for (uint64_t i = 0; i < m; i++) wt[i] = sched_weight(kind, h_in + in_off[b + i], in_size[b + i]);
+            for (uint64_t i = 0; i < m; i++) wt[i] = sched_weight(kind, h_in + in_off[b + i], in_size[b + i]) + out_cap[b + i] / 32;
             std::iota(o, o + m, 0u);
             std::stable_sort(o, o + m, [&](uint32_t x, uint32_t y) { return wt[x] > wt[y]; });
         }
@@ -660,6 +683,7 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
         }
         for (int k = 0; k < nw; k++) CU(cudaStreamSynchronize(ctx->wave_stream[k]));
     }
+    ctx->bsplit_allowed = true;
     CU(cudaMemcpyAsync(hd + 4 * n, dd + 4 * n, n * 8 + n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     memcpy(status, h_status, n * 4);

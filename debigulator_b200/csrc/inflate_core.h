@@ -325,7 +325,19 @@ DBG_DEV_NOINLINE void copy_match_slow(uint8_t *out, uint32_t pos, uint32_t len, 
     const uint8_t *src = dst - dist;
     simt::syncwarp();  // earlier stores by other lanes are visible from here on
     if (dist >= len) {
-        for (uint32_t i = ln; i < len; i += 32) dst[i] = src[i];
+        // no overlap: all loads first, then all stores (a store-load-store chain would pay one L2 round
+        // trip per 32 bytes; len <= 258 means at most 9 bytes per lane)
+        uint32_t v[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const uint32_t i = ln + 32 * j;
+            v[j] = i < len ? src[i] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const uint32_t i = ln + 32 * j;
+            if (i < len) dst[i] = (uint8_t)v[j];
+        }
     } else if (dist >= 32) {
         for (uint32_t b = 0; b < len; b += 32) {
             uint32_t i = b + ln;

@@ -54,6 +54,41 @@ __global__ void __launch_bounds__(INFLATE_THREADS, INFLATE_CTAS_PER_SM) inflate_
     }
 }
 
+// Largest-first work-queue order for callers that do not bring one: a counting sort of the streams by
+// the quarter-octave of their estimated decode time (one CTA; order inside a bucket is arbitrary).
+// Estimate: compressed bytes (1/64 of them when the stream opens with a stored block, i.e. a plain
+// copy) + output capacity / 32 (match copying of highly compressible streams).
+constexpr int SCHED_BUCKETS = 256;
+__global__ void __launch_bounds__(1024) sched_order_kernel(InflateBatch a, uint32_t *order)
+{
+    __shared__ uint32_t hist[SCHED_BUCKETS];
+    for (uint32_t i = threadIdx.x; i < SCHED_BUCKETS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    auto bucket = [&](uint32_t s) -> uint32_t {
+        const uint64_t size = a.in_size[s];
+        uint64_t w = size;
+        if (size && ((a.in_base[a.in_off[s]] >> 1) & 3) == 0) w = size >> 6;
+        w += a.out_cap[s] >> 5;
+        if (w < 4) return SCHED_BUCKETS - 1;
+        const int e = 63 - __clzll((long long)w);                  // 2 .. 63
+        const uint32_t q = (uint32_t)(w >> (e - 2)) & 3;           // two bits below the leading one
+        const uint32_t b = (uint32_t)e * 4 + q;                    // larger = heavier
+        return b >= SCHED_BUCKETS ? 0 : SCHED_BUCKETS - 1 - b;     // bucket 0 = heaviest
+    };
+    for (uint32_t s = threadIdx.x; s < a.n; s += blockDim.x) atomicAdd(&hist[bucket(s)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < SCHED_BUCKETS; i++) {
+            const uint32_t c = hist[i];
+            hist[i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < a.n; s += blockDim.x) order[atomicAdd(&hist[bucket(s)], 1u)] = s;
+}
+
 // gzip member framing, one thread per member: the header walk of
 // decode_gz.c:123-233 (silent build: FNAME skipped, FCOMMENT not) and the
 // payload size rule of decode_gz.c:270 (everything but the 8-byte trailer).

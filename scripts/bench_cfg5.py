@@ -49,7 +49,7 @@ d_out = torch.zeros(int(sum(caps)), dtype=torch.uint8, device=dev)
 d_size = torch.zeros(N, dtype=torch.int64, device=dev)
 d_st = torch.zeros(N, dtype=torch.int32, device=dev)
 order = np.argsort(-np.asarray(sizes, np.int64), kind="stable").astype(np.uint32)
-d_order = torch.from_numpy(order.view(np.int32)).to(dev)
+d_order = torch.from_numpy(order.view(np.int32)).to(dev) if os.environ.get("CFG5_HOST_ORDER") else None  # None: the library orders the queue
 a_off, a_sz, o_off, o_cap = i64(offs), i64(sizes), i64(out_off), i64(caps)
 
 
