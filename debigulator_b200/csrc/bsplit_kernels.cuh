@@ -38,7 +38,8 @@ struct BsBatch {
     uint64_t min_bytes;          // lower bound of the split threshold
     uint32_t factor_q;           // threshold = factor_q / 4 x (batch bytes / resident warps)
     BsSummary *summary;
-    uint32_t *flag;         // per stream: 1 = block-split path
+    uint32_t *flag;         // per stream: 1 = block-split path (stays set for a handed-back stream)
+    uint32_t *redo;         // per stream: 1 = handed back to the warp-per-stream kernel (second pass)
     uint32_t *chunk_base;   // per stream: first region index
     uint32_t *nchunks;      // per stream: regions
     uint64_t *cell_base;    // per stream
@@ -73,6 +74,7 @@ __global__ void bs_classify_kernel(BsBatch b)
                     size < (1ull << 31) && cap < (1ull << 32) - 1024;
     // a stream that opens with a stored block is (mostly) a plain copy, which one warp does at ~0.8 GB/s
     // and 16-bit cells would only slow down
+    b.redo[s] = 0;
     if (ok && ((b.in_base[b.in_off[s]] >> 1) & 3) != 0) {
         flag = 1;
         const uint32_t nreg = (uint32_t)((size + REGION_BYTES - 1) / REGION_BYTES);
@@ -190,7 +192,7 @@ __global__ void bs_chain_kernel(BsBatch b)
             b.c_flag[base + c] = CH_IDLE;
             b.c_out_len[base + c] = 0;
         }
-        b.flag[s] = 0;
+        b.redo[s] = 1;  // flag[s] stays set: the first warp-per-stream pass may already be running beside us
         b.cell_base[s] = 0;
         atomicAdd(&b.summary->n_fallback, 1u);
         return;
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_decode_kernel(BsBatc
     const uint32_t warps = gridDim.x * BS_WARPS_PER_CTA;
     for (uint32_t t = blockIdx.x * BS_WARPS_PER_CTA + (threadIdx.x >> 5); t < total_regions; t += warps) {
         const uint32_t s = b.chunk_stream[t];
-        if (!b.flag[s] || b.status[s] != ST_OK || b.c_flag[t] == CH_IDLE) continue;
+        if (!b.flag[s] || b.redo[s] || b.status[s] != ST_OK || b.c_flag[t] == CH_IDLE) continue;
         const uint64_t stop = b.c_flag[t] == CH_RUN ? b.exit_bits[t] : BS_NONE;
         const ChunkResult r = decode_block_chunk<SINK_U16>(sm, b.in_base + b.in_off[s], b.in_size[s], b.cand[t], stop,
                                                            b.cells + b.cell_base[s] + b.c_out_off[t], b.c_out_len[t], b.c_out_off[t]);

@@ -62,6 +62,8 @@ struct dbg_ctx {
     static constexpr int MAX_WAVES = 4;
     cudaStream_t wave_stream[MAX_WAVES] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t wave_ready = nullptr;
+    cudaStream_t aux_stream = nullptr;  // the warp-per-stream kernel runs here beside the block-split kernels
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     uint64_t launches = 0;
     char err[512] = "";
     // optional per-launch timing of the dominant (inflate) kernel, for roofline reports
@@ -159,6 +161,9 @@ extern "C" dbg_ctx *dbg_create(int device)
     }
     for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) cudaStreamCreateWithFlags(&ctx->wave_stream[i], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->wave_ready, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
     size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
@@ -195,6 +200,9 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
         if (ctx->wave_stream[i]) cudaStreamDestroy(ctx->wave_stream[i]);
     }
     if (ctx->wave_ready) cudaEventDestroy(ctx->wave_ready);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -250,10 +258,10 @@ extern "C" int dbg_synchronize(dbg_ctx *ctx)
 }
 
 // ------------------------------------------------------------------ launches --
-static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot = 0)
+static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot, bool may_order)
 {
     a.counter = d_counter;
-    if (!a.order && a.n > (uint32_t)ctx->sm_count) {  // heaviest first, so that the longest streams do not start last
+    if (may_order && !a.order && a.n > (uint32_t)ctx->sm_count) {  // heaviest first, so that the longest streams do not start last
         CU(ctx->d_sched[slot].reserve((size_t)a.n * 4));
         dbg::sched_order_kernel<<<1, 1024, 0, s>>>(a, (uint32_t *)ctx->d_sched[slot].p);
         ctx->launches++;
@@ -354,14 +362,20 @@ static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, c
 
 // Block-split path for the long streams of a batch (bsplit_kernels.cuh). Two small device->host reads:
 // how many regions, then how many cells. `taken` marks streams the split-stream path already owns.
-static int run_bsplit(dbg_ctx *ctx, int slot, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t *taken,
-                      const uint32_t **skip_out)
+static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot, bool may_order = true);
+
+// When streams do take this path, the warp-per-stream kernel for all the others is launched from here, on an
+// auxiliary stream, as soon as the classification is known: it is bound by the latency of its longest streams
+// and leaves most SM slots free, which the (throughput-bound) block-split kernels then fill. *regular_done
+// tells the caller that this has happened.
+static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, const uint32_t *taken,
+                      bool *regular_done)
 {
-    *skip_out = nullptr;
+    *regular_done = false;
     const uint32_t n = a.n;
     Buf &bs = ctx->d_bs_stream[slot], &br = ctx->d_bs_region[slot], &bc = ctx->d_bs_cells[slot], &hsb = ctx->h_bs_summary[slot];
     CU(hsb.reserve(sizeof(dbg::BsSummary)));
-    CU(bs.reserve(256 + (size_t)n * (8 + 4 + 4 + 4) + 256));
+    CU(bs.reserve(256 + (size_t)n * (8 + 4 + 4 + 4 + 4) + 256));
     uint8_t *p = (uint8_t *)bs.p;
     dbg::BsBatch b{};
     b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
@@ -375,6 +389,7 @@ static int run_bsplit(dbg_ctx *ctx, int slot, const dbg::InflateBatch &a, cudaSt
     b.flag = (uint32_t *)(b.cell_base + n);
     b.chunk_base = b.flag + n;
     b.nchunks = b.chunk_base + n;
+    b.redo = b.nchunks + n;
     const unsigned sb = (n + 127) / 128;
     CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::BsSummary), s));
     dbg::bs_sum_kernel<<<sb, 128, 0, s>>>(b);
@@ -385,6 +400,17 @@ static int run_bsplit(dbg_ctx *ctx, int slot, const dbg::InflateBatch &a, cudaSt
     CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::BsSummary), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (hs->n_split == 0) return DBG_OK;
+    // fork: everything that is not split, on the auxiliary stream
+    a.skip = taken;
+    a.skip2 = b.flag;
+    CU(cudaEventRecord(ctx->aux_fork, s));
+    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+    {
+        int rc = launch_inflate_plain(ctx, a, d_counter, ctx->aux_stream, slot);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+    *regular_done = true;
     const uint32_t T = hs->total_regions;
     CU(br.reserve((size_t)T * (4 + 8 + 8 + 8 + 4 + 4) + 256));
     b.cand = (uint64_t *)br.p;
@@ -406,21 +432,32 @@ static int run_bsplit(dbg_ctx *ctx, int slot, const dbg::InflateBatch &a, cudaSt
     CU(cudaStreamSynchronize(s));
     ctx->bs_streams += hs->n_split - hs->n_fallback;
     ctx->bs_fallbacks += hs->n_fallback;
-    *skip_out = b.flag;
-    if (hs->cells_used == 0) return DBG_OK;
-    CU(bc.reserve((size_t)hs->cells_used * 2 + 256));
-    b.cells = (uint16_t *)bc.p;
-    dbg::bs_decode_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b, T);
-    // cells -> bytes with the split-stream path's resolve kernels
-    dbg::SplitBatch r{};
-    r.out_base = a.out_base; r.out_off = a.out_off; r.out_size = a.out_size; r.status = a.status; r.n = n;
-    r.split_flag = b.flag; r.chunk_base = b.chunk_base; r.nchunks = b.nchunks; r.cell_base = b.cell_base;
-    r.chunk_stream = b.chunk_stream; r.c_out_off = b.c_out_off; r.c_out_len = b.c_out_len; r.c_flag = b.c_flag;
-    r.cells = b.cells;
-    dbg::split_resolve_tails_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(r);
-    dbg::split_resolve_body_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(r, T);
-    ctx->launches += 3;
-    CU(cudaGetLastError());
+    if (hs->cells_used) {
+        CU(bc.reserve((size_t)hs->cells_used * 2 + 256));
+        b.cells = (uint16_t *)bc.p;
+        dbg::bs_decode_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b, T);
+        // cells -> bytes with the split-stream path's resolve kernels
+        dbg::SplitBatch r{};
+        r.out_base = a.out_base; r.out_off = a.out_off; r.out_size = a.out_size; r.status = a.status; r.n = n;
+        r.split_flag = b.flag; r.redo = b.redo; r.chunk_base = b.chunk_base; r.nchunks = b.nchunks; r.cell_base = b.cell_base;
+        r.chunk_stream = b.chunk_stream; r.c_out_off = b.c_out_off; r.c_out_len = b.c_out_len; r.c_flag = b.c_flag;
+        r.cells = b.cells;
+        dbg::split_resolve_tails_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(r);
+        dbg::split_resolve_body_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(r, T);
+        ctx->launches += 3;
+        CU(cudaGetLastError());
+    }
+    if (hs->n_fallback) {
+        // second warp-per-stream pass for the streams whose hinted boundaries did not chain
+        dbg::InflateBatch again = a;
+        again.skip = nullptr;
+        again.skip2 = nullptr;
+        again.only = b.redo;
+        again.order = nullptr;  // and no device-made order either: the first pass may still be reading that buffer
+        int rc = launch_inflate_plain(ctx, again, d_counter + 1, s, slot, false);
+        if (rc) return rc;
+    }
+    CU(cudaStreamWaitEvent(s, ctx->aux_join, 0));  // join
     return DBG_OK;
 }
 
@@ -435,10 +472,9 @@ static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter
         a.skip = skip;
     }
     if (ctx->bsplit && ctx->bsplit_allowed) {
-        const uint32_t *skip2 = nullptr;
-        int rc = run_bsplit(ctx, slot, a, s, a.skip, &skip2);
-        if (rc) return rc;
-        a.skip2 = skip2;
+        bool done = false;
+        int rc = run_bsplit(ctx, slot, a, d_counter, s, a.skip, &done);
+        if (rc || done) return rc;
     }
     return launch_inflate_plain(ctx, a, d_counter, s, slot);
 }
@@ -455,7 +491,7 @@ static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t
         dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, gz_off, gz_size, gz_pre);
         ctx->launches++;
         CU(cudaGetLastError());
-        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
+        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
         int rc = launch_inflate(ctx, a, counter, s, slot);
         if (rc || !ctx->verify) return rc;
         uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
@@ -465,7 +501,7 @@ static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t
         CU(cudaGetLastError());
         return DBG_OK;
     }
-    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
+    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
     return launch_inflate(ctx, a, counter, s, slot);
 }
 
@@ -541,7 +577,7 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
     // 2. inflate the compacted zlib payloads into the filtered-scanline buffers
     // z_off holds absolute addresses: a single-IDAT image is inflated straight from the file
     dbg::InflateBatch a{nullptr, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
-                        lay.pre_status, nullptr, nullptr, nullptr, nullptr, (uint32_t)n};
+                        lay.pre_status, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t)n};
     rc = launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
     if (rc) return rc;
     if (ctx->verify) {

@@ -23,6 +23,7 @@ struct InflateBatch {
     const uint32_t *pre_status;  // optional: non-zero entries are reported as-is and skipped
     const uint32_t *skip;        // optional: non-zero entries are handled elsewhere (split-stream path)
     const uint32_t *skip2;       // optional: same, block-split path
+    const uint32_t *only;        // optional: only entries with a non-zero flag are processed (second pass)
     const uint32_t *order;       // optional scheduling permutation
     uint32_t *counter;           // work-queue head, zeroed before launch
     uint32_t n;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(INFLATE_THREADS, INFLATE_CTAS_PER_SM) inflate_
         idx = simt::shfl(idx, 0);
         if (idx >= a.n) break;
         const uint32_t s = a.order ? a.order[idx] : idx;
-        if ((a.skip && a.skip[s]) || (a.skip2 && a.skip2[s])) continue;
+        if ((a.skip && a.skip[s]) || (a.skip2 && a.skip2[s]) || (a.only && !a.only[s])) continue;
         uint32_t st = a.pre_status ? a.pre_status[s] : 0u;
         uint64_t fs = 0;
         if (st == 0)

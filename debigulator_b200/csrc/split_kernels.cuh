@@ -34,6 +34,7 @@ struct SplitBatch {
     // scratch
     SplitSummary *summary;
     uint32_t *split_flag;   // per stream: 1 = split path
+    const uint32_t *redo;   // optional (block-split path): 1 = handed back, nothing to resolve
     uint32_t *chunk_base;   // per stream: first global chunk index
     uint32_t *nchunks;      // per stream: number of chunks
     uint64_t *cell_base;    // per stream: first cell
@@ -160,6 +161,7 @@ constexpr int TAIL_PER_THREAD = TAIL_BYTES / RESOLVE_THREADS;
 __global__ void __launch_bounds__(RESOLVE_THREADS) split_resolve_tails_kernel(SplitBatch b)
 {
     const uint32_t s = blockIdx.x;
+    if (b.redo && b.redo[s]) return;
     if (!b.split_flag[s] || b.status[s] != ST_OK) {
         if (b.split_flag[s] && threadIdx.x == 0) b.out_size[s] = 0;
         return;

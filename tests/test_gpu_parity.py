@@ -239,3 +239,27 @@ def test_block_split_long_streams(ctx, ref):
         assert good == rg, k
         if good:
             assert out == rout, k
+
+
+def test_block_split_false_hints_fall_back(ctx, ref):
+    """Stored blocks whose payload is itself DEFLATE data put perfectly valid-looking dynamic block headers
+    where no block of the outer stream starts. The chain check must notice and hand the stream back to the
+    warp-per-stream kernel; the result is still the reference's."""
+    text = corpus.word_salad(3 << 20, 21)
+    inner = b"".join(corpus.raw_deflate(corpus.word_salad(8000, 100 + k), 6) for k in range(60))  # ~200 KB of headers
+    segs = []
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    segs.append(c.compress(text[: 1 << 20]) + c.flush(zlib.Z_FULL_FLUSH))
+    c0 = zlib.compressobj(0, zlib.DEFLATED, -15)
+    segs.append(c0.compress(inner) + c0.flush(zlib.Z_FULL_FLUSH))
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    segs.append(c.compress(text[1 << 20:]) + c.flush(zlib.Z_FINISH))
+    z = b"".join(segs)
+    assert zlib.decompress(z, -15) == text[: 1 << 20] + inner + text[1 << 20:]
+    before = ctx.bsplit_stats()
+    (good, out), (g2, out2) = ctx.inflate_batch([z, corpus.raw_deflate(text, 6)], [8 << 20, 8 << 20])
+    after = ctx.bsplit_stats()
+    rg, rout = ref.inflate(z, 8 << 20)
+    assert good == rg == 1 and out == rout
+    assert g2 == 1 and out2 == text
+    assert after[1] - before[1] == 1 and after[0] - before[0] == 1, (before, after)
