@@ -10,7 +10,7 @@
 
 namespace dbg {
 
-constexpr uint64_t BS_MIN_BYTES = 4 * (uint64_t)REGION_BYTES;  // shorter streams never take this path
+constexpr uint64_t BS_MIN_BYTES = 65536;  // shorter streams never take this path (4 regions of the smallest size)
 constexpr int BS_WARPS_PER_CTA = 4;
 
 struct BsSummary {         // device -> host after classify, and again after chain
@@ -20,6 +20,7 @@ struct BsSummary {         // device -> host after classify, and again after cha
     uint64_t cells_used;   // exact number of 16-bit cells (bs_chain_kernel)
     uint32_t n_fallback;   // streams whose chain did not close
     uint32_t pad;
+    uint64_t split_in;     // compressed bytes of the streams taking this path
 };
 
 struct BsBatch {
@@ -37,6 +38,7 @@ struct BsBatch {
     uint32_t resident_warps;     // streams the warp-per-stream kernel keeps in flight
     uint64_t min_bytes;          // lower bound of the split threshold
     uint32_t factor_q;           // threshold = factor_q / 4 x (batch bytes / resident warps)
+    uint32_t region_bytes;       // compressed bytes per region
     BsSummary *summary;
     uint32_t *flag;         // per stream: 1 = block-split path (stays set for a handed-back stream)
     uint32_t *redo;         // per stream: 1 = handed back to the warp-per-stream kernel (second pass)
@@ -72,17 +74,28 @@ __global__ void bs_classify_kernel(BsBatch b)
     uint32_t flag = 0;
     const bool ok = (!b.pre_status || b.pre_status[s] == 0) && (!b.taken || b.taken[s] == 0) && size >= thr && cap >= size &&
                     size < (1ull << 31) && cap < (1ull << 32) - 1024;
-    // a stream that opens with a stored block is (mostly) a plain copy, which one warp does at ~0.8 GB/s
-    // and 16-bit cells would only slow down
+    // not worth it / not possible: a stream that opens with a stored block is (mostly) a plain copy, which
+    // one warp does at ~0.8 GB/s and 16-bit cells would only slow down; a stream whose first block is also
+    // its last has no block boundary to split at
     b.redo[s] = 0;
-    if (ok && ((b.in_base[b.in_off[s]] >> 1) & 3) != 0) {
+    const uint32_t first = ok ? b.in_base[b.in_off[s]] : 0u;
+    if (ok && ((first >> 1) & 3) != 0 && (first & 1) == 0) {
         flag = 1;
-        const uint32_t nreg = (uint32_t)((size + REGION_BYTES - 1) / REGION_BYTES);
-        b.chunk_base[s] = atomicAdd(&b.summary->total_regions, nreg);
-        b.nchunks[s] = nreg;
         atomicAdd(&b.summary->n_split, 1u);
+        atomicAdd((unsigned long long *)&b.summary->split_in, (unsigned long long)size);
     }
     b.flag[s] = flag;
+}
+
+// Regions per stream, once the host has chosen the region size (smaller regions when the split
+// streams alone would not fill the GPU with 64 KiB ones).
+__global__ void bs_assign_kernel(BsBatch b)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n || !b.flag[s]) return;
+    const uint32_t nreg = (uint32_t)((b.in_size[s] + b.region_bytes - 1) / b.region_bytes);
+    b.chunk_base[s] = atomicAdd(&b.summary->total_regions, nreg);
+    b.nchunks[s] = nreg;
 }
 
 __global__ void bs_fill_kernel(BsBatch b)
@@ -94,8 +107,9 @@ __global__ void bs_fill_kernel(BsBatch b)
 }
 
 // Hints: one warp per region.
-__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_search_kernel(BsBatch b, uint32_t total_regions)
+__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_search_kernel(BsBatch b)
 {
+    const uint32_t total_regions = b.summary->total_regions;
     __shared__ uint16_t kraft12[4096];
     __shared__ SearchSmem qs[BS_WARPS_PER_CTA];
     build_kraft12(kraft12, threadIdx.x, blockDim.x);
@@ -105,8 +119,8 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_search_kernel(BsBatc
     for (uint32_t t = blockIdx.x * BS_WARPS_PER_CTA + (threadIdx.x >> 5); t < total_regions; t += warps) {
         const uint32_t s = b.chunk_stream[t], c = t - b.chunk_base[s];
         uint64_t cand = 0;
-        if (c) cand = find_block_start(q, kraft12, b.in_base + b.in_off[s], b.in_size[s], (uint64_t)c * REGION_BYTES * 8,
-                                       (uint64_t)(c + 1) * REGION_BYTES * 8);
+        if (c) cand = find_block_start(q, kraft12, b.in_base + b.in_off[s], b.in_size[s], (uint64_t)c * b.region_bytes * 8,
+                                       (uint64_t)(c + 1) * b.region_bytes * 8);
         if (simt::lane() == 0) b.cand[t] = cand;
         simt::syncwarp();
     }
@@ -121,8 +135,9 @@ __device__ __forceinline__ uint64_t bs_next_hint(const BsBatch &b, uint32_t s, u
 }
 
 // Sizes: one warp per hinted region decodes to the first block boundary at or past the next hint.
-__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_count_kernel(BsBatch b, uint32_t total_regions)
+__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_count_kernel(BsBatch b)
 {
+    const uint32_t total_regions = b.summary->total_regions;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
     const uint32_t warps = gridDim.x * BS_WARPS_PER_CTA;
@@ -203,8 +218,9 @@ __global__ void bs_chain_kernel(BsBatch b)
 }
 
 // Chunk decode into 16-bit cells: one warp per hinted region.
-__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_decode_kernel(BsBatch b, uint32_t total_regions)
+__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_decode_kernel(BsBatch b)
 {
+    const uint32_t total_regions = b.summary->total_regions;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
     const uint32_t warps = gridDim.x * BS_WARPS_PER_CTA;

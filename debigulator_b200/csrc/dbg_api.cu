@@ -82,6 +82,7 @@ struct dbg_ctx {
     bool bsplit = true;
     uint64_t bsplit_min_bytes = dbg::BS_MIN_BYTES;
     uint32_t bsplit_factor_q = 8;
+    uint32_t bsplit_region = dbg::REGION_BYTES, bsplit_region_min = 16384;
     uint64_t bs_streams = 0, bs_fallbacks = 0;  // counters: streams that took the block-split path / were handed back
     uint32_t split_max_streams = 1536;  // batches with fewer streams may use the split-stream path (measured crossover ~1,500 images of 1024^2)
     bool verify = false;                // opt-in: check gzip CRC32 / ISIZE trailers
@@ -175,7 +176,9 @@ extern "C" dbg_ctx *dbg_create(int device)
     if (const char *e = getenv("DBG_SPLIT_MAX_STREAMS")) ctx->split_max_streams = (uint32_t)atoi(e);
     if (const char *e = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(e) != 0;
     if (const char *e = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(e));
-    if (const char *e = getenv("DBG_BSPLIT_MIN_BYTES")) ctx->bsplit_min_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 2 * dbg::REGION_BYTES);
+    if (const char *e = getenv("DBG_BSPLIT_REGION")) ctx->bsplit_region = (uint32_t)std::min(1 << 20, std::max(4096, atoi(e)));
+    if (const char *e = getenv("DBG_BSPLIT_REGION_MIN")) ctx->bsplit_region_min = (uint32_t)std::min((int)ctx->bsplit_region, std::max(4096, atoi(e)));
+    if (const char *e = getenv("DBG_BSPLIT_MIN_BYTES")) ctx->bsplit_min_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 2 * (uint64_t)ctx->bsplit_region);
     if (const char *e = getenv("DBG_INFLATE_CTAS_PER_SM")) {
         int v = atoi(e);
         if (v >= 1 && v <= dbg::INFLATE_CTAS_PER_SM) ctx->inflate_ctas_per_sm = (uint32_t)v;
@@ -411,8 +414,14 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     }
     CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
     *regular_done = true;
-    const uint32_t T = hs->total_regions;
+    // region size: 64 KiB when that already gives every resident warp a few regions, else smaller (more, shorter
+    // chunks: the latency of a lone long stream is the decode time of its longest chunk)
+    uint32_t region = ctx->bsplit_region;
+    while (region > ctx->bsplit_region_min && hs->split_in / region < 4ull * b.resident_warps) region >>= 1;
+    b.region_bytes = region;
+    const uint32_t T = (uint32_t)(hs->split_in / region) + hs->n_split;  // upper bound of the region count
     CU(br.reserve((size_t)T * (4 + 8 + 8 + 8 + 4 + 4) + 256));
+    CU(cudaMemsetAsync(br.p, 0, (size_t)T * (4 + 8 + 8 + 8 + 4 + 4), s));
     b.cand = (uint64_t *)br.p;
     b.exit_bits = b.cand + T;
     b.c_out_off = b.exit_bits + T;
@@ -422,9 +431,11 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     const size_t smem = sizeof(dbg::InflateSmem) * dbg::BS_WARPS_PER_CTA;
     const uint32_t grid = std::min<uint32_t>((T + dbg::BS_WARPS_PER_CTA - 1) / dbg::BS_WARPS_PER_CTA,
                                              (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);
+    dbg::bs_assign_kernel<<<sb, 128, 0, s>>>(b);
+    ctx->launches++;
     dbg::bs_fill_kernel<<<n, 128, 0, s>>>(b);
-    dbg::bs_search_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, 0, s>>>(b, T);
-    dbg::bs_count_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b, T);
+    dbg::bs_search_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, 0, s>>>(b);
+    dbg::bs_count_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b);
     dbg::bs_chain_kernel<<<sb, 128, 0, s>>>(b);
     ctx->launches += 4;
     CU(cudaGetLastError());
@@ -435,7 +446,7 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     if (hs->cells_used) {
         CU(bc.reserve((size_t)hs->cells_used * 2 + 256));
         b.cells = (uint16_t *)bc.p;
-        dbg::bs_decode_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b, T);
+        dbg::bs_decode_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b);
         // cells -> bytes with the split-stream path's resolve kernels
         dbg::SplitBatch r{};
         r.out_base = a.out_base; r.out_off = a.out_off; r.out_size = a.out_size; r.status = a.status; r.n = n;
