@@ -317,6 +317,20 @@ def run_ours(args):
     for k in (0, 1, 2, 3, n - 1):
         assert hout_np[k * stride:k * stride + size].tobytes() == uniq[k % N_UNIQUE][1], "e2e payload mismatch"
     e2e_val = world * out_total * e2e_steps / e2e_s / 1e9
+    # the link ceiling of that path: the same pinned arenas copied H2D and D2H at once, nothing else running
+    pcie = None
+    if rank == 0 and world == 1:
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            with torch.cuda.stream(s_up):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 2
+        pcie = {"h2d_plus_d2h_s": dt, "output_GBps_if_copies_only": out_total / dt / 1e9}
 
     # ---- PNG (BASELINE config 3 shape), secondary metric
     png = None
@@ -371,7 +385,8 @@ def run_ours(args):
                        "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % ((comp_bytes + out_total) / 1e9),
                        "parallelism": f"{world} independent shard(s), no collective"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(in_total + 64), "d2h_bytes_per_step": int(out_span),
-                    "steps": e2e_steps, "api": "dbg_decode_batch_packed(kind=gzip), pinned host arenas"},
+                    "steps": e2e_steps, "api": "dbg_decode_batch_packed(kind=gzip), pinned host arenas",
+                    "link_ceiling": pcie},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": "profiles/r01_inflate_traffic.json (ncu --set full)" if traffic else None,
