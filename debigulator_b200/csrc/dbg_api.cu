@@ -59,9 +59,9 @@ struct dbg_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    static constexpr int MAX_WAVES = 8;
+    static constexpr int MAX_WAVES = 16;
     cudaStream_t wave_stream[MAX_WAVES] = {};
-    int waves = 8;  // waves the packed host API cuts a large batch into (H2D / kernels / D2H overlap); measured 26.6 GB/s vs 25.8 at 4
+    int waves = 16;  // waves the packed host API cuts a large batch into (H2D / kernels / D2H overlap); cfg2 end to end: 2 -> 23.5, 4 -> 25.8, 8 -> 26.7, 16 -> 27.4 GB/s
     cudaEvent_t wave_ready = nullptr;
     cudaStream_t aux_stream = nullptr;  // the warp-per-stream kernel runs here beside the block-split kernels
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
@@ -498,7 +498,7 @@ static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t
                                const uint32_t *d_order, cudaStream_t s, uint64_t *gz_off, uint64_t *gz_size,
                                uint32_t *gz_pre)
 {
-    CU(ctx->d_counter.reserve(64 * sizeof(uint32_t)));
+    CU(ctx->d_counter.reserve(8 * dbg_ctx::MAX_WAVES * sizeof(uint32_t)));
     uint32_t *counter = (uint32_t *)ctx->d_counter.p + 8 * slot;
     if (gz_off) {
         dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, gz_off, gz_size, gz_pre);
@@ -578,7 +578,7 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
     }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    CU(ctx->d_counter.reserve(64 * sizeof(uint32_t)));
+    CU(ctx->d_counter.reserve(8 * dbg_ctx::MAX_WAVES * sizeof(uint32_t)));
     CU(ctx->d_png_scratch.reserve(dbg::png_scratch_bytes(n, total_in_bytes, total_rgba_bytes)));
     dbg::PngLayout lay = dbg::png_layout((uint8_t *)ctx->d_png_scratch.p, n, total_in_bytes, total_rgba_bytes);
 
