@@ -75,9 +75,10 @@ struct dbg_ctx {
     Buf d_counter;                 // work-queue heads
     Buf d_meta;                    // derived descriptors (gzip payloads, PNG streams)
     Buf d_png_scratch;             // compacted IDAT + filtered scanlines
-    Buf d_split, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
+    Buf d_split, d_split_chunks, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
     // block-split path (long multi-block streams): per wave slot, since waves run concurrently
     Buf d_sched[MAX_WAVES];        // work-queue order computed on the device when the caller brings none
+    uint32_t split_chunk_forced = 0;  // DBG_SPLIT_CHUNK: fixed chunk size of the split-stream path (experiments)
     bool bsplit_allowed = true;    // cleared while the packed API runs several waves at once
     Buf d_bs_stream[MAX_WAVES], d_bs_region[MAX_WAVES], d_bs_cells[MAX_WAVES], h_bs_summary[MAX_WAVES];
     bool bsplit = true;
@@ -175,6 +176,7 @@ extern "C" dbg_ctx *dbg_create(int device)
     cudaFuncSetAttribute(dbg::split_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA));
     if (const char *e = getenv("DBG_SPLIT_MAX_STREAMS")) ctx->split_max_streams = (uint32_t)atoi(e);
+    if (const char *e = getenv("DBG_SPLIT_CHUNK")) ctx->split_chunk_forced = (uint32_t)std::min(1 << 20, std::max(4096, atoi(e))) & ~15u;
     if (const char *e = getenv("DBG_WAVES")) ctx->waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(e)));
     if (const char *e = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(e) != 0;
     if (const char *e = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(e));
@@ -194,7 +196,8 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Buf *all[] = {&ctx->d_counter, &ctx->d_meta, &ctx->d_png_scratch, &ctx->d_in,    &ctx->d_out,    &ctx->d_desc,
-                  &ctx->h_in,      &ctx->h_out,  &ctx->h_desc,        &ctx->d_split, &ctx->d_cells, &ctx->h_summary};
+                  &ctx->h_in,      &ctx->h_out,  &ctx->h_desc,        &ctx->d_split, &ctx->d_cells, &ctx->h_summary,
+                  &ctx->d_split_chunks};
     for (Buf *b : all) b->release();
     for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) {
         ctx->d_sched[i].release();
@@ -297,15 +300,13 @@ static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_c
 
 // Split-stream path for batches that cannot fill the GPU with one warp per stream: streams that are a
 // single fixed-Huffman block (every stb-written PNG) are cut into 32 KiB chunks decoded by one warp each.
-// Needs one small device->host read (how many chunks / cells) and therefore synchronises `s` once.
+// Needs one small device->host read (how many streams / bytes / cells) and therefore synchronises `s` once.
 static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t **skip_out)
 {
     *skip_out = nullptr;
     const uint32_t n = a.n;
     CU(ctx->h_summary.reserve(sizeof(dbg::SplitSummary)));
-    // per-stream scratch first; per-chunk scratch once the chunk count is known
-    size_t per_stream = (size_t)n * (4 + 4 + 4 + 8) + 256;
-    CU(ctx->d_split.reserve(per_stream + sizeof(dbg::SplitSummary) + 256));
+    CU(ctx->d_split.reserve(256 + (size_t)n * (8 + 4 + 4 + 4) + 256));
     uint8_t *p = (uint8_t *)ctx->d_split.p;
     dbg::SplitBatch b{};
     b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
@@ -316,57 +317,54 @@ static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, c
     b.split_flag = (uint32_t *)(b.cell_base + n);
     b.chunk_base = b.split_flag + n;
     b.nchunks = b.chunk_base + n;
+    const unsigned sb = (n + 127) / 128;
     CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::SplitSummary), s));
-    dbg::split_classify_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);
+    dbg::split_classify_kernel<<<sb, 128, 0, s>>>(b);
     ctx->launches++;
     CU(cudaGetLastError());
     dbg::SplitSummary *hs = (dbg::SplitSummary *)ctx->h_summary.p;
     CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::SplitSummary), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    if (hs->total_chunks == 0) return DBG_OK;
-    const uint32_t T = hs->total_chunks;
-    // growing d_split would drop the per-stream arrays just written: they are re-created below if it moves
-    size_t per_chunk = (size_t)T * (4 + 8 + 8 + 4 + 4 + 32 * sizeof(dbg::TransferEntry)) + 1024;
-    size_t need = per_stream + sizeof(dbg::SplitSummary) + 256 + per_chunk;
-    if (need > ctx->d_split.cap) {
-        CU(ctx->d_split.reserve(need));
-        p = (uint8_t *)ctx->d_split.p;
-        b.summary = (dbg::SplitSummary *)p;
-        b.cell_base = (uint64_t *)(p + 256);
-        b.split_flag = (uint32_t *)(b.cell_base + n);
-        b.chunk_base = b.split_flag + n;
-        b.nchunks = b.chunk_base + n;
-        CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::SplitSummary), s));
-        dbg::split_classify_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);  // same inputs, same decisions
-        ctx->launches++;
-        CU(cudaGetLastError());
-    }
-    uint8_t *q = p + ((per_stream + sizeof(dbg::SplitSummary) + 256 + 255) & ~(size_t)255);
+    if (hs->n_split == 0) return DBG_OK;
+    // chunk size: 32 KiB, doubled (up to 512 KiB) while the longest stream would otherwise have more than 512
+    // chunks and the batch still has a chunk for every second resident warp. The last 32 KiB of every chunk's
+    // output is resolved by a per-stream serial chain (the tails, ~10 us per chunk), which for 150 MB streams
+    // is the longest kernel of the step at 32 KiB (measured, four 8192^2 images: 149 ms per step at 32 KiB,
+    // 121 at 64, 116 at 128, 110 at 256); short streams keep small chunks (more parallelism per stream).
+    const uint64_t resident = (uint64_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM * dbg::SPLIT_WARPS_PER_CTA;
+    uint32_t chunk = dbg::CHUNK_BYTES;
+    while (chunk < 16 * dbg::CHUNK_BYTES && hs->max_in / chunk > 512 && hs->split_in / (2 * chunk) >= resident / 2) chunk <<= 1;
+    if (ctx->split_chunk_forced) chunk = ctx->split_chunk_forced;
+    b.chunk_bytes = chunk;
+    const uint32_t T = (uint32_t)(hs->split_in / chunk) + hs->n_split;  // upper bound of the chunk count
+    const size_t per_chunk = (size_t)T * (4 + 8 + 8 + 4 + 4 + 32 * sizeof(dbg::TransferEntry)) + 1024;
+    CU(ctx->d_split_chunks.reserve(per_chunk));
+    uint8_t *q = (uint8_t *)ctx->d_split_chunks.p;
     b.entry_bits = (uint64_t *)q;
     b.c_out_off = b.entry_bits + T;
     b.tf = (dbg::TransferEntry *)(b.c_out_off + T);
     b.chunk_stream = (uint32_t *)(b.tf + (size_t)T * 32);
     b.c_out_len = b.chunk_stream + T;
     b.c_flag = b.c_out_len + T;
+    CU(cudaMemsetAsync(b.chunk_stream, 0, (size_t)T * 12, s));  // chunk_stream, c_out_len, c_flag of unused slots
     CU(ctx->d_cells.reserve((size_t)hs->cells_cap * 2 + 256));
     b.cells = (uint16_t *)ctx->d_cells.p;
     size_t smem = sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA;
     uint32_t grid = std::min<uint32_t>((T + dbg::SPLIT_WARPS_PER_CTA - 1) / dbg::SPLIT_WARPS_PER_CTA,
                                        (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);
+    dbg::split_assign_kernel<<<sb, 128, 0, s>>>(b);
     dbg::split_fill_kernel<<<n, 128, 0, s>>>(b);
-    dbg::split_transfer_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b, T);
-    dbg::split_chain_kernel<<<(n + 127) / 128, 128, 0, s>>>(b);
-    dbg::split_decode_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b, T);
+    dbg::split_transfer_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b);
+    dbg::split_chain_kernel<<<sb, 128, 0, s>>>(b);
+    dbg::split_decode_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b);
     dbg::split_resolve_tails_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(b);
     dbg::split_resolve_body_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(b, T);
-    ctx->launches += 6;
+    ctx->launches += 7;
     CU(cudaGetLastError());
     *skip_out = b.split_flag;
     return DBG_OK;
 }
 
-// Block-split path for the long streams of a batch (bsplit_kernels.cuh). Two small device->host reads:
-// how many regions, then how many cells. `taken` marks streams the split-stream path already owns.
 static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot, bool may_order = true);
 
 // When streams do take this path, the warp-per-stream kernel for all the others is launched from here, on an

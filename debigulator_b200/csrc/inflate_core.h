@@ -869,7 +869,7 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
 //             marker (256 + 32768 - distance_before_chunk_start).
 //   resolve   one CTA per stream, chunk after chunk: cells -> bytes, markers
 //             read the already finished output.
-enum { CHUNK_BYTES = 32768, CHUNK_BITS = CHUNK_BYTES * 8 };
+enum { CHUNK_BYTES = 32768 };  // smallest chunk; the host doubles it (up to 8x) for very large batches, see run_split
 enum : uint32_t { CH_RUN = 0, CH_EOB = 1, CH_Q2 = 2, CH_IDLE = 3, CH_ERR = 16 };  // CH_ERR + status
 
 // Lane-local fixed-Huffman size decode of the symbol at ring bit `pos`:
@@ -912,7 +912,8 @@ struct TransferEntry {   // result of entering a chunk at bit (chunk start + lan
 // Transfer table of chunk `chunk` (>= 1) of a single-fixed-block stream; lane j
 // writes table[j]. Chunk 0 has one known entry (bit 3) and is computed by lane 0
 // semantics: every lane starts at bit 3, so all 32 entries are identical.
-DBG_DEV void transfer_chunk_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint32_t chunk, TransferEntry *table)
+DBG_DEV void transfer_chunk_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint32_t chunk, uint32_t chunk_bytes,
+                                 TransferEntry *table)
 {
     const uint32_t ln = (uint32_t)simt::lane();
     Window w;
@@ -921,8 +922,8 @@ DBG_DEV void transfer_chunk_warp(InflateSmem *sm, const uint8_t *in, uint64_t in
     bt.lit_max = bt.dist_max = 0;
     read_huffman_tables(w, sm, 1, bt);  // the fixed code
     const uint64_t off = 8ull * g.mis;  // stream-relative bit -> ring-coordinate bit
-    const uint64_t start = (uint64_t)chunk * CHUNK_BITS + off;
-    const uint64_t stop = start + CHUNK_BITS;
+    const uint64_t start = (uint64_t)chunk * chunk_bytes * 8 + off;
+    const uint64_t stop = start + (uint64_t)chunk_bytes * 8;
     uint64_t pos = chunk == 0 ? off + 3 : start + ln;
     uint32_t outb = 0, flag = CH_RUN;
     // the input is walked in 512-byte ring chunks; all lanes stay within 31 bits of each other
@@ -978,8 +979,8 @@ DBG_DEV bool is_single_fixed_block(const uint8_t *in) { return (in[0] & 7) == 3;
 
 // Decodes chunk `chunk` from its exact entry bit (stream-relative) into cells.
 template <int SINK>
-DBG_DEV ChunkResult decode_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint32_t chunk, uint64_t entry_bits,
-                                 uint16_t *cells, uint32_t cell_cap, uint64_t abs_base)
+DBG_DEV ChunkResult decode_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint32_t chunk, uint32_t chunk_bytes,
+                                 uint64_t entry_bits, uint16_t *cells, uint32_t cell_cap, uint64_t abs_base)
 {
     ChunkResult r;
     Window w;
@@ -988,7 +989,7 @@ DBG_DEV ChunkResult decode_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in
     bt.lit_max = bt.dist_max = 0;
     read_huffman_tables(w, sm, 1, bt);
     const uint64_t off = 8ull * g.mis;
-    const uint64_t chunk_end = (uint64_t)(chunk + 1) * CHUNK_BITS + off;
+    const uint64_t chunk_end = (uint64_t)(chunk + 1) * chunk_bytes * 8 + off;
     const bool q2_first = g.q2_limit <= chunk_end;
     w.lim_w = (uint32_t)((q2_first ? g.q2_limit : chunk_end) >> 5);
     w.lim_b = (uint32_t)(q2_first ? g.q2_limit : chunk_end) & 31;

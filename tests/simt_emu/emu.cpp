@@ -135,7 +135,7 @@ struct ChunkArgs {
     dbg::InflateSmem *sm;
     const uint8_t *in;
     uint64_t in_size;
-    uint32_t chunk;
+    uint32_t chunk, chunk_bytes;
     uint64_t entry;
     uint16_t *cells;
     uint32_t cell_cap;
@@ -149,15 +149,15 @@ static void chunk_body(void *p)
     ChunkArgs *a = (ChunkArgs *)p;
     int l = simt::lane();
     if (a->write)
-        a->res[l] = dbg::decode_chunk<dbg::SINK_U16>(a->sm, a->in, a->in_size, a->chunk, a->entry, a->cells, a->cell_cap, a->abs_base);
+        a->res[l] = dbg::decode_chunk<dbg::SINK_U16>(a->sm, a->in, a->in_size, a->chunk, a->chunk_bytes, a->entry, a->cells, a->cell_cap, a->abs_base);
     else
-        dbg::transfer_chunk_warp(a->sm, a->in, a->in_size, a->chunk, a->table);
+        dbg::transfer_chunk_warp(a->sm, a->in, a->in_size, a->chunk, a->chunk_bytes, a->table);
 }
 
 // The whole split-stream pipeline (transfer tables, chain, 16-bit decode, resolve) run chunk
 // by chunk through the emulator, mirroring split_kernels.cuh. Returns the status.
 extern "C" uint32_t emu_split_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
-                                      int misalign, int reverse)
+                                      int misalign, int reverse, uint32_t chunk_bytes)
 {
     size_t arena_sz = ((size_t)in_size + 64 + 32 + 15) & ~(size_t)15;
     uint8_t *arena = (uint8_t *)aligned_alloc(16, arena_sz);
@@ -168,12 +168,12 @@ extern "C" uint32_t emu_split_inflate(const uint8_t *in, uint64_t in_size, uint8
     *final_size = 0;
     uint32_t status = 0;
     if (!dbg::is_single_fixed_block(src)) { free(sm); free(arena); return 0x2000; }
-    uint32_t nch = (uint32_t)((in_size + dbg::CHUNK_BYTES - 1) / dbg::CHUNK_BYTES);
+    uint32_t nch = (uint32_t)((in_size + chunk_bytes - 1) / chunk_bytes);
     dbg::TransferEntry *tf = (dbg::TransferEntry *)calloc((size_t)nch * 32, sizeof(dbg::TransferEntry));
     uint64_t *entry = (uint64_t *)calloc(nch, 8), *ooff = (uint64_t *)calloc(nch + 1, 8);
     uint32_t *olen = (uint32_t *)calloc(nch, 4), *flag = (uint32_t *)calloc(nch, 4);
     ChunkArgs a;
-    a.sm = sm; a.in = src; a.in_size = in_size; a.cells = nullptr;
+    a.sm = sm; a.in = src; a.in_size = in_size; a.cells = nullptr; a.chunk_bytes = chunk_bytes;
     for (uint32_t c = 0; c < nch; c++) {
         a.chunk = c; a.write = 0; a.table = tf + (size_t)c * 32;
         simt::run_warp(chunk_body, &a, reverse);
@@ -185,7 +185,7 @@ extern "C" uint32_t emu_split_inflate(const uint8_t *in, uint64_t in_size, uint8
         ooff[c] = total;
         if (ended) { flag[c] = dbg::CH_IDLE; continue; }
         dbg::TransferEntry t = tf[(size_t)c * 32 + idx];
-        entry[c] = c == 0 ? 3 : (uint64_t)c * dbg::CHUNK_BITS + idx;
+        entry[c] = c == 0 ? 3 : (uint64_t)c * chunk_bytes * 8 + idx;
         olen[c] = t.out_bytes; flag[c] = t.flag; total += t.out_bytes;
         if (t.flag != dbg::CH_RUN) { ended = true; if (t.flag >= dbg::CH_ERR) status = dbg::ST_BAD_SYMBOL; }
         idx = t.next;

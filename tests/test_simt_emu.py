@@ -31,7 +31,7 @@ def emu():
     L.emu_inflate.restype = C.c_uint32
     L.emu_png_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
     L.emu_png_decode.restype = C.c_uint32
-    L.emu_split_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+    L.emu_split_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_uint32]
     L.emu_split_inflate.restype = C.c_uint32
     L.emu_bsplit_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int,
                                      C.c_uint32, C.POINTER(C.c_uint32)]
@@ -120,7 +120,7 @@ def test_split_stream_kernel_source(emu):
         ib = C.create_string_buffer(z, len(z))
         ob = C.create_string_buffer(cap + 64)
         n = C.c_uint64(0)
-        st = emu.emu_split_inflate(ib, len(z), ob, cap, C.byref(n), (3 * k) % 16, k & 1)
+        st = emu.emu_split_inflate(ib, len(z), ob, cap, C.byref(n), (3 * k) % 16, k & 1, (32768, 4096, 65536, 8192)[k % 4])
         assert st == 0, (k, st)
         assert ob.raw[: n.value] == zlib.decompress(z, -15), k
 
