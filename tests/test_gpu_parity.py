@@ -263,3 +263,74 @@ def test_block_split_false_hints_fall_back(ctx, ref):
     assert good == rg == 1 and out == rout
     assert g2 == 1 and out2 == text
     assert after[1] - before[1] == 1 and after[0] - before[0] == 1, (before, after)
+
+
+def test_block_split_equals_warp_per_stream_on_damaged_streams():
+    """The block-split path with tiny regions (forced on every stream of >= 64 KiB) against the warp-per-stream
+    path of the same library on intact, truncated and bit-flipped streams: same verdict, same bytes. Intact
+    streams are also checked against zlib. (The reference itself is not run on damaged input: it has no bounds
+    checks there.)"""
+    import debigulator_b200 as dbg
+    rng = np.random.default_rng(4242)
+
+    def many_blocks(data, level, mem):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, mem)
+        return c.compress(data) + c.flush()
+
+    streams, intact = [], []
+    for k in range(48):
+        n = int(rng.integers(200_000, 1_500_000))
+        kind = k % 6
+        if kind == 0:
+            data = corpus.word_salad(n, 500 + k)
+        elif kind == 1:
+            data = corpus.low_entropy(n, 500 + k, 5)
+        elif kind == 2:
+            data = corpus.periodic(n, 500 + k, int(rng.integers(300, 32000)))
+        elif kind == 3:
+            data = corpus.runs(n * 4, 500 + k)
+        elif kind == 4:
+            data = corpus.word_salad(n // 2, 500 + k) + bytes(rng.integers(0, 256, n // 8, dtype=np.uint8)) + corpus.word_salad(n // 2, 900 + k)
+        else:
+            data = corpus.png_filter_rows(corpus.gradient_noise_rgba(512, int(n // 2048) + 8, k), 4)
+        z = corpus.mixed_deflate(data, k) if k % 8 == 7 else many_blocks(data, int(rng.choice([1, 6, 9])), int(rng.choice([1, 4, 8, 9])))
+        if len(z) < 70_000:
+            continue
+        streams.append(z)
+        intact.append(data)
+        if k % 3 == 0:  # truncated
+            streams.append(z[: int(len(z) * rng.uniform(0.3, 0.95))])
+            intact.append(None)
+        if k % 3 == 1:  # a few flipped bits
+            b = bytearray(z)
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(len(b) // 10, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            streams.append(bytes(b))
+            intact.append(None)
+    caps = [12 << 20] * len(streams)
+    old = {k: os.environ.get(k) for k in ("DBG_BSPLIT", "DBG_BSPLIT_REGION", "DBG_BSPLIT_REGION_MIN", "DBG_BSPLIT_MIN_BYTES")}
+    try:
+        os.environ.update({"DBG_BSPLIT": "1", "DBG_BSPLIT_REGION": "8192", "DBG_BSPLIT_REGION_MIN": "4096", "DBG_BSPLIT_MIN_BYTES": "65536"})
+        split_ctx = dbg.Context(0)
+        os.environ["DBG_BSPLIT"] = "0"
+        plain_ctx = dbg.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    a = split_ctx.inflate_batch(streams, caps)
+    b = plain_ctx.inflate_batch(streams, caps)
+    taken, fallbacks = split_ctx.bsplit_stats()
+    assert plain_ctx.bsplit_stats() == (0, 0) and taken >= len(streams) // 2, (taken, fallbacks)
+    for k, ((ga, oa), (gb, ob)) in enumerate(zip(a, b)):
+        assert ga == gb, k
+        if ga:
+            assert oa == ob, k
+        if intact[k] is not None:
+            assert ga == 1 or len(oa) == 0  # rule Q2 may end low-entropy streams early; then both paths agree above
+            if ga and len(oa) == len(intact[k]):
+                assert oa == intact[k], k
+    split_ctx.close()
+    plain_ctx.close()
