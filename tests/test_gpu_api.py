@@ -210,17 +210,17 @@ def test_failed_items_do_not_poison_batch(ctx):
 
 
 def test_example_mains_print_the_readme_golden(golden_dir, tmp_path):
-    """examples/hellopng.c and hellogz.c (the roles of the reference's stale examples) build with gcc against
+    """examples/hellopng.c, hellogz.c and hellobmp.c (the roles of the reference's stale examples) build with gcc against
     include/*.h and print the reference README's golden for gimp_test.png (README.md:41-47)."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = os.path.join(root, "debigulator_b200")
     outs = {}
-    for name in ("hellopng", "hellogz"):
+    for name in ("hellopng", "hellogz", "hellobmp"):
         exe = str(tmp_path / name)
         subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", name + ".c"),
                                "-L" + lib, "-ldebigulator_b200", "-Wl,-rpath," + lib, "-o", exe])
-        arg = os.path.join(golden_dir, "gimp_test.png" if name == "hellopng" else "gzipsample.gz")
+        arg = os.path.join(golden_dir, {"hellopng": "gimp_test.png", "hellogz": "gzipsample.gz", "hellobmp": "fs_psychologist.bmp"}[name])
         outs[name] = subprocess.run([exe, arg], capture_output=True, text=True, timeout=300)
         assert outs[name].returncode == 0, outs[name].stdout + outs[name].stderr
     p = outs["hellopng"].stdout
@@ -229,6 +229,10 @@ def test_example_mains_print_the_readme_golden(golden_dir, tmp_path):
                  "average pixel: [248,249,251,158]"):
         assert line in p, p
     assert "decompressed bytes: 561872" in outs["hellogz"].stdout
+    b = outs["hellobmp"].stdout
+    for line in ("image width: 406", "image height: 610", "decode_BMP result was: SUCCESS", "encode_BMP wrote: 990695 bytes",
+                 "round trip: EXACT"):
+        assert line in b, b
 
 
 def test_optin_gzip_trailer_verification(ctx):
