@@ -227,7 +227,8 @@ DBG_DEV uint64_t find_block_start(SearchSmem *q, const uint16_t *kraft12, const 
 // past `stop_bit` (BS_NONE: to the end of the stream). SINK_COUNT: sizes only; SINK_U16: into cells.
 template <int SINK>
 DBG_DEV ChunkResult decode_block_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint64_t start_bit, uint64_t stop_bit,
-                                       uint16_t *cells, uint32_t cell_cap, uint64_t abs_base)
+                                       uint16_t *cells, uint32_t cell_cap, uint64_t abs_base, uint32_t *tok = nullptr,
+                                       uint32_t tok_cap = 0)
 {
     ChunkResult r;
     Window w;
@@ -243,14 +244,68 @@ DBG_DEV ChunkResult decode_block_chunk(InflateSmem *sm, const uint8_t *in, uint6
     k.pd.ptr = nullptr;
     k.pd.val = 0;
     k.pd.on = false;
+    k.tok = tok;
+    k.ntok = 0;
+    k.tok_cap = tok_cap;
     uint32_t end = BLK_FINAL;
     const uint32_t st = inflate_blocks<SINK>(w, g, sm, k, stop_bit == BS_NONE ? BS_NONE : stop_bit + off, end);
     if (SINK == SINK_U16) flush_pending16(k.pd);
     r.exit_bits = w.abs_bits() - off;
     r.out_bytes = k.pos;
+    r.ntok = k.ntok;
     if (st) r.flag = CH_ERR + st;
     else r.flag = end == BLK_STOP ? CH_RUN : end == BLK_FINAL ? CH_EOB : CH_Q2;
     return r;
+}
+
+// Second pass over a chunk whose symbols were recorded as tokens: expands them into the chunk's 16-bit
+// cells. 32 tokens per step: an exclusive scan of their lengths gives every token its output offset, all
+// literals are stored at once, then the matches -- those that only read what lies before this step's
+// output and are short are copied by their own lane, all at the same time; the others (they may read
+// what this step writes, or are long) one after the other with the whole warp. Returns ST_OK or the
+// status of a distance that reaches before the start of the stream (inflate.c:1843).
+DBG_DEV uint32_t expand_tokens_warp(const uint32_t *tok, uint32_t ntok, uint16_t *cells, uint64_t abs_base, uint32_t *out_bytes)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    uint32_t pos = 0, err = ST_OK;
+    for (uint32_t base = 0; base < ntok; base += 32) {
+        const bool have = base + ln < ntok;
+        const uint32_t t = have ? simt::ldg_u32(tok + base + ln) : 0u;
+        const bool is_match = have && (t & TOKEN_MATCH);
+        const uint32_t len = !have ? 0u : is_match ? (t >> 16) & 0x1ff : 1u;
+        const uint32_t dist = (t & 0x7fff) + 1;
+        uint32_t incl = len;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = simt::shfl_up(incl, d);
+            if (ln >= (uint32_t)d) incl += y;
+        }
+        const uint32_t o = pos + incl - len;        // this token's output offset
+        const uint32_t total = simt::shfl(incl, 31);
+        if (have && !is_match) cells[o] = (uint16_t)t;
+        // a match is "free" when its whole source lies before this step's output and it is short
+        const bool bad = is_match && dist > abs_base + o;
+        const bool free_m = is_match && !bad && len <= 24 && o + len <= pos + dist;
+        if (simt::any(bad)) {
+            err = ST_BAD_DISTANCE;
+            break;
+        }
+        if (free_m) {
+            for (uint32_t i = 0; i < len; i++) {
+                const int32_t si = (int32_t)(o + i) - (int32_t)dist;
+                cells[o + i] = si < 0 ? (uint16_t)(256 + 32768 + si) : cells[si];
+            }
+        }
+        simt::syncwarp();  // literals and free matches of this step are in place
+        uint32_t m = simt::ballot(is_match && !free_m);
+        while (m) {
+            const int j = simt::ffs(m) - 1;
+            m &= m - 1;
+            copy_match_u16(cells, simt::shfl(o, j), simt::shfl(len, j), simt::shfl(dist, j));
+        }
+        pos += total;
+    }
+    *out_bytes = pos;
+    return err;
 }
 
 }  // namespace dbg

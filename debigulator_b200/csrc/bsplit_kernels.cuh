@@ -21,6 +21,7 @@ struct BsSummary {         // device -> host after classify, and again after cha
     uint32_t n_fallback;   // streams whose chain did not close
     uint32_t pad;
     uint64_t split_in;     // compressed bytes of the streams taking this path
+    uint64_t tok_bytes;    // allocation cursor of the token areas, in compressed bytes (bs_assign_kernel)
 };
 
 struct BsBatch {
@@ -52,7 +53,23 @@ struct BsBatch {
     uint32_t *c_out_len;    // per region
     uint32_t *c_flag;       // per region
     uint16_t *cells;
+    // tokens recorded by the count pass (optional: tok == nullptr = decode twice)
+    uint32_t *tok;
+    uint64_t *tok_stream_base;  // per stream: first token slot
+    uint32_t *c_ntok;           // per region: symbols seen by the count pass
+    uint32_t tok_per_byte;      // token slots per compressed byte; a chunk that needs more is Huffman-decoded again
 };
+
+// Token area of the chunk that starts at stream bit `start` and ends at the next hint (or the stream end).
+__device__ __forceinline__ uint64_t bs_tok_base(const BsBatch &b, uint32_t s, uint64_t start)
+{
+    return b.tok_stream_base[s] + (uint64_t)b.tok_per_byte * (start >> 3);
+}
+__device__ __forceinline__ uint32_t bs_tok_cap(const BsBatch &b, uint32_t s, uint64_t start, uint64_t next_hint)
+{
+    const uint64_t end_byte = next_hint == BS_NONE ? b.in_size[s] : next_hint >> 3;
+    return (uint32_t)((uint64_t)b.tok_per_byte * (end_byte - (start >> 3)));
+}
 
 __global__ void bs_sum_kernel(BsBatch b)
 {
@@ -96,6 +113,9 @@ __global__ void bs_assign_kernel(BsBatch b)
     const uint32_t nreg = (uint32_t)((b.in_size[s] + b.region_bytes - 1) / b.region_bytes);
     b.chunk_base[s] = atomicAdd(&b.summary->total_regions, nreg);
     b.nchunks[s] = nreg;
+    if (b.tok)
+        b.tok_stream_base[s] = (uint64_t)b.tok_per_byte *
+                               atomicAdd((unsigned long long *)&b.summary->tok_bytes, (unsigned long long)b.in_size[s]);
 }
 
 __global__ void bs_fill_kernel(BsBatch b)
@@ -145,12 +165,18 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_count_kernel(BsBatch
         const uint64_t start = b.cand[t];
         if (start == BS_NONE) continue;
         const uint32_t s = b.chunk_stream[t];
-        const ChunkResult r = decode_block_chunk<SINK_COUNT>(sm, b.in_base + b.in_off[s], b.in_size[s], start, bs_next_hint(b, s, t),
-                                                             nullptr, 0, 0);
+        const uint64_t next = bs_next_hint(b, s, t);
+        ChunkResult r;
+        if (b.tok)
+            r = decode_block_chunk<SINK_TOKENS>(sm, b.in_base + b.in_off[s], b.in_size[s], start, next, nullptr, 0, 0,
+                                                b.tok + bs_tok_base(b, s, start), bs_tok_cap(b, s, start, next));
+        else
+            r = decode_block_chunk<SINK_COUNT>(sm, b.in_base + b.in_off[s], b.in_size[s], start, next, nullptr, 0, 0);
         if (simt::lane() == 0) {
             b.exit_bits[t] = r.exit_bits;
             b.c_out_len[t] = r.out_bytes;
             b.c_flag[t] = r.flag;
+            if (b.tok) b.c_ntok[t] = r.ntok;
         }
         simt::syncwarp();
     }
@@ -228,8 +254,19 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_decode_kernel(BsBatc
         const uint32_t s = b.chunk_stream[t];
         if (!b.flag[s] || b.redo[s] || b.status[s] != ST_OK || b.c_flag[t] == CH_IDLE) continue;
         const uint64_t stop = b.c_flag[t] == CH_RUN ? b.exit_bits[t] : BS_NONE;
-        const ChunkResult r = decode_block_chunk<SINK_U16>(sm, b.in_base + b.in_off[s], b.in_size[s], b.cand[t], stop,
-                                                           b.cells + b.cell_base[s] + b.c_out_off[t], b.c_out_len[t], b.c_out_off[t]);
+        uint16_t *cells = b.cells + b.cell_base[s] + b.c_out_off[t];
+        ChunkResult r;
+        const uint64_t next = b.tok ? bs_next_hint(b, s, t) : BS_NONE;
+        if (b.tok && b.c_ntok[t] <= bs_tok_cap(b, s, b.cand[t], next)) {
+            // every symbol of this chunk was recorded by the count pass: expand the tokens
+            const uint32_t st = expand_tokens_warp(b.tok + bs_tok_base(b, s, b.cand[t]), b.c_ntok[t], cells, b.c_out_off[t],
+                                                   &r.out_bytes);
+            r.flag = st ? CH_ERR + st : b.c_flag[t];
+            if (st) r.out_bytes = b.c_out_len[t];
+        } else {
+            r = decode_block_chunk<SINK_U16>(sm, b.in_base + b.in_off[s], b.in_size[s], b.cand[t], stop, cells, b.c_out_len[t],
+                                             b.c_out_off[t]);
+        }
         if (simt::lane() == 0) {
             uint32_t st = ST_OK;
             if (r.flag >= CH_ERR) st = r.flag - CH_ERR;  // e.g. a distance reaching before the stream start

@@ -80,7 +80,9 @@ struct dbg_ctx {
     Buf d_sched[MAX_WAVES];        // work-queue order computed on the device when the caller brings none
     uint32_t split_chunk_forced = 0;  // DBG_SPLIT_CHUNK: fixed chunk size of the split-stream path (experiments)
     bool bsplit_allowed = true;    // cleared while the packed API runs several waves at once
-    Buf d_bs_stream[MAX_WAVES], d_bs_region[MAX_WAVES], d_bs_cells[MAX_WAVES], h_bs_summary[MAX_WAVES];
+    Buf d_bs_stream[MAX_WAVES], d_bs_region[MAX_WAVES], d_bs_cells[MAX_WAVES], d_bs_tok[MAX_WAVES], h_bs_summary[MAX_WAVES];
+    uint32_t bsplit_tok_per_byte = 4;             // token slots per compressed byte (0 = no tokens: decode twice)
+    uint64_t bsplit_tok_max_bytes = 24ull << 30;  // the token area never grows beyond this
     bool bsplit = true;
     uint64_t bsplit_min_bytes = dbg::BS_MIN_BYTES;
     uint32_t bsplit_factor_q = 8;
@@ -180,6 +182,7 @@ extern "C" dbg_ctx *dbg_create(int device)
     if (const char *e = getenv("DBG_WAVES")) ctx->waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(e)));
     if (const char *e = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(e) != 0;
     if (const char *e = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(e));
+    if (const char *e = getenv("DBG_BSPLIT_TOKENS")) ctx->bsplit_tok_per_byte = (uint32_t)std::min(8, std::max(0, atoi(e)));
     if (const char *e = getenv("DBG_BSPLIT_REGION")) ctx->bsplit_region = (uint32_t)std::min(1 << 20, std::max(4096, atoi(e)));
     if (const char *e = getenv("DBG_BSPLIT_REGION_MIN")) ctx->bsplit_region_min = (uint32_t)std::min((int)ctx->bsplit_region, std::max(4096, atoi(e)));
     if (const char *e = getenv("DBG_BSPLIT_MIN_BYTES")) ctx->bsplit_min_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 2 * (uint64_t)ctx->bsplit_region);
@@ -204,6 +207,7 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
         ctx->d_bs_stream[i].release();
         ctx->d_bs_region[i].release();
         ctx->d_bs_cells[i].release();
+        ctx->d_bs_tok[i].release();
         ctx->h_bs_summary[i].release();
         if (ctx->wave_stream[i]) cudaStreamDestroy(ctx->wave_stream[i]);
     }
@@ -378,7 +382,7 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     const uint32_t n = a.n;
     Buf &bs = ctx->d_bs_stream[slot], &br = ctx->d_bs_region[slot], &bc = ctx->d_bs_cells[slot], &hsb = ctx->h_bs_summary[slot];
     CU(hsb.reserve(sizeof(dbg::BsSummary)));
-    CU(bs.reserve(256 + (size_t)n * (8 + 4 + 4 + 4 + 4) + 256));
+    CU(bs.reserve(256 + (size_t)n * (8 + 8 + 4 + 4 + 4 + 4) + 256));
     uint8_t *p = (uint8_t *)bs.p;
     dbg::BsBatch b{};
     b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
@@ -389,7 +393,8 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     b.factor_q = ctx->bsplit_factor_q;
     b.summary = (dbg::BsSummary *)p;
     b.cell_base = (uint64_t *)(p + 256);
-    b.flag = (uint32_t *)(b.cell_base + n);
+    b.tok_stream_base = b.cell_base + n;
+    b.flag = (uint32_t *)(b.tok_stream_base + n);
     b.chunk_base = b.flag + n;
     b.nchunks = b.chunk_base + n;
     b.redo = b.nchunks + n;
@@ -420,14 +425,23 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     while (region > ctx->bsplit_region_min && hs->split_in / region < 4ull * b.resident_warps) region >>= 1;
     b.region_bytes = region;
     const uint32_t T = (uint32_t)(hs->split_in / region) + hs->n_split;  // upper bound of the region count
-    CU(br.reserve((size_t)T * (4 + 8 + 8 + 8 + 4 + 4) + 256));
-    CU(cudaMemsetAsync(br.p, 0, (size_t)T * (4 + 8 + 8 + 8 + 4 + 4), s));
+    CU(br.reserve((size_t)T * (4 + 8 + 8 + 8 + 4 + 4 + 4) + 256));
+    CU(cudaMemsetAsync(br.p, 0, (size_t)T * (4 + 8 + 8 + 8 + 4 + 4 + 4), s));
     b.cand = (uint64_t *)br.p;
     b.exit_bits = b.cand + T;
     b.c_out_off = b.exit_bits + T;
     b.chunk_stream = (uint32_t *)(b.c_out_off + T);
     b.c_out_len = b.chunk_stream + T;
     b.c_flag = b.c_out_len + T;
+    b.c_ntok = b.c_flag + T;
+    // token areas: the count pass records every symbol so that the second pass need not decode Huffman codes again
+    uint32_t tpb = ctx->bsplit_tok_per_byte;
+    while (tpb > 1 && (uint64_t)tpb * 4 * hs->split_in > ctx->bsplit_tok_max_bytes) tpb >>= 1;
+    if (tpb && (uint64_t)tpb * 4 * hs->split_in <= ctx->bsplit_tok_max_bytes) {
+        CU(ctx->d_bs_tok[slot].reserve((size_t)tpb * 4 * hs->split_in + 256));
+        b.tok = (uint32_t *)ctx->d_bs_tok[slot].p;
+        b.tok_per_byte = tpb;
+    }
     const size_t smem = sizeof(dbg::InflateSmem) * dbg::BS_WARPS_PER_CTA;
     const uint32_t grid = std::min<uint32_t>((T + dbg::BS_WARPS_PER_CTA - 1) / dbg::BS_WARPS_PER_CTA,
                                              (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);

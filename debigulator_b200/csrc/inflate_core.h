@@ -446,7 +446,11 @@ DBG_DEV uint32_t decode_candidate(const InflateSmem *sm, uint32_t lo, uint32_t m
 //   SINK_U16    chunk decode for the split-stream path: 16-bit cells, where a value
 //               >= 256 is a marker "byte at distance 32768 - (v - 256) before this chunk's
 //               output start", resolved later against the finished output.
-enum { SINK_BYTES = 0, SINK_COUNT = 1, SINK_U16 = 2 };
+//   SINK_TOKENS the sizes-only pass of the block-split path, which also records every symbol as a
+//               32-bit token (literal: the byte; match: bit 31 | length << 16 | distance - 1) so that
+//               the second pass expands tokens instead of decoding Huffman codes again.
+enum { SINK_BYTES = 0, SINK_COUNT = 1, SINK_U16 = 2, SINK_TOKENS = 3 };
+constexpr uint32_t TOKEN_MATCH = 0x80000000u;
 enum { END_EOB = 0, END_LIMIT = 1 };
 
 struct Sink {
@@ -455,6 +459,8 @@ struct Sink {
     uint32_t pos;     // bytes produced so far (relative to out / out16)
     uint32_t cap;
     uint64_t abs_base;  // SINK_U16: stream output offset of out16[0] (markers may not reach before the stream)
+    uint32_t *tok;      // SINK_TOKENS: token area, `tok_cap` entries; ntok keeps counting past it (= overflow)
+    uint32_t ntok, tok_cap;
     PendingStore pd;
 };
 
@@ -462,7 +468,10 @@ struct Sink {
 template <int SINK, bool CHECK>
 DBG_DEV uint32_t emit_literal(Sink &k, uint32_t byte)
 {
-    if (SINK != SINK_COUNT) {
+    if (SINK == SINK_TOKENS) {
+        if (k.ntok < k.tok_cap && simt::lane() == 0) k.tok[k.ntok] = byte;
+        k.ntok++;
+    } else if (SINK != SINK_COUNT) {
         if (CHECK && k.pos >= k.cap) return ST_OUT_OVERFLOW;
         if (simt::lane() == 0) {
             if (SINK == SINK_BYTES) k.out[k.pos] = (uint8_t)byte;
@@ -497,7 +506,11 @@ DBG_DEV_NOINLINE void copy_match_u16(uint16_t *o, uint32_t pos, uint32_t len, ui
 template <int SINK, bool CHECK>
 DBG_DEV uint32_t emit_match(Sink &k, uint32_t len, uint32_t dist)
 {
-    if (SINK == SINK_COUNT) {
+    if (SINK == SINK_TOKENS) {
+        if (k.ntok < k.tok_cap && simt::lane() == 0) k.tok[k.ntok] = TOKEN_MATCH | (len << 16) | (dist - 1);
+        k.ntok++;
+    }
+    if (SINK == SINK_COUNT || SINK == SINK_TOKENS) {
         k.pos += len;
         return ST_OK;
     }
@@ -643,7 +656,7 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
         bool eob = false, slow = false;
         // one pass yields at most 64 symbols of at most 258 bytes: with that much room left the
         // per-symbol capacity checks are dropped
-        const bool roomy = SINK == SINK_COUNT || k.cap - k.pos >= 64 * 258;
+        const bool roomy = SINK == SINK_COUNT || SINK == SINK_TOKENS || k.cap - k.pos >= 64 * 258;
 #define DBG_WALK(CHECK)                                                                        \
         do {                                                                                   \
             cur = p;                                                                           \
@@ -786,7 +799,12 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
             if (len) {
                 const uint64_t bytepos = w.abs_bits() >> 3;
                 if (bytepos + len > g.end_byte) return ST_TRUNCATED;
-                if (SINK != SINK_COUNT) {
+                if (SINK == SINK_TOKENS) {  // stored bytes become literal tokens
+                    const uint8_t *src = w.base + bytepos;
+                    for (uint32_t i = (uint32_t)simt::lane(); i < len; i += 32)
+                        if (k.ntok + i < k.tok_cap) k.tok[k.ntok + i] = src[i];
+                    k.ntok += len;
+                } else if (SINK != SINK_COUNT) {
                     if ((uint64_t)k.pos + len > k.cap) return ST_OUT_OVERFLOW;
                     if (SINK == SINK_BYTES) {
                         copy_stored(k.out + k.pos, w.base + bytepos, len);
@@ -839,6 +857,8 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     k.pd.ptr = out;
     k.pd.val = 0;
     k.pd.on = false;
+    k.tok = nullptr;
+    k.ntok = k.tok_cap = 0;
     uint32_t end;
     const uint32_t st = inflate_blocks<SINK_BYTES>(w, g, sm, k, ~0ull, end);
     if (st) return st;
@@ -972,6 +992,7 @@ struct ChunkResult {
     uint64_t exit_bits;  // stream-relative bit where the next chunk's first symbol starts
     uint32_t out_bytes;
     uint32_t flag;
+    uint32_t ntok;       // SINK_TOKENS: symbols seen (more than the token area holds = overflow)
 };
 
 // A stream qualifies for the split path when it is one final fixed-Huffman block.
@@ -1003,11 +1024,14 @@ DBG_DEV ChunkResult decode_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in
     k.pd.ptr = nullptr;
     k.pd.val = 0;
     k.pd.on = false;
+    k.tok = nullptr;
+    k.ntok = k.tok_cap = 0;
     uint32_t why = END_EOB;
     uint32_t st = decode_symbols<SINK>(w, sm, bt, k, why);
     if (SINK == SINK_U16) flush_pending16(k.pd);
     r.exit_bits = w.abs_bits() - off;
     r.out_bytes = k.pos;
+    r.ntok = 0;
     if (st) r.flag = CH_ERR + st;
     else if (why == END_EOB) r.flag = CH_EOB;
     else r.flag = q2_first ? CH_Q2 : CH_RUN;

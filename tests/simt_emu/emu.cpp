@@ -224,7 +224,9 @@ struct BsArgs {
     const uint16_t *kraft;
     const uint8_t *in;
     uint64_t in_size;
-    int mode;  // 0 search, 1 count, 2 decode
+    int mode;  // 0 search, 1 count, 2 decode, 3 expand tokens
+    uint32_t *tok;
+    uint32_t tok_cap, ntok, exp_bytes[32], exp_st[32];
     uint64_t lo, hi, start, stop;
     uint16_t *cells;
     uint32_t cell_cap;
@@ -237,7 +239,10 @@ static void bs_body(void *p)
     BsArgs *a = (BsArgs *)p;
     int l = simt::lane();
     if (a->mode == 0) a->found[l] = dbg::find_block_start(a->q, a->kraft, a->in, a->in_size, a->lo, a->hi);
+    else if (a->mode == 1 && a->tok)
+        a->res[l] = dbg::decode_block_chunk<dbg::SINK_TOKENS>(a->sm, a->in, a->in_size, a->start, a->stop, nullptr, 0, 0, a->tok, a->tok_cap);
     else if (a->mode == 1) a->res[l] = dbg::decode_block_chunk<dbg::SINK_COUNT>(a->sm, a->in, a->in_size, a->start, a->stop, nullptr, 0, 0);
+    else if (a->mode == 3) a->exp_st[l] = dbg::expand_tokens_warp(a->tok, a->ntok, a->cells, a->abs_base, &a->exp_bytes[l]);
     else a->res[l] = dbg::decode_block_chunk<dbg::SINK_U16>(a->sm, a->in, a->in_size, a->start, a->stop, a->cells, a->cell_cap, a->abs_base);
 }
 
@@ -245,7 +250,7 @@ static void bs_body(void *p)
 // region by region through the emulator. Returns the status; 0x4000 = the chain did not close (the
 // product would hand the stream back to the warp-per-stream kernel). *n_chunks = hinted regions used.
 extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
-                                       int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks)
+                                       int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks, uint32_t tok_per_byte)
 {
     size_t arena_sz = ((size_t)in_size + 64 + 32 + 15) & ~(size_t)15;
     uint8_t *arena = (uint8_t *)aligned_alloc(16, arena_sz);
@@ -260,9 +265,10 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
     *n_chunks = 0;
     const uint32_t nreg = (uint32_t)((in_size + region_bytes - 1) / region_bytes);
     uint64_t *cand = (uint64_t *)calloc(nreg, 8), *exitb = (uint64_t *)calloc(nreg, 8), *ooff = (uint64_t *)calloc(nreg, 8);
-    uint32_t *olen = (uint32_t *)calloc(nreg, 4), *flag = (uint32_t *)calloc(nreg, 4);
+    uint32_t *olen = (uint32_t *)calloc(nreg, 4), *flag = (uint32_t *)calloc(nreg, 4), *ntok = (uint32_t *)calloc(nreg, 4);
+    uint32_t *tokens = tok_per_byte ? (uint32_t *)malloc(((size_t)tok_per_byte * in_size + 16) * 4) : nullptr;
     BsArgs a;
-    a.sm = sm; a.q = &q; a.kraft = kraft; a.in = src; a.in_size = in_size; a.cells = nullptr;
+    a.sm = sm; a.q = &q; a.kraft = kraft; a.in = src; a.in_size = in_size; a.cells = nullptr; a.tok = nullptr; a.tok_cap = 0;
     uint32_t status = 0;
     for (uint32_t c = 0; c < nreg; c++) {
         cand[c] = 0;
@@ -276,8 +282,12 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
     for (uint32_t c = 0; c < nreg && !status; c++) {
         if (cand[c] == dbg::BS_NONE) continue;
         a.mode = 1; a.start = cand[c]; a.stop = next_hint(c);
+        if (tokens) {
+            a.tok = tokens + (size_t)tok_per_byte * (cand[c] >> 3);
+            a.tok_cap = (uint32_t)(tok_per_byte * ((a.stop == dbg::BS_NONE ? in_size : a.stop >> 3) - (cand[c] >> 3)));
+        }
         simt::run_warp(bs_body, &a, reverse);
-        exitb[c] = a.res[0].exit_bits; olen[c] = a.res[0].out_bytes; flag[c] = a.res[0].flag;
+        exitb[c] = a.res[0].exit_bits; olen[c] = a.res[0].out_bytes; flag[c] = a.res[0].flag; ntok[c] = a.res[0].ntok;
     }
     uint64_t pos = 0, expected = 0;
     bool ended = false, fail = false;
@@ -299,6 +309,16 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
             if (flag[c] == dbg::CH_IDLE) continue;
             a.mode = 2; a.start = cand[c]; a.stop = flag[c] == dbg::CH_RUN ? exitb[c] : dbg::BS_NONE;
             a.cells = cells + ooff[c]; a.cell_cap = olen[c]; a.abs_base = ooff[c];
+            uint64_t nh = next_hint(c);
+            uint32_t cap_c = tokens ? (uint32_t)(tok_per_byte * ((nh == dbg::BS_NONE ? in_size : nh >> 3) - (cand[c] >> 3))) : 0;
+            if (tokens && ntok[c] <= cap_c) {
+                a.mode = 3; a.tok = tokens + (size_t)tok_per_byte * (cand[c] >> 3); a.ntok = ntok[c];
+                simt::run_warp(bs_body, &a, reverse);
+                if (a.exp_st[0]) status = a.exp_st[0];
+                else if (a.exp_bytes[0] != olen[c]) status = 0x3000;
+                (*n_chunks) += 0x10000;  // high half: chunks expanded from tokens
+                continue;
+            }
             simt::run_warp(bs_body, &a, reverse);
             if (a.res[0].flag >= dbg::CH_ERR) status = a.res[0].flag - dbg::CH_ERR;
             else if (a.res[0].out_bytes != olen[c] || a.res[0].flag != flag[c]) status = 0x3000;
@@ -313,7 +333,7 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
         free(cells);
         if (!status) *final_size = pos;
     }
-    free(cand); free(exitb); free(ooff); free(olen); free(flag); free(sm); free(arena);
+    free(cand); free(exitb); free(ooff); free(olen); free(flag); free(ntok); free(tokens); free(sm); free(arena);
     return status;
 }
 

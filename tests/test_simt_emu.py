@@ -34,7 +34,7 @@ def emu():
     L.emu_split_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_uint32]
     L.emu_split_inflate.restype = C.c_uint32
     L.emu_bsplit_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int,
-                                     C.c_uint32, C.POINTER(C.c_uint32)]
+                                     C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
     L.emu_bsplit_inflate.restype = C.c_uint32
     L.emu_crc32.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
     L.emu_crc32.restype = C.c_uint32
@@ -147,16 +147,20 @@ def test_block_split_kernel_source(emu, ref):
         (corpus.raw_deflate(bytes(rng.integers(0, 256, 70000, dtype=np.uint8)), 6), 4096),  # stored blocks only: no hints
         (many_blocks(corpus.word_salad(60000, 6))[:-700], 2048),                             # truncated
     ]
-    used = 0
+    used = expanded = 0
     for k, (z, region) in enumerate(cases):
         want_good, want = ref.inflate(z, 400000)
-        ib = C.create_string_buffer(z, len(z))
-        ob = C.create_string_buffer(400000 + 64)
-        n, nch = C.c_uint64(0), C.c_uint32(0)
-        st = emu.emu_bsplit_inflate(ib, len(z), ob, 400000, C.byref(n), (5 * k) % 16, k & 1, region, C.byref(nch))
-        assert st != 0x4000 and st < 0x1000, (k, hex(st))
-        assert (st == 0) == bool(want_good), (k, st)
-        if want_good:
-            assert ob.raw[: n.value] == want, k
-        used += nch.value
-    assert used > 40  # the search really finds block boundaries
+        # tokens per compressed byte: 0 = both passes decode Huffman codes, 4 = the second pass expands the tokens
+        # the first one recorded, 1 = too few slots for most chunks (mixes both)
+        for tpb in (0, 4, 1):
+            ib = C.create_string_buffer(z, len(z))
+            ob = C.create_string_buffer(400000 + 64)
+            n, nch = C.c_uint64(0), C.c_uint32(0)
+            st = emu.emu_bsplit_inflate(ib, len(z), ob, 400000, C.byref(n), (5 * k) % 16, k & 1, region, C.byref(nch), tpb)
+            assert st != 0x4000 and st < 0x1000, (k, tpb, hex(st))
+            assert (st == 0) == bool(want_good), (k, tpb, st)
+            if want_good:
+                assert ob.raw[: n.value] == want, (k, tpb)
+            used += nch.value & 0xffff
+            expanded += nch.value >> 16
+    assert used > 120 and expanded > 60  # the search really finds block boundaries, and tokens really get expanded
