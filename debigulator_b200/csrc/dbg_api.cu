@@ -438,9 +438,12 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     uint32_t tpb = ctx->bsplit_tok_per_byte;
     while (tpb > 1 && (uint64_t)tpb * 4 * hs->split_in > ctx->bsplit_tok_max_bytes) tpb >>= 1;
     if (tpb && (uint64_t)tpb * 4 * hs->split_in <= ctx->bsplit_tok_max_bytes) {
-        CU(ctx->d_bs_tok[slot].reserve((size_t)tpb * 4 * hs->split_in + 256));
-        b.tok = (uint32_t *)ctx->d_bs_tok[slot].p;
-        b.tok_per_byte = tpb;
+        if (ctx->d_bs_tok[slot].reserve((size_t)tpb * 4 * hs->split_in + 256) == cudaSuccess) {
+            b.tok = (uint32_t *)ctx->d_bs_tok[slot].p;
+            b.tok_per_byte = tpb;
+        } else {
+            (void)cudaGetLastError();  // no room for tokens: the second pass decodes the Huffman codes again
+        }
     }
     const size_t smem = sizeof(dbg::InflateSmem) * dbg::BS_WARPS_PER_CTA;
     const uint32_t grid = std::min<uint32_t>((T + dbg::BS_WARPS_PER_CTA - 1) / dbg::BS_WARPS_PER_CTA,
