@@ -27,6 +27,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -344,6 +345,9 @@ def run_ours(args):
     bmp = None
     if args.bmp and rank == 0 and world == 1:
         bmp = bench_bmp(ctx, dev, torch, args.bmp)
+    cfg5 = None
+    if args.cfg5 and rank == 0 and world == 1:
+        cfg5 = bench_cfg5(ctx, dev, torch, args.cfg5)
 
     # ---- CPU baseline: the reference C on this box's host cores (rank 0, N=1 only)
     cpu = None
@@ -399,6 +403,8 @@ def run_ours(args):
             line["png"] = png
         if png_large:
             line["png_cfg4_shape"] = png_large
+        if cfg5:
+            line["cfg5_shape"] = cfg5
         if bmp:
             bmp["roofline"]["peak"] = peak
             bmp["roofline"]["frac"] = bmp["roofline"]["achieved"] / peak
@@ -459,6 +465,69 @@ def bench_png(ctx, dev, torch, n=PNG_N, w=PNG_W, h=PNG_H, n_unique=PNG_UNIQUE):
             "rgba_GBps": n * rgba / (ms / 1e3) / 1e9, "ms_per_step": ms,
             "config": {"workload": f"{shape}: {n} x {PNG_W_}x{PNG_H_} RGBA PNGs, {filt}one fixed-Huffman block each (stb stream shape)",
                        "unique_images": PNG_UNIQUE_, "png_bytes": tot_in}}
+
+
+def _gen_cfg5(i):
+    from debigulator_b200 import corpus
+    size = int(65536 * (256.0 ** (((i * 2654435761) % 1000) / 999.0)))  # log-uniform in [64 KiB, 16 MiB]
+    g, d = corpus.gz_member_cfg5(i, size)
+    return g, len(d)
+
+
+def bench_cfg5(ctx, dev, torch, n, n_unique=64):
+    """BASELINE config 5 shape, scaled to one GPU: gzip members of 64 KiB-16 MiB (log-uniform), eight
+    compressibility classes, device-resident. The long members take the block-split path."""
+    with mp.get_context("fork").Pool(min(n_unique, host_cores())) as pool:
+        uniq = pool.map(_gen_cfg5, range(n_unique))
+    offs, sizes, caps, total = [], [], [], 0
+    for i in range(n):
+        g, m = uniq[i % n_unique]
+        offs.append(total)
+        sizes.append(len(g))
+        caps.append((m + len(g) + 64 + 15) // 16 * 16)
+        total += (len(g) + 31) // 16 * 16
+    h = np.zeros(total + 64, np.uint8)
+    for i in range(n):
+        g = uniq[i % n_unique][0]
+        h[offs[i]:offs[i] + len(g)] = np.frombuffer(g, np.uint8)
+    out_off = np.concatenate([[0], np.cumsum(caps[:-1])]).astype(np.uint64)
+    i64 = lambda a: torch.from_numpy(np.asarray(a, np.uint64).view(np.int64)).to(dev)
+    d_in = torch.from_numpy(h).to(dev)
+    d_out = torch.zeros(int(sum(caps)), dtype=torch.uint8, device=dev)
+    d_size = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    a_off, a_sz, o_off, o_cap = i64(offs), i64(sizes), i64(out_off), i64(caps)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ctx.inflate_device(d_in, a_off, a_sz, d_out, o_off, o_cap, d_size, d_st, None, stream=stream, gz=True)
+
+    before = ctx.bsplit_stats()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum().item()) == 0, "cfg5 decode failures"
+    got = d_size.cpu().numpy()
+    # spot check of the longest text member against zlib
+    k = max(range(min(n, n_unique)), key=lambda i: sizes[i] if i % 8 in (1, 2) else 0)
+    want = zlib.decompress(uniq[k][0], 31)[: int(got[k])]
+    assert d_out[int(out_off[k]):int(out_off[k]) + int(got[k])].cpu().numpy().tobytes() == want, "cfg5 payload mismatch"
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 3
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    after = ctx.bsplit_stats()
+    out_bytes = int(got.sum())
+    return {"metric": "inflate_output_GBps", "value": out_bytes / ms / 1e6, "unit": "GB/s", "ms_per_step": ms,
+            "config": {"workload": f"cfg5 shape: {n} gzip members, 64 KiB-16 MiB log-uniform, 8 compressibility classes "
+                                   "(stored / text / Huffman-only / period ~32 kB / runs / zeros)",
+                       "unique_members": n_unique, "output_bytes": out_bytes, "compressed_bytes": int(sum(sizes)),
+                       "members_with_spec_size": int(sum(int(got[i]) == uniq[i % n_unique][1] for i in range(n)))},
+            "block_split_streams_per_step": (after[0] - before[0]) // (steps + 2), "block_split_fallbacks": after[1] - before[1]}
 
 
 def bench_bmp(ctx, dev, torch, n, w=2048, h=2048):
@@ -536,6 +605,7 @@ def main():
     ap.add_argument("--png-only", action="store_true")
     ap.add_argument("--png-images", type=int, default=PNG_N)
     ap.add_argument("--png-large", type=int, default=4, help="number of 8192x8192 images in the config-4-shape line (0 = skip)")
+    ap.add_argument("--cfg5", type=int, default=2048, help="members of the config-5-shape line (0 = skip)")
     ap.add_argument("--bmp", type=int, default=64, help="number of 2048x2048 BMP files in the BMP line (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
