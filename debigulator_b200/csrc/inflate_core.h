@@ -657,29 +657,43 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
         // one pass yields at most 64 symbols of at most 258 bytes: with that much room left the
         // per-symbol capacity checks are dropped
         const bool roomy = SINK == SINK_COUNT || SINK == SINK_TOKENS || k.cap - k.pos >= 64 * 258;
+        // The walk is unrolled four symbols deep: ptxas makes the warp wait for the deferred match load at the
+        // first branch after a loop back-edge (not at the store that needs the bytes), so a one-symbol loop would
+        // expose that load's latency on every symbol; inside the unrolled body the wait sits on the consumer.
+#define DBG_SYM(CHECK)                                                                         \
+            cur = p;                                                                           \
+            {                                                                                  \
+                const uint32_t info = cand[p];                                                 \
+                const uint32_t lf = (info >> 7) & 511;                                         \
+                p = info & 127;                                                                \
+                if (lf == 0) {                                                                 \
+                    err = emit_literal<SINK, CHECK>(k, info >> 16);                            \
+                    if (CHECK && err) break;                                                   \
+                } else if (lf >= 3) {                                                          \
+                    err = emit_match<SINK, CHECK>(k, lf, (info >> 16) + 1);                    \
+                    if (err) break;                                                            \
+                } else {                                                                       \
+                    const uint32_t code = info >> 16;                                          \
+                    if (code == CAND_EOB) eob = true;                                          \
+                    else if (code == CAND_ERR) err = ST_BAD_SYMBOL;                            \
+                    else slow = true; /* a code longer than the primary LUT index starts at cur */ \
+                    break;                                                                     \
+                }                                                                              \
+            }
 #define DBG_WALK(CHECK)                                                                        \
         do {                                                                                   \
-            cur = p;                                                                           \
-            const uint32_t info = cand[p];                                                     \
-            const uint32_t lf = (info >> 7) & 511;                                             \
-            p = info & 127;                                                                    \
-            if (lf == 0) {                                                                     \
-                err = emit_literal<SINK, CHECK>(k, info >> 16);                                \
-                if (CHECK && err) break;                                                       \
-            } else if (lf >= 3) {                                                              \
-                err = emit_match<SINK, CHECK>(k, lf, (info >> 16) + 1);                        \
-                if (err) break;                                                                \
-            } else {                                                                           \
-                const uint32_t code = info >> 16;                                              \
-                if (code == CAND_EOB) eob = true;                                              \
-                else if (code == CAND_ERR) err = ST_BAD_SYMBOL;                                \
-                else slow = true; /* a code longer than the primary LUT index starts at cur */ \
-                break;                                                                         \
-            }                                                                                  \
+            DBG_SYM(CHECK)                                                                     \
+            if (p >= lim) break;                                                               \
+            DBG_SYM(CHECK)                                                                     \
+            if (p >= lim) break;                                                               \
+            DBG_SYM(CHECK)                                                                     \
+            if (p >= lim) break;                                                               \
+            DBG_SYM(CHECK)                                                                     \
         } while (p < lim)
         if (roomy) DBG_WALK(false);
         else DBG_WALK(true);
 #undef DBG_WALK
+#undef DBG_SYM
         if (err) return err;
         if (slow) {
             // rare: decode this one symbol serially (uniform), then rebuild the window candidates
