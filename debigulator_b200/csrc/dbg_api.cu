@@ -731,21 +731,53 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
         CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
         CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
         CU(cudaEventRecord(ctx->wave_ready, s));
+        const bool trace = getenv("DBG_WAVE_TRACE") != nullptr;  // debugging aid: per-wave timeline on stderr
+        std::vector<cudaEvent_t> tev;
+        if (trace) {
+            tev.resize(3 * nw + 1);
+            for (auto &e : tev) cudaEventCreate(&e);
+            cudaEventRecord(tev[3 * nw], s);
+        }
+        // Issued breadth-first (all uploads, then all kernels, then all downloads): the streams share a limited
+        // number of hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and with wave-by-wave issue the
+        // upload of wave k+8 sits behind the download of wave k, i.e. behind wave k's kernels (measured with
+        // DBG_WAVE_TRACE: the second half of the waves did not start before the first half had finished).
+        for (int k = 0; k < nw; k++) {
+            cudaStream_t ws = ctx->wave_stream[k];
+            uint64_t b = cut[k], e = cut[k + 1];
+            uint64_t i0 = in_off[b], i1 = in_off[e - 1] + in_size[e - 1];
+            CU(cudaStreamWaitEvent(ws, ctx->wave_ready, 0));
+            CU(cudaMemcpyAsync((uint8_t *)ctx->d_in.p + i0, h_in + i0, i1 - i0, cudaMemcpyHostToDevice, ws));
+            if (trace) cudaEventRecord(tev[3 * k], ws);
+        }
         for (int k = 0; k < nw; k++) {
             cudaStream_t ws = ctx->wave_stream[k];
             uint64_t b = cut[k], e = cut[k + 1], m = e - b;
-            uint64_t i0 = in_off[b], i1 = in_off[e - 1] + in_size[e - 1];
-            uint64_t o0 = out_off[b], o1 = out_off[e - 1] + out_cap[e - 1];
-            CU(cudaStreamWaitEvent(ws, ctx->wave_ready, 0));
-            CU(cudaMemcpyAsync((uint8_t *)ctx->d_in.p + i0, h_in + i0, i1 - i0, cudaMemcpyHostToDevice, ws));
             int rc = inflate_device_slot(ctx, k, m, (const uint8_t *)ctx->d_in.p, dd + b, dd + n + b, (uint8_t *)ctx->d_out.p,
                                          dd + 2 * n + b, dd + 3 * n + b, dd + 4 * n + b, d_status + b, d_order + b, ws,
                                          gz_off ? gz_off + b : nullptr, gz_off ? gz_size + b : nullptr,
                                          gz_off ? gz_pre + b : nullptr);
             if (rc) return rc;
+            if (trace) cudaEventRecord(tev[3 * k + 1], ws);
+        }
+        for (int k = 0; k < nw; k++) {
+            cudaStream_t ws = ctx->wave_stream[k];
+            uint64_t b = cut[k], e = cut[k + 1];
+            uint64_t o0 = out_off[b], o1 = out_off[e - 1] + out_cap[e - 1];
             CU(cudaMemcpyAsync(h_out + o0, (uint8_t *)ctx->d_out.p + o0, o1 - o0, cudaMemcpyDeviceToHost, ws));
+            if (trace) cudaEventRecord(tev[3 * k + 2], ws);
         }
         for (int k = 0; k < nw; k++) CU(cudaStreamSynchronize(ctx->wave_stream[k]));
+        if (trace) {
+            for (int k = 0; k < nw; k++) {
+                float a = 0, b2 = 0, c = 0;
+                cudaEventElapsedTime(&a, tev[3 * nw], tev[3 * k]);
+                cudaEventElapsedTime(&b2, tev[3 * nw], tev[3 * k + 1]);
+                cudaEventElapsedTime(&c, tev[3 * nw], tev[3 * k + 2]);
+                fprintf(stderr, "wave %2d: h2d done %7.2f ms, kernels done %7.2f ms, d2h done %7.2f ms\n", k, a, b2, c);
+            }
+            for (auto &e : tev) cudaEventDestroy(e);
+        }
     }
     ctx->bsplit_allowed = true;
     CU(cudaMemcpyAsync(hd + 4 * n, dd + 4 * n, n * 8 + n * 4, cudaMemcpyDeviceToHost, s));
