@@ -110,8 +110,11 @@ int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h
  * the next 16-byte boundary after its end must be readable (pad the arena by
  * 16). Output item i is written at d_out + out_off[i], at most out_cap[i]
  * bytes. d_order (may be NULL) is a permutation giving the scheduling order
- * (largest first balances best). Work is enqueued on `stream` (a cudaStream_t,
- * NULL = the context's own stream) and NOT synchronised. */
+ * (heaviest first balances best; with NULL the library sorts the queue itself).
+ * Work is enqueued on `stream` (a cudaStream_t, NULL = the context's own
+ * stream) and the call returns with it still running. It may wait for `stream`
+ * on the way: the chunk-parallel paths for long streams
+ * read a few counters back before they size their scratch memory. */
 int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                              const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
                              const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
