@@ -18,7 +18,7 @@ ctx = dbg.Context(0)
 s = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(s)
 i64 = lambda a: torch.from_numpy(np.asarray(a, np.uint64).view(np.int64)).to(dev)
-for k in range(8):
+for k in [int(c) for c in os.environ.get("CLASSES", "0,1,2,3,4,5,6,7").split(",")]:
     g, d = corpus.gz_member_cfg5(k, MB << 20)
     h = np.zeros(len(g) + 64, np.uint8)
     h[: len(g)] = np.frombuffer(g, np.uint8)
