@@ -22,6 +22,8 @@ struct BsSummary {         // device -> host after classify, and again after cha
     uint32_t pad;
     uint64_t split_in;     // compressed bytes of the streams taking this path
     uint64_t tok_bytes;    // allocation cursor of the token areas, in compressed bytes (bs_assign_kernel)
+    uint32_t n_pruned;     // streams taken off this path again because their hints were too sparse (bs_prune_kernel)
+    uint32_t pad2;
 };
 
 struct BsBatch {
@@ -146,6 +148,31 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_search_kernel(BsBatc
     }
 }
 
+// Hints too sparse? When the largest stretch between two consecutive chunk starts exceeds a third of the
+// stream, the two passes of this path take longer than the single pass of one warp (a stream of long stored or
+// fixed-Huffman stretches has no dynamic-block headers to find there). Such a stream is handed back before the
+// count pass: it joins the streams of the second warp-per-stream pass. One thread per stream.
+__global__ void bs_prune_kernel(BsBatch b)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n || !b.flag[s]) return;
+    const uint32_t nch = b.nchunks[s], base = b.chunk_base[s];
+    const uint64_t bits = 8 * b.in_size[s];
+    uint64_t prev = 0, worst = 0;
+    for (uint32_t c = 1; c < nch; c++) {
+        const uint64_t cand = b.cand[base + c];
+        if (cand == BS_NONE) continue;
+        if (cand - prev > worst) worst = cand - prev;
+        prev = cand;
+    }
+    if (bits - prev > worst) worst = bits - prev;
+    if (worst > bits / 3) {
+        for (uint32_t c = 0; c < nch; c++) b.cand[base + c] = BS_NONE;
+        b.redo[s] = 1;  // flag[s] stays set: the first warp-per-stream pass is already running beside us
+        atomicAdd(&b.summary->n_pruned, 1u);
+    }
+}
+
 __device__ __forceinline__ uint64_t bs_next_hint(const BsBatch &b, uint32_t s, uint32_t t)
 {
     const uint32_t end = b.chunk_base[s] + b.nchunks[s];
@@ -186,7 +213,7 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_count_kernel(BsBatch
 __global__ void bs_chain_kernel(BsBatch b)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.n || !b.flag[s]) return;
+    if (s >= b.n || !b.flag[s] || b.redo[s]) return;
     const uint32_t nch = b.nchunks[s], base = b.chunk_base[s];
     const uint64_t cap = b.out_cap[s];
     uint64_t pos = 0, expected = 0;

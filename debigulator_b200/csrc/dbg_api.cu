@@ -452,13 +452,15 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     ctx->launches++;
     dbg::bs_fill_kernel<<<n, 128, 0, s>>>(b);
     dbg::bs_search_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, 0, s>>>(b);
+    dbg::bs_prune_kernel<<<sb, 128, 0, s>>>(b);
+    ctx->launches += 2;
     dbg::bs_count_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b);
     dbg::bs_chain_kernel<<<sb, 128, 0, s>>>(b);
-    ctx->launches += 4;
+    ctx->launches += 3;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::BsSummary), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    ctx->bs_streams += hs->n_split - hs->n_fallback;
+    ctx->bs_streams += hs->n_split - hs->n_pruned - hs->n_fallback;
     ctx->bs_fallbacks += hs->n_fallback;
     if (hs->cells_used) {
         CU(bc.reserve((size_t)hs->cells_used * 2 + 256));
@@ -475,8 +477,8 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
         ctx->launches += 3;
         CU(cudaGetLastError());
     }
-    if (hs->n_fallback) {
-        // second warp-per-stream pass for the streams whose hinted boundaries did not chain
+    if (hs->n_fallback || hs->n_pruned) {
+        // second warp-per-stream pass for the streams whose hinted boundaries did not chain or were too sparse
         dbg::InflateBatch again = a;
         again.skip = nullptr;
         again.skip2 = nullptr;

@@ -813,11 +813,18 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
             if (len) {
                 const uint64_t bytepos = w.abs_bits() >> 3;
                 if (bytepos + len > g.end_byte) return ST_TRUNCATED;
-                if (SINK == SINK_TOKENS) {  // stored bytes become literal tokens
-                    const uint8_t *src = w.base + bytepos;
-                    for (uint32_t i = (uint32_t)simt::lane(); i < len; i += 32)
-                        if (k.ntok + i < k.tok_cap) k.tok[k.ntok + i] = src[i];
-                    k.ntok += len;
+                if (SINK == SINK_TOKENS) {
+                    if (len > 256) {
+                        // a sizeable stored block: one token per byte would make the expansion slower than decoding
+                        // the chunk again (where stored bytes are a lane-parallel copy), so give up on tokens here
+                        k.tok_cap = 0;
+                        k.ntok = 0x40000000u;
+                    } else {  // stored bytes become literal tokens
+                        const uint8_t *src = w.base + bytepos;
+                        for (uint32_t i = (uint32_t)simt::lane(); i < len; i += 32)
+                            if (k.ntok + i < k.tok_cap) k.tok[k.ntok + i] = src[i];
+                        k.ntok += len;
+                    }
                 } else if (SINK != SINK_COUNT) {
                     if ((uint64_t)k.pos + len > k.cap) return ST_OUT_OVERFLOW;
                     if (SINK == SINK_BYTES) {

@@ -19,7 +19,11 @@ s = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(s)
 i64 = lambda a: torch.from_numpy(np.asarray(a, np.uint64).view(np.int64)).to(dev)
 for k in [int(c) for c in os.environ.get("CLASSES", "0,1,2,3,4,5,6,7").split(",")]:
-    g, d = corpus.gz_member_cfg5(k, MB << 20)
+    if k == 8:  # not a config-5 class: stored + fixed + dynamic segments in one stream (config 2's "mixed")
+        d = corpus.word_salad(MB << 20, 99)
+        g = corpus.gzip_frame(corpus.mixed_deflate(d, 99), d)
+    else:
+        g, d = corpus.gz_member_cfg5(k, MB << 20)
     h = np.zeros(len(g) + 64, np.uint8)
     h[: len(g)] = np.frombuffer(g, np.uint8)
     cap = len(d) + len(g) + 64
