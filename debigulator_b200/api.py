@@ -55,6 +55,8 @@ def load_library():
     L.dbg_profile_read.restype = i32
     L.dbg_bsplit_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.dbg_bsplit_stats.restype = i32
+    L.dbg_fx_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.dbg_fx_stats.restype = i32
     L.dbg_synchronize.argtypes = [vp]
     L.dbg_synchronize.restype = i32
     for name in ("dbg_inflate_batch", "dbg_decode_gz_batch"):
@@ -164,6 +166,12 @@ class Context:
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._check(self.L.dbg_bsplit_stats(self.h, C.byref(a), C.byref(b)), "dbg_bsplit_stats")
         return int(a.value), int(b.value)
+
+    def fx_stats(self):
+        """(streams decoded by the lane-serial fixed-block path, streams handed back, extra decode runs)."""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.L.dbg_fx_stats(self.h, C.byref(a), C.byref(b), C.byref(c)), "dbg_fx_stats")
+        return int(a.value), int(b.value), int(c.value)
 
     def synchronize(self):
         self._check(self.L.dbg_synchronize(self.h), "dbg_synchronize")

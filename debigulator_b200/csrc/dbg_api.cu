@@ -17,6 +17,7 @@
 #include "../../include/debigulator_b200.h"
 #include "bmp_kernels.cuh"
 #include "bsplit_kernels.cuh"
+#include "fx_kernels.cuh"
 #include "kernels.cuh"
 #include "png_kernels.cuh"
 #include "split_kernels.cuh"
@@ -88,7 +89,11 @@ struct dbg_ctx {
     uint32_t bsplit_factor_q = 8;
     uint32_t bsplit_region = dbg::REGION_BYTES, bsplit_region_min = 16384;
     uint64_t bs_streams = 0, bs_fallbacks = 0;  // counters: streams that took the block-split path / were handed back
-    uint32_t split_max_streams = 1536;  // batches with fewer streams may use the split-stream path (measured crossover ~1,500 images of 1024^2)
+    uint32_t split_max_streams = 1536;  // packed host API: smaller batches run as one wave (so that the per-context paths may take them)
+    bool fx = true;                     // lane-serial path for single fixed-Huffman-block streams (fx_kernels.cuh)
+    uint32_t fx_group_forced = 0;       // DBG_FX_GROUP: fixed group size (experiments)
+    uint64_t fx_streams = 0, fx_redo = 0, fx_extra = 0;  // counters: streams on that path / handed back / extra survivors
+    Buf d_fx_tok;                       // its tokens
     bool verify = false;                // opt-in: check gzip CRC32 / ISIZE trailers
     uint32_t inflate_ctas_per_sm = dbg::INFLATE_CTAS_PER_SM;  // resident streams per SM = 4x this (tunable: L2 footprint)
     // host-API staging
@@ -173,12 +178,10 @@ extern "C" dbg_ctx *dbg_create(int device)
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
     dbg::png_configure_kernels();
-    cudaFuncSetAttribute(dbg::split_transfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA));
-    cudaFuncSetAttribute(dbg::split_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA));
     if (const char *e = getenv("DBG_SPLIT_MAX_STREAMS")) ctx->split_max_streams = (uint32_t)atoi(e);
-    if (const char *e = getenv("DBG_SPLIT_CHUNK")) ctx->split_chunk_forced = (uint32_t)std::min(1 << 20, std::max(4096, atoi(e))) & ~15u;
+    if (const char *e = getenv("DBG_SPLIT_CHUNK")) ctx->split_chunk_forced = (uint32_t)std::min(1 << 20, std::max((int)dbg::FX_MIN_CHUNK, atoi(e))) & ~15u;
+    if (const char *e = getenv("DBG_FX_GROUP")) ctx->fx_group_forced = (uint32_t)std::min(1 << 22, std::max(4096, atoi(e))) & ~15u;
+    if (const char *e = getenv("DBG_FX")) ctx->fx = atoi(e) != 0;
     if (const char *e = getenv("DBG_WAVES")) ctx->waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(e)));
     if (const char *e = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(e) != 0;
     if (const char *e = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(e));
@@ -200,7 +203,7 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     Buf *all[] = {&ctx->d_counter, &ctx->d_meta, &ctx->d_png_scratch, &ctx->d_in,    &ctx->d_out,    &ctx->d_desc,
                   &ctx->h_in,      &ctx->h_out,  &ctx->h_desc,        &ctx->d_split, &ctx->d_cells, &ctx->h_summary,
-                  &ctx->d_split_chunks};
+                  &ctx->d_split_chunks, &ctx->d_fx_tok};
     for (Buf *b : all) b->release();
     for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) {
         ctx->d_sched[i].release();
@@ -224,6 +227,15 @@ extern "C" int dbg_bsplit_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t 
     if (!ctx) return DBG_ERR_NO_DEVICE;
     if (streams) *streams = ctx->bs_streams;
     if (fallbacks) *fallbacks = ctx->bs_fallbacks;
+    return DBG_OK;
+}
+
+extern "C" int dbg_fx_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *handed_back, uint64_t *extra_runs)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (streams) *streams = ctx->fx_streams;
+    if (handed_back) *handed_back = ctx->fx_redo;
+    if (extra_runs) *extra_runs = ctx->fx_extra;
     return DBG_OK;
 }
 
@@ -302,70 +314,121 @@ static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_c
     return DBG_OK;
 }
 
-// Split-stream path for batches that cannot fill the GPU with one warp per stream: streams that are a
-// single fixed-Huffman block (every stb-written PNG) are cut into 32 KiB chunks decoded by one warp each.
-// Needs one small device->host read (how many streams / bytes / cells) and therefore synchronises `s` once.
-static int run_split(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t **skip_out)
+// Lane-serial path for streams that are a single fixed-Huffman block (every stb-written PNG): fx_core.h /
+// fx_kernels.cuh. Two small device->host reads (how many streams / bytes; exact token and cell counts), so `s`
+// is synchronised twice. *skip_out = per-stream flags of the streams handled here, *redo_out = those handed
+// back (flag set as well) for a second warp-per-stream pass; *n_redo tells whether there are any.
+static int run_fx(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t **skip_out, const uint32_t **redo_out,
+                  uint32_t *n_redo)
 {
     *skip_out = nullptr;
+    *redo_out = nullptr;
+    *n_redo = 0;
     const uint32_t n = a.n;
-    CU(ctx->h_summary.reserve(sizeof(dbg::SplitSummary)));
-    CU(ctx->d_split.reserve(256 + (size_t)n * (8 + 4 + 4 + 4) + 256));
+    CU(ctx->h_summary.reserve(sizeof(dbg::FxSummary)));
+    CU(ctx->d_split.reserve(256 + (size_t)n * (2 * 8 + 6 * 4) + 256));
     uint8_t *p = (uint8_t *)ctx->d_split.p;
-    dbg::SplitBatch b{};
+    dbg::FxBatch b{};
     b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
     b.out_base = a.out_base; b.out_off = a.out_off; b.out_cap = a.out_cap;
     b.out_size = a.out_size; b.status = a.status; b.pre_status = a.pre_status; b.n = n;
-    b.summary = (dbg::SplitSummary *)p;
+    b.summary = (dbg::FxSummary *)p;
     b.cell_base = (uint64_t *)(p + 256);
-    b.split_flag = (uint32_t *)(b.cell_base + n);
-    b.chunk_base = b.split_flag + n;
+    b.tok_base = b.cell_base + n;
+    b.flag = (uint32_t *)(b.tok_base + n);
+    b.redo = b.flag + n;
+    b.chunk_base = b.redo + n;
     b.nchunks = b.chunk_base + n;
+    b.group_base = b.nchunks + n;
+    b.ngroups = b.group_base + n;
     const unsigned sb = (n + 127) / 128;
-    CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::SplitSummary), s));
-    dbg::split_classify_kernel<<<sb, 128, 0, s>>>(b);
+    CU(cudaMemsetAsync(b.summary, 0, sizeof(dbg::FxSummary), s));
+    dbg::fx_classify_kernel<<<sb, 128, 0, s>>>(b);
     ctx->launches++;
     CU(cudaGetLastError());
-    dbg::SplitSummary *hs = (dbg::SplitSummary *)ctx->h_summary.p;
-    CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::SplitSummary), cudaMemcpyDeviceToHost, s));
+    dbg::FxSummary *hs = (dbg::FxSummary *)ctx->h_summary.p;
+    CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::FxSummary), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    if (hs->n_split == 0) return DBG_OK;
-    // chunk size: 32 KiB, doubled (up to 512 KiB) while the longest stream would otherwise have more than 512
-    // chunks and the batch still has a chunk for every second resident warp. The last 32 KiB of every chunk's
-    // output is resolved by a per-stream serial chain (the tails, ~10 us per chunk), which for 150 MB streams
-    // is the longest kernel of the step at 32 KiB (measured, four 8192^2 images: 149 ms per step at 32 KiB,
-    // 121 at 64, 116 at 128, 110 at 256); short streams keep small chunks (more parallelism per stream).
-    const uint64_t resident = (uint64_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM * dbg::SPLIT_WARPS_PER_CTA;
-    uint32_t chunk = dbg::CHUNK_BYTES;
-    while (chunk < 16 * dbg::CHUNK_BYTES && hs->max_in / chunk > 512 && hs->split_in / (2 * chunk) >= resident / 2) chunk <<= 1;
+    if (hs->n_fx == 0) return DBG_OK;
+    // chunk = what one lane decodes: 16 KiB, halved (down to 2 KiB) while the batch has fewer chunks than the
+    // GPU has lanes to give; group = what one warp expands and the unit of the marker / resolve scheme:
+    // 256 KiB of compressed data, smaller for small batches (more warps), larger for very long streams (the
+    // last 32 KiB of every group's output is resolved by a per-stream serial chain).
+    const uint64_t lanes_wanted = (uint64_t)ctx->sm_count * 2048;
+    uint32_t chunk = 16384;
+    while (chunk > dbg::FX_MIN_CHUNK && hs->fx_in / chunk < lanes_wanted) chunk >>= 1;
     if (ctx->split_chunk_forced) chunk = ctx->split_chunk_forced;
+    uint32_t group = 262144;
+    const uint64_t warps_wanted = (uint64_t)ctx->sm_count * 32;
+    while (group > 32768 && hs->fx_in / group < warps_wanted) group >>= 1;
+    while (group < (1u << 20) && hs->max_in / group > 384 && hs->fx_in / (2 * group) >= warps_wanted) group <<= 1;
+    if (ctx->fx_group_forced) group = ctx->fx_group_forced;
+    if (group < chunk) group = chunk;
     b.chunk_bytes = chunk;
-    const uint32_t T = (uint32_t)(hs->split_in / chunk) + hs->n_split;  // upper bound of the chunk count
-    const size_t per_chunk = (size_t)T * (4 + 8 + 8 + 4 + 4 + 32 * sizeof(dbg::TransferEntry)) + 1024;
+    b.group_chunks = group / chunk;
+    const uint32_t T = (uint32_t)(hs->fx_in / chunk) + hs->n_fx;               // upper bounds
+    const uint32_t NG = (uint32_t)(hs->fx_in / ((uint64_t)chunk * b.group_chunks)) + hs->n_fx;
+    b.extra_cap = T / 8 + 1024;
+    const size_t per_chunk = (size_t)T * (3 * 32 * 4 + 5 * 4) + (size_t)b.extra_cap * 4 + ((size_t)T + b.extra_cap) * sizeof(dbg::FxRec) +
+                             (size_t)NG * (2 * 8 + 4 * 4) + 1024;
     CU(ctx->d_split_chunks.reserve(per_chunk));
     uint8_t *q = (uint8_t *)ctx->d_split_chunks.p;
-    b.entry_bits = (uint64_t *)q;
-    b.c_out_off = b.entry_bits + T;
-    b.tf = (dbg::TransferEntry *)(b.c_out_off + T);
-    b.chunk_stream = (uint32_t *)(b.tf + (size_t)T * 32);
-    b.c_out_len = b.chunk_stream + T;
-    b.c_flag = b.c_out_len + T;
-    CU(cudaMemsetAsync(b.chunk_stream, 0, (size_t)T * 12, s));  // chunk_stream, c_out_len, c_flag of unused slots
-    CU(ctx->d_cells.reserve((size_t)hs->cells_cap * 2 + 256));
-    b.cells = (uint16_t *)ctx->d_cells.p;
-    size_t smem = sizeof(dbg::InflateSmem) * dbg::SPLIT_WARPS_PER_CTA;
-    uint32_t grid = std::min<uint32_t>((T + dbg::SPLIT_WARPS_PER_CTA - 1) / dbg::SPLIT_WARPS_PER_CTA,
-                                       (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);
-    dbg::split_assign_kernel<<<sb, 128, 0, s>>>(b);
-    dbg::split_fill_kernel<<<n, 128, 0, s>>>(b);
-    dbg::split_transfer_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b);
-    dbg::split_chain_kernel<<<sb, 128, 0, s>>>(b);
-    dbg::split_decode_kernel<<<grid, dbg::SPLIT_WARPS_PER_CTA * 32, smem, s>>>(b);
-    dbg::split_resolve_tails_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(b);
-    dbg::split_resolve_body_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(b, T);
-    ctx->launches += 7;
+    b.rec = (dbg::FxRec *)q;
+    b.g_out_off = (uint64_t *)(b.rec + T + b.extra_cap);
+    b.g_tok_off = b.g_out_off + NG;
+    b.hyp = (uint32_t *)(b.g_tok_off + NG);
+    b.surv_start = b.hyp + (size_t)T * 32;
+    b.extra_slot = b.surv_start + (size_t)T * 32;
+    b.chunk_stream = b.extra_slot + (size_t)T * 32;
+    b.nsurv = b.chunk_stream + T;
+    b.c_surv = b.nsurv + T;
+    b.c_out_off = b.c_surv + T;
+    b.c_tok_off = b.c_out_off + T;
+    b.extra_item = b.c_tok_off + T;
+    b.group_stream = b.extra_item + b.extra_cap;
+    b.g_out_len = b.group_stream + NG;
+    b.g_flag = b.g_out_len + NG;
+    b.g_ntok = b.g_flag + NG;
+    CU(cudaMemsetAsync(b.chunk_stream, 0, (size_t)T * 2 * 4, s));                    // chunk_stream, nsurv of unused slots
+    CU(cudaMemsetAsync(b.c_surv, 0xff, (size_t)T * 4, s));                           // FX_NONE
+    CU(cudaMemsetAsync(b.group_stream, 0, (size_t)NG * 4 * 4, s));                   // group_stream, g_out_len, g_flag, g_ntok of unused slots
+    const uint32_t warp_grid = std::min<uint32_t>((T + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 12);
+    const uint32_t lane_grid = std::min<uint32_t>((T + dbg::FX_LANE_THREADS - 1) / dbg::FX_LANE_THREADS, (uint32_t)ctx->sm_count * 12);
+    dbg::fx_assign_kernel<<<sb, 128, 0, s>>>(b);
+    dbg::fx_fill_kernel<<<n, 128, 0, s>>>(b);
+    dbg::fx_head_kernel<<<warp_grid, dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
+    dbg::fx_sizes_kernel<<<lane_grid, dbg::FX_LANE_THREADS, 0, s>>>(b);
+    dbg::fx_chain_kernel<<<std::min<uint32_t>((n + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 8),
+                           dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
+    ctx->launches += 5;
     CU(cudaGetLastError());
-    *skip_out = b.split_flag;
+    CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::FxSummary), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (hs->cells_used) {
+        CU(ctx->d_cells.reserve((size_t)hs->cells_used * 2 + 256));
+        CU(ctx->d_fx_tok.reserve((size_t)hs->tok_used * 4 + 256));
+        b.cells = (uint16_t *)ctx->d_cells.p;
+        b.tok = (uint32_t *)ctx->d_fx_tok.p;
+        dbg::fx_tokens_kernel<<<lane_grid, dbg::FX_LANE_THREADS, 0, s>>>(b);
+        dbg::fx_expand_kernel<<<std::min<uint32_t>((NG + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 12),
+                                dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
+        // cells -> bytes: the resolve kernels see the groups as their chunks
+        dbg::SplitBatch r{};
+        r.out_base = a.out_base; r.out_off = a.out_off; r.out_size = a.out_size; r.status = a.status; r.n = n;
+        r.split_flag = b.flag; r.redo = b.redo; r.chunk_base = b.group_base; r.nchunks = b.ngroups; r.cell_base = b.cell_base;
+        r.chunk_stream = b.group_stream; r.c_out_off = b.g_out_off; r.c_out_len = b.g_out_len; r.c_flag = b.g_flag;
+        r.cells = b.cells;
+        dbg::split_resolve_tails_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(r);
+        dbg::split_resolve_body_kernel<<<std::min<uint32_t>(NG, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(r, NG);
+        ctx->launches += 4;
+        CU(cudaGetLastError());
+    }
+    *skip_out = b.flag;
+    *redo_out = b.redo;
+    *n_redo = hs->n_redo;
+    ctx->fx_streams += hs->n_fx - hs->n_redo;
+    ctx->fx_redo += hs->n_redo;
+    ctx->fx_extra += hs->n_extra;
     return DBG_OK;
 }
 
@@ -495,11 +558,23 @@ static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter
 {
     a.skip = nullptr;
     a.skip2 = nullptr;
-    if (a.n < ctx->split_max_streams && slot == 0) {
+    const uint32_t *fx_redo = nullptr;
+    uint32_t n_redo = 0;
+    if (ctx->fx && slot == 0 && ctx->bsplit_allowed) {  // (the scratch of this path is per context: single-wave calls only)
         const uint32_t *skip = nullptr;
-        int rc = run_split(ctx, a, s, &skip);
+        int rc = run_fx(ctx, a, s, &skip, &fx_redo, &n_redo);
         if (rc) return rc;
         a.skip = skip;
+    }
+    if (n_redo) {
+        // streams the lane-serial path handed back: a warp-per-stream pass of their own (a.skip keeps them out of
+        // everything below)
+        dbg::InflateBatch again = a;
+        again.skip = nullptr;
+        again.only = fx_redo;
+        again.order = nullptr;
+        int rc = launch_inflate_plain(ctx, again, d_counter + 2, s, slot, false);
+        if (rc) return rc;
     }
     if (ctx->bsplit && ctx->bsplit_allowed) {
         bool done = false;

@@ -148,6 +148,11 @@ int dbg_set_verify(dbg_ctx *ctx, int on);
  * hinted block boundary turned out not to be one. Diagnostics only; either pointer may be NULL. */
 int dbg_bsplit_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *fallbacks);
 
+/* The same for the lane-serial path that decodes single fixed-Huffman-block streams (what stb_image_write emits
+ * for every PNG): streams decoded there, streams handed back to the warp-per-stream kernel, and
+ * chunk entry points that needed more than one decode run (strictly periodic symbol streams). Diagnostics only. */
+int dbg_fx_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *handed_back, uint64_t *extra_runs);
+
 /* Optional timing of the dominant kernel (inflate): after dbg_profile_enable(ctx, 1)
  * every inflate launch is bracketed by CUDA events on its own stream;
  * dbg_profile_read() waits for them, returns the summed device time and the

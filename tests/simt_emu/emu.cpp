@@ -130,93 +130,122 @@ extern "C" uint32_t emu_inflate(const uint8_t *in, uint64_t in_size, uint8_t *ou
     return st;
 }
 
-// ----------------------------------------------------------- split stream ----
-struct ChunkArgs {
-    dbg::InflateSmem *sm;
+// ------------------------------------------------- lane-serial fixed-block path ----
+#include "../../debigulator_b200/csrc/bsplit_core.h"
+#include "../../debigulator_b200/csrc/fx_core.h"
+
+struct FxHeadArgs {
+    const dbg::FxLuts *luts;
     const uint8_t *in;
     uint64_t in_size;
     uint32_t chunk, chunk_bytes;
-    uint64_t entry;
-    uint16_t *cells;
-    uint32_t cell_cap;
-    uint64_t abs_base;
-    int write;
-    dbg::TransferEntry *table;
-    dbg::ChunkResult res[32];
+    uint32_t *hyp, *surv_start;
+    uint32_t nsurv[32];
 };
-static void chunk_body(void *p)
+static void fx_head_body(void *p)
 {
-    ChunkArgs *a = (ChunkArgs *)p;
-    int l = simt::lane();
-    if (a->write)
-        a->res[l] = dbg::decode_chunk<dbg::SINK_U16>(a->sm, a->in, a->in_size, a->chunk, a->chunk_bytes, a->entry, a->cells, a->cell_cap, a->abs_base);
-    else
-        dbg::transfer_chunk_warp(a->sm, a->in, a->in_size, a->chunk, a->chunk_bytes, a->table);
+    FxHeadArgs *a = (FxHeadArgs *)p;
+    a->nsurv[simt::lane()] = dbg::fx_head_warp(a->luts, a->in, a->in_size, a->chunk, a->chunk_bytes, a->hyp, a->surv_start);
+}
+struct FxExpandArgs {
+    const uint32_t *tok;
+    uint32_t ntok;
+    uint16_t *cells;
+    uint64_t abs_base;
+    uint32_t st[32], ob[32];
+};
+static void fx_expand_body(void *p)
+{
+    FxExpandArgs *a = (FxExpandArgs *)p;
+    const int l = simt::lane();
+    a->st[l] = dbg::expand_tokens_warp(a->tok, a->ntok, a->cells, a->abs_base, &a->ob[l]);
 }
 
-// The whole split-stream pipeline (transfer tables, chain, 16-bit decode, resolve) run chunk
-// by chunk through the emulator, mirroring split_kernels.cuh. Returns the status.
-extern "C" uint32_t emu_split_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
-                                      int misalign, int reverse, uint32_t chunk_bytes)
+// The whole lane-serial pipeline of fx_kernels.cuh (head, sizes, chain, tokens, expansion per group, resolve)
+// run through the emulator. Returns the status; 0x2000 = not a single fixed block, 0x3000 = the passes
+// disagree (cannot happen), 0x4000 = the chain needed a survivor that has no work item. *max_surv = the largest
+// number of survivors any chunk had, *n_chunks = chunks on the real chain.
+extern "C" uint32_t emu_fx_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
+                                   int misalign, int reverse, uint32_t chunk_bytes, uint32_t group_chunks, uint32_t *max_surv,
+                                   uint32_t *n_chunks)
 {
     size_t arena_sz = ((size_t)in_size + 64 + 32 + 15) & ~(size_t)15;
     uint8_t *arena = (uint8_t *)aligned_alloc(16, arena_sz);
     memset(arena, 0xA5, arena_sz);
     uint8_t *src = arena + 16 + (misalign & 15);
     memcpy(src, in, in_size);
-    dbg::InflateSmem *sm = (dbg::InflateSmem *)aligned_alloc(16, sizeof(dbg::InflateSmem));
+    memset(src + in_size, 0, 16);  // what the host API puts behind every item (and the reference binding behind its input)
     *final_size = 0;
+    *max_surv = 0;
+    *n_chunks = 0;
+    if (!dbg::is_single_fixed_block(src)) { free(arena); return 0x2000; }
+    dbg::FxLuts luts;
+    dbg::fx_build_luts(&luts, 0, 1);
+    const uint32_t nch = (uint32_t)((in_size + chunk_bytes - 1) / chunk_bytes);
+    uint32_t *hyp = (uint32_t *)calloc((size_t)(nch + 1) * 32, 4), *sstart = (uint32_t *)calloc((size_t)nch * 32, 4);
+    uint32_t *nsurv = (uint32_t *)calloc(nch, 4);
+    dbg::FxRec *rec = (dbg::FxRec *)calloc((size_t)nch * 32, sizeof(dbg::FxRec));
     uint32_t status = 0;
-    if (!dbg::is_single_fixed_block(src)) { free(sm); free(arena); return 0x2000; }
-    uint32_t nch = (uint32_t)((in_size + chunk_bytes - 1) / chunk_bytes);
-    dbg::TransferEntry *tf = (dbg::TransferEntry *)calloc((size_t)nch * 32, sizeof(dbg::TransferEntry));
-    uint64_t *entry = (uint64_t *)calloc(nch, 8), *ooff = (uint64_t *)calloc(nch + 1, 8);
-    uint32_t *olen = (uint32_t *)calloc(nch, 4), *flag = (uint32_t *)calloc(nch, 4);
-    ChunkArgs a;
-    a.sm = sm; a.in = src; a.in_size = in_size; a.cells = nullptr; a.chunk_bytes = chunk_bytes;
+    FxHeadArgs h;
+    h.luts = &luts; h.in = src; h.in_size = in_size; h.chunk_bytes = chunk_bytes;
     for (uint32_t c = 0; c < nch; c++) {
-        a.chunk = c; a.write = 0; a.table = tf + (size_t)c * 32;
-        simt::run_warp(chunk_body, &a, reverse);
+        h.chunk = c; h.hyp = hyp + (size_t)c * 32; h.surv_start = sstart + (size_t)c * 32;
+        simt::run_warp(fx_head_body, &h, reverse);
+        for (int i = 1; i < 32; i++) if (h.nsurv[i] != h.nsurv[0]) status = 0x1000 | i;
+        nsurv[c] = h.nsurv[0];
+        if (nsurv[c] > *max_surv) *max_surv = nsurv[c];
     }
-    uint64_t total = 0;
-    uint32_t idx = 0;
+    for (uint32_t c = 0; c < nch && !status; c++)
+        for (uint32_t sv = 0; sv < nsurv[c]; sv++)
+            rec[(size_t)c * 32 + sv] = dbg::fx_sizes_lane(&luts, src, in_size, c, chunk_bytes, sstart[(size_t)c * 32 + sv], hyp + (size_t)(c + 1) * 32);
+    // chain
+    uint32_t *csv = (uint32_t *)calloc(nch, 4), *ooff = (uint32_t *)calloc(nch + 1, 4), *toff = (uint32_t *)calloc(nch + 1, 4);
+    uint64_t pos = 0, tok = 0;
+    uint32_t e = 0, used = 0, end_flag = dbg::CH_RUN;
     bool ended = false;
-    for (uint32_t c = 0; c < nch; c++) {
-        ooff[c] = total;
-        if (ended) { flag[c] = dbg::CH_IDLE; continue; }
-        dbg::TransferEntry t = tf[(size_t)c * 32 + idx];
-        entry[c] = c == 0 ? 3 : (uint64_t)c * chunk_bytes * 8 + idx;
-        olen[c] = t.out_bytes; flag[c] = t.flag; total += t.out_bytes;
-        if (t.flag != dbg::CH_RUN) { ended = true; if (t.flag >= dbg::CH_ERR) status = dbg::ST_BAD_SYMBOL; }
-        idx = t.next;
+    for (uint32_t c = 0; c < nch && !status && !ended; c++) {
+        if (e >= nsurv[c]) { status = 0x4000; break; }
+        const dbg::FxRec r = rec[(size_t)c * 32 + e];
+        csv[c] = e; ooff[c] = (uint32_t)pos; toff[c] = (uint32_t)tok;
+        pos += r.out_bytes; tok += r.ntok; used++;
+        if ((r.link & 0xff) != dbg::CH_RUN) { ended = true; end_flag = r.link & 0xff; }
+        e = r.link >> 8;
     }
-    if (!ended) status = dbg::ST_TRUNCATED;
-    if (!status && total > cap) status = dbg::ST_OUT_OVERFLOW;
+    if (!status && !ended) status = dbg::ST_TRUNCATED;
+    if (!status && end_flag >= dbg::CH_ERR) status = end_flag - dbg::CH_ERR;
+    if (!status && pos > cap) status = dbg::ST_OUT_OVERFLOW;
+    *n_chunks = used;
     if (!status) {
-        uint16_t *cells = (uint16_t *)malloc((total + 16) * 2);
-        for (uint32_t c = 0; c < nch && !status; c++) {
-            if (flag[c] == dbg::CH_IDLE) break;
-            a.chunk = c; a.entry = entry[c]; a.write = 1; a.cells = cells + ooff[c]; a.cell_cap = olen[c]; a.abs_base = ooff[c];
-            simt::run_warp(chunk_body, &a, reverse);
-            if (a.res[0].flag >= dbg::CH_ERR) status = a.res[0].flag - dbg::CH_ERR;
-            else if (a.res[0].out_bytes != olen[c] || a.res[0].flag != flag[c]) status = 0x3000;
+        uint32_t *tokens = (uint32_t *)malloc((tok + 16) * 4);
+        for (uint32_t c = 0; c < used && !status; c++) {
+            const dbg::FxRec r = rec[(size_t)c * 32 + csv[c]];
+            uint32_t ob = 0, nt = 0;
+            dbg::fx_tokens_lane(&luts, src, in_size, c, chunk_bytes, sstart[(size_t)c * 32 + csv[c]], r.exit_rel, tokens + toff[c], &ob, &nt);
+            if (ob != r.out_bytes || nt != r.ntok) status = 0x3000;
         }
-        for (uint32_t c = 0; c < nch && !status; c++) {
-            if (flag[c] == dbg::CH_IDLE) break;
-            for (uint32_t i = 0; i < olen[c]; i++) {
-                uint32_t v = cells[ooff[c] + i];
-                out[ooff[c] + i] = v < 256 ? (uint8_t)v : out[ooff[c] + (int64_t)v - 33024];
+        uint16_t *cells = (uint16_t *)malloc((pos + 16) * 2);
+        ooff[used] = (uint32_t)pos; toff[used] = (uint32_t)tok;
+        for (uint32_t c = 0; c < used && !status; c += group_chunks) {
+            const uint32_t ce = c + group_chunks < used ? c + group_chunks : used;
+            FxExpandArgs x;
+            x.tok = tokens + toff[c]; x.ntok = toff[ce] - toff[c]; x.cells = cells + ooff[c]; x.abs_base = ooff[c];
+            simt::run_warp(fx_expand_body, &x, reverse);
+            if (x.st[0]) status = x.st[0];
+            else if (x.ob[0] != ooff[ce] - ooff[c]) status = 0x3000;
+            // resolve this group (markers point at most 32 KiB before the group)
+            for (uint32_t i = ooff[c]; i < ooff[ce] && !status; i++) {
+                const uint32_t v = cells[i];
+                out[i] = v < 256 ? (uint8_t)v : out[ooff[c] + (int64_t)v - 33024];
             }
         }
-        free(cells);
-        if (!status) *final_size = total;
+        free(cells); free(tokens);
+        if (!status) *final_size = pos;
     }
-    free(tf); free(entry); free(ooff); free(olen); free(flag); free(sm); free(arena);
+    free(hyp); free(sstart); free(nsurv); free(rec); free(csv); free(ooff); free(toff); free(arena);
     return status;
 }
 
 // ------------------------------------------------------------ block split ----
-#include "../../debigulator_b200/csrc/bsplit_core.h"
 
 struct BsArgs {
     dbg::InflateSmem *sm;

@@ -173,9 +173,10 @@ def test_large_batch_roundtrip_property(ctx):
         assert good == 1 and sha(out) == want[i % 64], i
 
 
-def test_split_stream_path_vs_reference(ctx, ref):
-    """Few large single-fixed-block streams (what stb writes): the batch is below the split threshold, so
-    these go through the chunk-parallel split-stream kernels. BASELINE config 4 shape at reduced size."""
+def test_lane_serial_fixed_block_path_vs_reference(ctx, ref):
+    """Large single-fixed-block streams (what stb writes) go through the lane-serial kernels (fx_kernels.cuh):
+    one lane per chunk, exact entry points from the 32-hypothesis head pass. BASELINE config 4 shape at reduced size."""
+    fx0 = ctx.fx_stats()
     imgs = [corpus.gradient_noise_rgba(1536, 1024, 500 + i) for i in range(3)]
     files = [ref.stb_png(im.tobytes(), 1536, 1024, 4, f) for im, f in zip(imgs, (4, -1, 0))]
     assert all(len(f) > 4 * 32768 for f in files)
@@ -194,6 +195,8 @@ def test_split_stream_path_vs_reference(ctx, ref):
     for s, c, (good, out) in zip(streams, caps, got):
         rgood, rout = ref.inflate(s, c)
         assert good == rgood and out == rout
+    fx1 = ctx.fx_stats()
+    assert fx1[0] - fx0[0] == 6 and fx1[1] == fx0[1], (fx0, fx1)  # all but the 3 KB stream of zeros took that path, none was handed back
 
 
 def test_cfg5_extremes_vs_reference(ctx, ref):
