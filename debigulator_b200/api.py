@@ -53,6 +53,24 @@ def load_library():
     L.dbg_profile_enable.restype = i32
     L.dbg_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     L.dbg_profile_read.restype = i32
+    L.dbg_profile_read_tag.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.dbg_profile_read_tag.restype = i32
+    L.dbg_trim.argtypes = [vp]
+    L.dbg_trim.restype = i32
+    L.dbg_multi_create.argtypes = [i32, C.POINTER(i32)]
+    L.dbg_multi_create.restype = vp
+    L.dbg_multi_destroy.argtypes = [vp]
+    L.dbg_multi_destroy.restype = None
+    L.dbg_multi_device_count.argtypes = [vp]
+    L.dbg_multi_device_count.restype = i32
+    L.dbg_multi_ctx.argtypes = [vp, i32]
+    L.dbg_multi_ctx.restype = vp
+    L.dbg_multi_last_error.argtypes = [vp]
+    L.dbg_multi_last_error.restype = C.c_char_p
+    L.dbg_decode_batch_packed_multi.argtypes = [vp, i32, u64] + [vp] * 9
+    L.dbg_decode_batch_packed_multi.restype = i32
+    L.dbg_multi_partition.argtypes = [i32, i32, u64] + [vp] * 7
+    L.dbg_multi_partition.restype = i32
     L.dbg_bsplit_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.dbg_bsplit_stats.restype = i32
     L.dbg_fx_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -160,6 +178,18 @@ class Context:
         ms, n = C.c_double(0), C.c_uint64(0)
         self._check(self.L.dbg_profile_read(self.h, C.byref(ms), C.byref(n)), "dbg_profile_read")
         return float(ms.value), int(n.value)
+
+    PROF_INFLATE, PROF_FX_SIZES, PROF_FX_EXPAND, PROF_PNG_SCAN, PROF_PNG_UNFILTER = range(5)
+
+    def profile_read_tag(self, tag):
+        """(total ms, brackets) of one kernel group (PROF_*) since profile_enable."""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        self._check(self.L.dbg_profile_read_tag(self.h, tag, C.byref(ms), C.byref(n)), "dbg_profile_read_tag")
+        return float(ms.value), int(n.value)
+
+    def trim(self):
+        """Releases the grow-only scratch of the context (dbg_trim)."""
+        self._check(self.L.dbg_trim(self.h), "dbg_trim")
 
     def bsplit_stats(self):
         """(streams decoded by the block-split path, streams handed back to the warp-per-stream kernel)."""
@@ -274,3 +304,58 @@ class Context:
                                                        _ptr(rgba_size), _ptr(width), _ptr(height), _ptr(d_out),
                                                        _ptr(out_off), _ptr(out_cap), _ptr(out_size), _ptr(status), stream),
                     "dbg_encode_bmp_batch_device")
+
+
+def partition(n_devices, kind, in_off, in_size, out_off, out_cap, h_in=None):
+    """dbg_multi_partition: (device index per item, estimated cost per device, runs). Pure host code, needs no GPU."""
+    L = load_library()
+    n = len(in_off)
+    a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (in_off, in_size, out_off, out_cap)]
+    dev = np.zeros(n, dtype=np.uint32)
+    cost = np.zeros(n_devices, dtype=np.uint64)
+    runs = L.dbg_multi_partition(int(n_devices), int(kind), n, _ptr(h_in), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]),
+                                 _ptr(dev), _ptr(cost))
+    if runs < 0:
+        raise DebigulatorError("dbg_multi_partition: bad arguments")
+    return dev, cost, runs
+
+
+class MultiContext:
+    """Several GPUs of one box behind one call (dbg_multi_*): one context, stream set and host thread per device."""
+
+    def __init__(self, n_devices=0, device_ids=None):
+        self.L = load_library()
+        ids = (C.c_int * len(device_ids))(*device_ids) if device_ids else None
+        self.h = self.L.dbg_multi_create(int(n_devices), ids)
+        if not self.h:
+            raise DebigulatorError("dbg_multi_create failed: " + (self.L.dbg_last_error(None) or b"").decode())
+        self.n_devices = self.L.dbg_multi_device_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.dbg_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def fx_stats(self, k):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.L.dbg_fx_stats(self.L.dbg_multi_ctx(self.h, k), C.byref(a), C.byref(b), C.byref(c))
+        return int(a.value), int(b.value), int(c.value)
+
+    def decode_packed(self, kind, h_in, in_off, in_size, h_out, out_off, out_cap):
+        """Returns (out_size, status, device_of_item)."""
+        n = len(in_off)
+        a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (in_off, in_size, out_off, out_cap)]
+        out_size = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.uint32)
+        dev = np.zeros(n, dtype=np.uint32)
+        rc = self.L.dbg_decode_batch_packed_multi(self.h, int(kind), n, _ptr(h_in), _ptr(a[0]), _ptr(a[1]), _ptr(h_out), _ptr(a[2]),
+                                                  _ptr(a[3]), _ptr(out_size), _ptr(status), _ptr(dev))
+        if rc != 0:
+            raise DebigulatorError("dbg_decode_batch_packed_multi failed (%d): %s" % (rc, (self.L.dbg_multi_last_error(self.h) or b"").decode()))
+        return out_size, status, dev

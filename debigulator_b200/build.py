@@ -52,5 +52,21 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+STBGEN = os.path.join(HERE, "tools", "libstbgen.so")
+REF_SRC = "/root/reference/src"
+
+
+def build_tools():
+    """Corpus tooling (not product code): the synthetic-PNG writer, compiled against the reference's vendored
+    stb_write.h where it lies. Returns the library path, or None when neither the reference tree nor a prebuilt
+    library is there (the GPU box uses the prebuilt one)."""
+    src = os.path.join(HERE, "tools", "stb_gen.c")
+    if os.path.isdir(REF_SRC):
+        if not os.path.exists(STBGEN) or os.path.getmtime(src) > os.path.getmtime(STBGEN):
+            subprocess.check_call(["gcc", "-O2", "-w", "-fPIC", "-shared", "-I" + REF_SRC, src, "-o", STBGEN])
+    return STBGEN if os.path.exists(STBGEN) else None
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_tools())

@@ -42,6 +42,55 @@ def fixed_block_deflate(data):
     assert n <= cap
     return out.raw[:n]
 
+_STB = None
+
+
+def stb_available():
+    from .build import build_tools
+    return build_tools() is not None
+
+
+def _stb():
+    """The reference's vendored stb_image_write (tools/stb_gen.c, compiled against /root/reference/src/stb_write.h)."""
+    global _STB
+    if _STB is None:
+        from .build import build_tools
+        path = build_tools()
+        if path is None:
+            raise RuntimeError("tools/libstbgen.so is missing and /root/reference is not here to build it")
+        L = ctypes.CDLL(path)
+        L.stbgen_png.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.stbgen_png.restype = ctypes.c_void_p
+        L.stbgen_zlib.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.stbgen_zlib.restype = ctypes.c_void_p
+        L.stbgen_free.argtypes = [ctypes.c_void_p]
+        L.stbgen_free.restype = None
+        _STB = L
+    return _STB
+
+
+def stb_png(pixels, w, h, comp=4, filt=-1):
+    """PNG bytes written by stb_image_write (stb_write.h:1128): one IDAT, one fixed-Huffman block."""
+    L = _stb()
+    n = ctypes.c_int(0)
+    px = np.ascontiguousarray(np.frombuffer(pixels, np.uint8) if isinstance(pixels, (bytes, bytearray)) else pixels)
+    assert px.size == w * h * comp
+    p = L.stbgen_png(px.ctypes.data, w, h, comp, filt, ctypes.byref(n))
+    out = ctypes.string_at(p, n.value)
+    L.stbgen_free(p)
+    return out
+
+
+def stb_zlib(data, quality=8):
+    L = _stb()
+    n = ctypes.c_int(0)
+    buf = ctypes.create_string_buffer(bytes(data), len(data))
+    p = L.stbgen_zlib(buf, len(data), quality, ctypes.byref(n))
+    out = ctypes.string_at(p, n.value)
+    L.stbgen_free(p)
+    return out
+
+
 GZ_SEED_BASE = 0x64620000
 
 
@@ -233,9 +282,17 @@ def write_png(img, filt=-1, level=6, strategy=zlib.Z_FIXED, idat_split=0, color_
 
 
 def png_cfg3(i, w=1024, h=1024):
-    """BASELINE config 3 image i: forced filter i%6-1 (-1 = adaptive). Returns (png bytes, rgba bytes)."""
+    """BASELINE config 3 image i: forced filter i%6-1 (-1 = adaptive). Returns (png bytes, rgba bytes).
+    Written by this module's own encoder (tools/fixed_deflate.c): the stream shape stb writes, not stb itself."""
     img = gradient_noise_rgba(w, h, 0x706E6700 + i)
     return write_png(img, filt=i % 6 - 1, single_block=True), img.tobytes()
+
+
+def png_stb(i, w=1024, h=1024, filt=None):
+    """BASELINE config 3 / 4 image i written by stb_image_write itself: smooth gradient + low-amplitude
+    noise, filter forced to i%6-1 (-1 = adaptive) unless `filt` says otherwise. Returns (png bytes, rgba bytes)."""
+    img = gradient_noise_rgba(w, h, 0x706E6700 + i)
+    return stb_png(img, w, h, 4, (i % 6 - 1) if filt is None else filt), img.tobytes()
 
 
 def bmp_file(rgba: bytes, w: int, h: int, bottom_up: bool = False, v4: bool = False, pad: int = 0,

@@ -268,9 +268,11 @@ DBG_DEV uint32_t expand_tokens_warp(const uint32_t *tok, uint32_t ntok, uint16_t
 {
     const uint32_t ln = (uint32_t)simt::lane();
     uint32_t pos = 0, err = ST_OK;
+    uint32_t t_next = ln < ntok ? simt::ldg_u32(tok + ln) : 0u;
     for (uint32_t base = 0; base < ntok; base += 32) {
         const bool have = base + ln < ntok;
-        const uint32_t t = have ? simt::ldg_u32(tok + base + ln) : 0u;
+        const uint32_t t = t_next;
+        t_next = base + 32 + ln < ntok ? simt::ldg_u32(tok + base + 32 + ln) : 0u;  // the next step's tokens are on their way
         const bool is_match = have && (t & TOKEN_MATCH);
         const uint32_t len = !have ? 0u : is_match ? (t >> 16) & 0x1ff : 1u;
         const uint32_t dist = (t & 0x7fff) + 1;
@@ -290,9 +292,29 @@ DBG_DEV uint32_t expand_tokens_warp(const uint32_t *tok, uint32_t ntok, uint16_t
             break;
         }
         if (free_m) {
-            for (uint32_t i = 0; i < len; i++) {
-                const int32_t si = (int32_t)(o + i) - (int32_t)dist;
-                cells[o + i] = si < 0 ? (uint16_t)(256 + 32768 + si) : cells[si];
+            // nothing this step writes is read here, so the loads of a round all go out before its stores (a
+            // load-store-load chain would pay one L2 round trip per cell)
+            const int32_t s0 = (int32_t)o - (int32_t)dist;
+            if (s0 >= 0) {
+                const uint16_t *src = cells + s0;
+                uint16_t *dst = cells + o;
+                for (uint32_t rem = len; ; rem -= 8) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = (uint32_t)j < rem ? src[j] : 0u;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if ((uint32_t)j < rem) dst[j] = (uint16_t)v[j];
+                    if (rem <= 8) break;
+                    src += 8;
+                    dst += 8;
+                }
+            } else {  // reaches before the group: markers for that part
+                for (uint32_t i = 0; i < len; i++) {
+                    const int32_t si = s0 + (int32_t)i;
+                    const uint32_t v = si < 0 ? (uint32_t)(256 + 32768 + si) : cells[si];
+                    cells[o + i] = (uint16_t)v;
+                }
             }
         }
         simt::syncwarp();  // literals and free matches of this step are in place

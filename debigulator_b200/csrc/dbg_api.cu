@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -56,13 +57,34 @@ struct Buf {
     }
 };
 
+// Scratch of one batch in flight. The device-resident entry points use slot 0; the packed host API cuts a batch
+// into waves and gives every wave its own slot and stream, so that the waves' uploads, kernels and downloads overlap.
+struct Slot {
+    cudaStream_t stream = nullptr;   // the wave's stream
+    cudaEvent_t done = nullptr;      // recorded behind the last work that used this slot's scratch
+    Buf counter;                     // work-queue heads
+    Buf meta;                        // derived descriptors (gzip payloads, BMP items)
+    Buf png_scratch;                 // PNG: per-image meta, task queues, compacted IDAT, filtered scanlines
+    Buf sched;                       // work-queue order computed on the device when the caller brings none
+    Buf fx_stream, fx_chunks, fx_tok, cells, h_fx;            // lane-serial fixed-block path (fx_kernels.cuh)
+    Buf bs_stream, bs_region, bs_cells, bs_tok, h_bs;         // block-split path (bsplit_kernels.cuh)
+    Slot() { h_fx.pinned_host = h_bs.pinned_host = true; }
+    void release()
+    {
+        Buf *all[] = {&counter, &meta, &png_scratch, &sched, &fx_stream, &fx_chunks, &fx_tok, &cells, &h_fx,
+                      &bs_stream, &bs_region, &bs_cells, &bs_tok, &h_bs};
+        for (Buf *b : all) b->release();
+    }
+};
+
 struct dbg_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     static constexpr int MAX_WAVES = 16;
-    cudaStream_t wave_stream[MAX_WAVES] = {};
-    int waves = 16;  // waves the packed host API cuts a large batch into (H2D / kernels / D2H overlap); cfg2 end to end: 2 -> 23.5, 4 -> 25.8, 8 -> 26.7, 16 -> 27.4 GB/s
+    Slot slot[MAX_WAVES];
+    int waves = 16;      // waves the packed host API cuts a large gzip / deflate batch into (cfg2 end to end: 2 -> 23.5, 4 -> 25.8, 8 -> 26.7, 16 -> 27.4 GB/s)
+    int png_waves = 8;   // the same for PNG batches (every wave synchronises the host twice on the lane-serial path)
     cudaEvent_t wave_ready = nullptr;
     cudaStream_t aux_stream = nullptr;  // the warp-per-stream kernel runs here beside the block-split kernels
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
@@ -71,39 +93,27 @@ struct dbg_ctx {
     // optional per-launch timing of the dominant (inflate) kernel, for roofline reports
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<int> prof_tag;  // DBG_PROF_* of every bracket
     size_t prof_used = 0;
-    // device-side scratch
-    Buf d_counter;                 // work-queue heads
-    Buf d_meta;                    // derived descriptors (gzip payloads, PNG streams)
-    Buf d_png_scratch;             // compacted IDAT + filtered scanlines
-    Buf d_split, d_split_chunks, d_cells, h_summary;  // split-stream path: chunk tables, 16-bit cells, pinned summary
-    // block-split path (long multi-block streams): per wave slot, since waves run concurrently
-    Buf d_sched[MAX_WAVES];        // work-queue order computed on the device when the caller brings none
-    uint32_t split_chunk_forced = 0;  // DBG_SPLIT_CHUNK: fixed chunk size of the split-stream path (experiments)
-    bool bsplit_allowed = true;    // cleared while the packed API runs several waves at once
-    Buf d_bs_stream[MAX_WAVES], d_bs_region[MAX_WAVES], d_bs_cells[MAX_WAVES], d_bs_tok[MAX_WAVES], h_bs_summary[MAX_WAVES];
+    // tunables (environment)
+    uint32_t fx_chunk_forced = 0, fx_group_forced = 0;  // DBG_FX_CHUNK / DBG_FX_GROUP: fixed chunk / group size (experiments)
+    bool fx = true;                 // lane-serial path for single fixed-Huffman-block streams
     uint32_t bsplit_tok_per_byte = 4;             // token slots per compressed byte (0 = no tokens: decode twice)
     uint64_t bsplit_tok_max_bytes = 24ull << 30;  // the token area never grows beyond this
     bool bsplit = true;
     uint64_t bsplit_min_bytes = dbg::BS_MIN_BYTES;
     uint32_t bsplit_factor_q = 8;
     uint32_t bsplit_region = dbg::REGION_BYTES, bsplit_region_min = 16384;
-    uint64_t bs_streams = 0, bs_fallbacks = 0;  // counters: streams that took the block-split path / were handed back
-    uint32_t split_max_streams = 1536;  // packed host API: smaller batches run as one wave (so that the per-context paths may take them)
-    bool fx = true;                     // lane-serial path for single fixed-Huffman-block streams (fx_kernels.cuh)
-    uint32_t fx_group_forced = 0;       // DBG_FX_GROUP: fixed group size (experiments)
-    uint64_t fx_streams = 0, fx_redo = 0, fx_extra = 0;  // counters: streams on that path / handed back / extra survivors
-    Buf d_fx_tok;                       // its tokens
-    bool verify = false;                // opt-in: check gzip CRC32 / ISIZE trailers
+    uint32_t small_batch = 1536;    // packed host API: gzip / deflate batches below this run as one wave with the intra-stream paths on
+    bool verify = false;            // opt-in: check gzip CRC32 / ISIZE trailers, zlib Adler-32
     uint32_t inflate_ctas_per_sm = dbg::INFLATE_CTAS_PER_SM;  // resident streams per SM = 4x this (tunable: L2 footprint)
+    // counters
+    uint64_t bs_streams = 0, bs_fallbacks = 0;
+    uint64_t fx_streams = 0, fx_redo = 0, fx_extra = 0;
     // host-API staging
     Buf d_in, d_out, d_desc;       // arenas + descriptor tables
     Buf h_in, h_out, h_desc;       // pinned mirrors
-    dbg_ctx()
-    {
-        h_in.pinned_host = h_out.pinned_host = h_desc.pinned_host = h_summary.pinned_host = true;
-        for (int k = 0; k < MAX_WAVES; k++) h_bs_summary[k].pinned_host = true;
-    }
+    dbg_ctx() { h_in.pinned_host = h_out.pinned_host = h_desc.pinned_host = true; }
 };
 
 static void set_err(dbg_ctx *ctx, const char *fmt, ...)
@@ -124,7 +134,7 @@ static void set_err(dbg_ctx *ctx, const char *fmt, ...)
         }                                                                                               \
     } while (0)
 
-extern "C" int dbg_version(void) { return 100; }
+extern "C" int dbg_version(void) { return 200; }
 
 extern "C" int dbg_device_count(void)
 {
@@ -140,6 +150,8 @@ extern "C" int dbg_device_count(void)
 extern "C" const char *dbg_last_error(const dbg_ctx *ctx) { return ctx ? ctx->err : g_err; }
 extern "C" int dbg_ctx_device(const dbg_ctx *ctx) { return ctx ? ctx->device : -1; }
 extern "C" uint64_t dbg_kernel_launches(const dbg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void dbg_destroy(dbg_ctx *ctx);
 
 extern "C" dbg_ctx *dbg_create(int device)
 {
@@ -164,34 +176,40 @@ extern "C" dbg_ctx *dbg_create(int device)
     dbg_ctx *ctx = new dbg_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        set_err(nullptr, "cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
-        delete ctx;
+    // every stream, event and kernel attribute is needed: a half-made context would run waves on the legacy stream
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < dbg_ctx::MAX_WAVES && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot[i].done, cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->wave_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
+    const size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
+    if (e != cudaSuccess) {
+        set_err(nullptr, "dbg_create: %s", cudaGetErrorString(e));
+        dbg_destroy(ctx);
         return nullptr;
     }
-    for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) cudaStreamCreateWithFlags(&ctx->wave_stream[i], cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&ctx->wave_ready, cudaEventDisableTiming);
-    cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
-    size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
-    cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
     dbg::png_configure_kernels();
-    if (const char *e = getenv("DBG_SPLIT_MAX_STREAMS")) ctx->split_max_streams = (uint32_t)atoi(e);
-    if (const char *e = getenv("DBG_SPLIT_CHUNK")) ctx->split_chunk_forced = (uint32_t)std::min(1 << 20, std::max((int)dbg::FX_MIN_CHUNK, atoi(e))) & ~15u;
-    if (const char *e = getenv("DBG_FX_GROUP")) ctx->fx_group_forced = (uint32_t)std::min(1 << 22, std::max(4096, atoi(e))) & ~15u;
-    if (const char *e = getenv("DBG_FX")) ctx->fx = atoi(e) != 0;
-    if (const char *e = getenv("DBG_WAVES")) ctx->waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(e)));
-    if (const char *e = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(e) != 0;
-    if (const char *e = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(e));
-    if (const char *e = getenv("DBG_BSPLIT_TOKENS")) ctx->bsplit_tok_per_byte = (uint32_t)std::min(8, std::max(0, atoi(e)));
-    if (const char *e = getenv("DBG_BSPLIT_REGION")) ctx->bsplit_region = (uint32_t)std::min(1 << 20, std::max(4096, atoi(e)));
-    if (const char *e = getenv("DBG_BSPLIT_REGION_MIN")) ctx->bsplit_region_min = (uint32_t)std::min((int)ctx->bsplit_region, std::max(4096, atoi(e)));
-    if (const char *e = getenv("DBG_BSPLIT_MIN_BYTES")) ctx->bsplit_min_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 2 * (uint64_t)ctx->bsplit_region);
-    if (const char *e = getenv("DBG_INFLATE_CTAS_PER_SM")) {
-        int v = atoi(e);
-        if (v >= 1 && v <= dbg::INFLATE_CTAS_PER_SM) ctx->inflate_ctas_per_sm = (uint32_t)v;
+    if (const char *v = getenv("DBG_SMALL_BATCH")) ctx->small_batch = (uint32_t)atoi(v);
+    if (const char *v = getenv("DBG_FX_CHUNK")) ctx->fx_chunk_forced = (uint32_t)std::min(1 << 20, std::max((int)dbg::FX_MIN_CHUNK, atoi(v))) & ~15u;
+    if (const char *v = getenv("DBG_FX_GROUP")) ctx->fx_group_forced = (uint32_t)std::min(1 << 22, std::max(4096, atoi(v))) & ~15u;
+    if (const char *v = getenv("DBG_FX")) ctx->fx = atoi(v) != 0;
+    if (const char *v = getenv("DBG_WAVES")) ctx->waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(v)));
+    if (const char *v = getenv("DBG_PNG_WAVES")) ctx->png_waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(v)));
+    if (const char *v = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(v) != 0;
+    if (const char *v = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(v));
+    if (const char *v = getenv("DBG_BSPLIT_TOKENS")) ctx->bsplit_tok_per_byte = (uint32_t)std::min(8, std::max(0, atoi(v)));
+    if (const char *v = getenv("DBG_BSPLIT_REGION")) ctx->bsplit_region = (uint32_t)std::min(1 << 20, std::max(4096, atoi(v)));
+    if (const char *v = getenv("DBG_BSPLIT_REGION_MIN")) ctx->bsplit_region_min = (uint32_t)std::min((int)ctx->bsplit_region, std::max(4096, atoi(v)));
+    if (const char *v = getenv("DBG_BSPLIT_MIN_BYTES")) ctx->bsplit_min_bytes = std::max<uint64_t>(strtoull(v, nullptr, 10), 2 * (uint64_t)ctx->bsplit_region);
+    if (const char *v = getenv("DBG_INFLATE_CTAS_PER_SM")) {
+        int k = atoi(v);
+        if (k >= 1 && k <= dbg::INFLATE_CTAS_PER_SM) ctx->inflate_ctas_per_sm = (uint32_t)k;
     }
     return ctx;
 }
@@ -200,25 +218,23 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    Buf *all[] = {&ctx->d_counter, &ctx->d_meta, &ctx->d_png_scratch, &ctx->d_in,    &ctx->d_out,    &ctx->d_desc,
-                  &ctx->h_in,      &ctx->h_out,  &ctx->h_desc,        &ctx->d_split, &ctx->d_cells, &ctx->h_summary,
-                  &ctx->d_split_chunks, &ctx->d_fx_tok};
+    cudaDeviceSynchronize();
+    Buf *all[] = {&ctx->d_in, &ctx->d_out, &ctx->d_desc, &ctx->h_in, &ctx->h_out, &ctx->h_desc};
     for (Buf *b : all) b->release();
     for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) {
-        ctx->d_sched[i].release();
-        ctx->d_bs_stream[i].release();
-        ctx->d_bs_region[i].release();
-        ctx->d_bs_cells[i].release();
-        ctx->d_bs_tok[i].release();
-        ctx->h_bs_summary[i].release();
-        if (ctx->wave_stream[i]) cudaStreamDestroy(ctx->wave_stream[i]);
+        ctx->slot[i].release();
+        if (ctx->slot[i].stream) cudaStreamDestroy(ctx->slot[i].stream);
+        if (ctx->slot[i].done) cudaEventDestroy(ctx->slot[i].done);
+    }
+    for (auto &pe : ctx->prof_events) {
+        cudaEventDestroy(pe.first);
+        cudaEventDestroy(pe.second);
     }
     if (ctx->wave_ready) cudaEventDestroy(ctx->wave_ready);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
     if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -246,6 +262,19 @@ extern "C" int dbg_set_verify(dbg_ctx *ctx, int on)
     return DBG_OK;
 }
 
+// Releases the grow-only scratch the context keeps between calls (cells, tokens, PNG scanline buffers, staging
+// arenas); the next call allocates what it needs again.
+extern "C" int dbg_trim(dbg_ctx *ctx)
+{
+    if (!ctx) return DBG_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) ctx->slot[i].release();
+    Buf *all[] = {&ctx->d_in, &ctx->d_out, &ctx->d_desc, &ctx->h_in, &ctx->h_out, &ctx->h_desc};
+    for (Buf *b : all) b->release();
+    return DBG_OK;
+}
+
 extern "C" int dbg_profile_enable(dbg_ctx *ctx, int on)
 {
     if (!ctx) return DBG_ERR_ARG;
@@ -254,23 +283,33 @@ extern "C" int dbg_profile_enable(dbg_ctx *ctx, int on)
     return DBG_OK;
 }
 
-// Sum of the device durations (ms) of the inflate kernels launched since
-// dbg_profile_enable(ctx, 1), and how many there were. Waits for them.
-extern "C" int dbg_profile_read(dbg_ctx *ctx, double *total_ms, uint64_t *launches)
+// Sum of the device durations (ms) of the brackets with tag `tag` recorded since dbg_profile_enable(ctx, 1), and
+// how many there were. Waits for them; dbg_profile_enable(ctx, 1) resets.
+extern "C" int dbg_profile_read_tag(dbg_ctx *ctx, int tag, double *total_ms, uint64_t *launches)
 {
     if (!ctx || !total_ms || !launches) return DBG_ERR_ARG;
     CU(cudaSetDevice(ctx->device));
     double sum = 0;
+    uint64_t cnt = 0;
     for (size_t i = 0; i < ctx->prof_used; i++) {
+        if (ctx->prof_tag[i] != tag) continue;
         float ms = 0;
         CU(cudaEventSynchronize(ctx->prof_events[i].second));
         CU(cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second));
         sum += ms;
+        cnt++;
     }
     *total_ms = sum;
-    *launches = ctx->prof_used;
-    ctx->prof_used = 0;
+    *launches = cnt;
     return DBG_OK;
+}
+
+// The warp-per-stream inflate kernel's launches (tag DBG_PROF_INFLATE); resets the recording.
+extern "C" int dbg_profile_read(dbg_ctx *ctx, double *total_ms, uint64_t *launches)
+{
+    int rc = dbg_profile_read_tag(ctx, DBG_PROF_INFLATE, total_ms, launches);
+    if (rc == DBG_OK) ctx->prof_used = 0;
+    return rc;
 }
 
 extern "C" int dbg_synchronize(dbg_ctx *ctx)
@@ -282,35 +321,50 @@ extern "C" int dbg_synchronize(dbg_ctx *ctx)
 }
 
 // ------------------------------------------------------------------ launches --
-static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot, bool may_order)
-{
-    a.counter = d_counter;
-    if (may_order && !a.order && a.n > (uint32_t)ctx->sm_count) {  // heaviest first, so that the longest streams do not start last
-        CU(ctx->d_sched[slot].reserve((size_t)a.n * 4));
-        dbg::sched_order_kernel<<<1, 1024, 0, s>>>(a, (uint32_t *)ctx->d_sched[slot].p);
-        ctx->launches++;
-        a.order = (const uint32_t *)ctx->d_sched[slot].p;
+// Brackets a kernel sequence with the profiling events when dbg_profile_enable() is on.
+struct ProfScope {
+    dbg_ctx *ctx;
+    cudaStream_t s;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(dbg_ctx *c, cudaStream_t st, int tag) : ctx(c), s(st)
+    {
+        if (!ctx->profiling) return;
+        if (ctx->prof_used == ctx->prof_events.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            ctx->prof_events.push_back({a, b});
+            ctx->prof_tag.push_back(0);
+        }
+        ctx->prof_tag[ctx->prof_used] = tag;
+        cudaEventRecord(ctx->prof_events[ctx->prof_used].first, s);
+        e1 = ctx->prof_events[ctx->prof_used].second;
+        ctx->prof_used++;
     }
-    CU(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), s));
+    ~ProfScope()
+    {
+        if (e1) cudaEventRecord(e1, s);
+    }
+};
+
+static int launch_inflate_plain(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, int counter_idx, cudaStream_t s, bool may_order = true)
+{
+    a.counter = (uint32_t *)sl.counter.p + counter_idx;
+    if (may_order && !a.order && a.n > (uint32_t)ctx->sm_count) {  // heaviest first, so that the longest streams do not start last
+        CU(sl.sched.reserve((size_t)a.n * 4));
+        dbg::sched_order_kernel<<<1, 1024, 0, s>>>(a, (uint32_t *)sl.sched.p);
+        ctx->launches++;
+        a.order = (const uint32_t *)sl.sched.p;
+    }
+    CU(cudaMemsetAsync(a.counter, 0, sizeof(uint32_t), s));
     uint32_t ctas_needed = (a.n + dbg::INFLATE_WARPS_PER_CTA - 1) / dbg::INFLATE_WARPS_PER_CTA;
     uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)ctx->sm_count * ctx->inflate_ctas_per_sm);
     size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ctx->profiling) {
-        if (ctx->prof_used == ctx->prof_events.size()) {
-            CU(cudaEventCreate(&e0));
-            CU(cudaEventCreate(&e1));
-            ctx->prof_events.push_back({e0, e1});
-        }
-        e0 = ctx->prof_events[ctx->prof_used].first;
-        e1 = ctx->prof_events[ctx->prof_used].second;
-        ctx->prof_used++;
-        CU(cudaEventRecord(e0, s));
+    {
+        ProfScope prof(ctx, s, DBG_PROF_INFLATE);
+        dbg::inflate_batch_kernel<<<grid, dbg::INFLATE_THREADS, smem, s>>>(a);
     }
-    dbg::inflate_batch_kernel<<<grid, dbg::INFLATE_THREADS, smem, s>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
-    if (e1) CU(cudaEventRecord(e1, s));
     return DBG_OK;
 }
 
@@ -318,16 +372,16 @@ static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_c
 // fx_kernels.cuh. Two small device->host reads (how many streams / bytes; exact token and cell counts), so `s`
 // is synchronised twice. *skip_out = per-stream flags of the streams handled here, *redo_out = those handed
 // back (flag set as well) for a second warp-per-stream pass; *n_redo tells whether there are any.
-static int run_fx(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t **skip_out, const uint32_t **redo_out,
-                  uint32_t *n_redo)
+static int run_fx(dbg_ctx *ctx, Slot &sl, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t **skip_out,
+                  const uint32_t **redo_out, uint32_t *n_redo)
 {
     *skip_out = nullptr;
     *redo_out = nullptr;
     *n_redo = 0;
     const uint32_t n = a.n;
-    CU(ctx->h_summary.reserve(sizeof(dbg::FxSummary)));
-    CU(ctx->d_split.reserve(256 + (size_t)n * (2 * 8 + 6 * 4) + 256));
-    uint8_t *p = (uint8_t *)ctx->d_split.p;
+    CU(sl.h_fx.reserve(sizeof(dbg::FxSummary)));
+    CU(sl.fx_stream.reserve(256 + (size_t)n * (2 * 8 + 6 * 4) + 256));
+    uint8_t *p = (uint8_t *)sl.fx_stream.p;
     dbg::FxBatch b{};
     b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
     b.out_base = a.out_base; b.out_off = a.out_off; b.out_cap = a.out_cap;
@@ -346,7 +400,7 @@ static int run_fx(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, cons
     dbg::fx_classify_kernel<<<sb, 128, 0, s>>>(b);
     ctx->launches++;
     CU(cudaGetLastError());
-    dbg::FxSummary *hs = (dbg::FxSummary *)ctx->h_summary.p;
+    dbg::FxSummary *hs = (dbg::FxSummary *)sl.h_fx.p;
     CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::FxSummary), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (hs->n_fx == 0) return DBG_OK;
@@ -357,7 +411,7 @@ static int run_fx(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, cons
     const uint64_t lanes_wanted = (uint64_t)ctx->sm_count * 2048;
     uint32_t chunk = 16384;
     while (chunk > dbg::FX_MIN_CHUNK && hs->fx_in / chunk < lanes_wanted) chunk >>= 1;
-    if (ctx->split_chunk_forced) chunk = ctx->split_chunk_forced;
+    if (ctx->fx_chunk_forced) chunk = ctx->fx_chunk_forced;
     uint32_t group = 262144;
     const uint64_t warps_wanted = (uint64_t)ctx->sm_count * 32;
     while (group > 32768 && hs->fx_in / group < warps_wanted) group >>= 1;
@@ -371,8 +425,8 @@ static int run_fx(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, cons
     b.extra_cap = T / 8 + 1024;
     const size_t per_chunk = (size_t)T * (3 * 32 * 4 + 5 * 4) + (size_t)b.extra_cap * 4 + ((size_t)T + b.extra_cap) * sizeof(dbg::FxRec) +
                              (size_t)NG * (2 * 8 + 4 * 4) + 1024;
-    CU(ctx->d_split_chunks.reserve(per_chunk));
-    uint8_t *q = (uint8_t *)ctx->d_split_chunks.p;
+    CU(sl.fx_chunks.reserve(per_chunk));
+    uint8_t *q = (uint8_t *)sl.fx_chunks.p;
     b.rec = (dbg::FxRec *)q;
     b.g_out_off = (uint64_t *)(b.rec + T + b.extra_cap);
     b.g_tok_off = b.g_out_off + NG;
@@ -389,26 +443,30 @@ static int run_fx(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, cons
     b.g_out_len = b.group_stream + NG;
     b.g_flag = b.g_out_len + NG;
     b.g_ntok = b.g_flag + NG;
-    CU(cudaMemsetAsync(b.chunk_stream, 0, (size_t)T * 2 * 4, s));                    // chunk_stream, nsurv of unused slots
-    CU(cudaMemsetAsync(b.c_surv, 0xff, (size_t)T * 4, s));                           // FX_NONE
-    CU(cudaMemsetAsync(b.group_stream, 0, (size_t)NG * 4 * 4, s));                   // group_stream, g_out_len, g_flag, g_ntok of unused slots
+    CU(cudaMemsetAsync(b.chunk_stream, 0, (size_t)T * 2 * 4, s));     // chunk_stream, nsurv of unused slots
+    CU(cudaMemsetAsync(b.c_surv, 0xff, (size_t)T * 4, s));            // FX_NONE
+    CU(cudaMemsetAsync(b.group_stream, 0, (size_t)NG * 4 * 4, s));    // group_stream, g_out_len, g_flag, g_ntok of unused slots
     const uint32_t warp_grid = std::min<uint32_t>((T + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 12);
     const uint32_t lane_grid = std::min<uint32_t>((T + dbg::FX_LANE_THREADS - 1) / dbg::FX_LANE_THREADS, (uint32_t)ctx->sm_count * 12);
-    dbg::fx_assign_kernel<<<sb, 128, 0, s>>>(b);
-    dbg::fx_fill_kernel<<<n, 128, 0, s>>>(b);
-    dbg::fx_head_kernel<<<warp_grid, dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
-    dbg::fx_sizes_kernel<<<lane_grid, dbg::FX_LANE_THREADS, 0, s>>>(b);
-    dbg::fx_chain_kernel<<<std::min<uint32_t>((n + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 8),
-                           dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
+    {
+        ProfScope prof(ctx, s, DBG_PROF_FX_SIZES);
+        dbg::fx_assign_kernel<<<sb, 128, 0, s>>>(b);
+        dbg::fx_fill_kernel<<<n, 128, 0, s>>>(b);
+        dbg::fx_head_kernel<<<warp_grid, dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
+        dbg::fx_sizes_kernel<<<lane_grid, dbg::FX_LANE_THREADS, 0, s>>>(b);
+        dbg::fx_chain_kernel<<<std::min<uint32_t>((n + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 8),
+                               dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
+    }
     ctx->launches += 5;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::FxSummary), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (hs->cells_used) {
-        CU(ctx->d_cells.reserve((size_t)hs->cells_used * 2 + 256));
-        CU(ctx->d_fx_tok.reserve((size_t)hs->tok_used * 4 + 256));
-        b.cells = (uint16_t *)ctx->d_cells.p;
-        b.tok = (uint32_t *)ctx->d_fx_tok.p;
+        CU(sl.cells.reserve((size_t)hs->cells_used * 2 + 256));
+        CU(sl.fx_tok.reserve((size_t)hs->tok_used * 4 + 256));
+        b.cells = (uint16_t *)sl.cells.p;
+        b.tok = (uint32_t *)sl.fx_tok.p;
+        ProfScope prof(ctx, s, DBG_PROF_FX_EXPAND);
         dbg::fx_tokens_kernel<<<lane_grid, dbg::FX_LANE_THREADS, 0, s>>>(b);
         dbg::fx_expand_kernel<<<std::min<uint32_t>((NG + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 12),
                                 dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
@@ -432,21 +490,29 @@ static int run_fx(dbg_ctx *ctx, const dbg::InflateBatch &a, cudaStream_t s, cons
     return DBG_OK;
 }
 
-static int launch_inflate_plain(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot, bool may_order = true);
+// Joins the auxiliary stream into `s` when run_bsplit leaves early: the kernel forked onto it reads the caller's
+// buffers and the slot's work queue, so nothing the caller enqueues next may overtake it.
+struct AuxJoin {
+    dbg_ctx *ctx;
+    cudaStream_t s;
+    bool armed = false;
+    ~AuxJoin()
+    {
+        if (armed) cudaStreamWaitEvent(s, ctx->aux_join, 0);
+    }
+};
 
-// When streams do take this path, the warp-per-stream kernel for all the others is launched from here, on an
-// auxiliary stream, as soon as the classification is known: it is bound by the latency of its longest streams
-// and leaves most SM slots free, which the (throughput-bound) block-split kernels then fill. *regular_done
-// tells the caller that this has happened.
-static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, const uint32_t *taken,
-                      bool *regular_done)
+// Block-split path (bsplit_kernels.cuh): long multi-block streams. When streams do take this path, the warp-per-stream
+// kernel for all the others is launched from here, on an auxiliary stream, as soon as the classification is known: it
+// is bound by the latency of its longest streams and leaves most SM slots free, which the (throughput-bound)
+// block-split kernels then fill. *regular_done tells the caller that this has happened.
+static int run_bsplit(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t s, const uint32_t *taken, bool *regular_done)
 {
     *regular_done = false;
     const uint32_t n = a.n;
-    Buf &bs = ctx->d_bs_stream[slot], &br = ctx->d_bs_region[slot], &bc = ctx->d_bs_cells[slot], &hsb = ctx->h_bs_summary[slot];
-    CU(hsb.reserve(sizeof(dbg::BsSummary)));
-    CU(bs.reserve(256 + (size_t)n * (8 + 8 + 4 + 4 + 4 + 4) + 256));
-    uint8_t *p = (uint8_t *)bs.p;
+    CU(sl.h_bs.reserve(sizeof(dbg::BsSummary)));
+    CU(sl.bs_stream.reserve(256 + (size_t)n * (8 + 8 + 4 + 4 + 4 + 4) + 256));
+    uint8_t *p = (uint8_t *)sl.bs_stream.p;
     dbg::BsBatch b{};
     b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
     b.out_base = a.out_base; b.out_off = a.out_off; b.out_cap = a.out_cap;
@@ -467,20 +533,23 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     dbg::bs_classify_kernel<<<sb, 128, 0, s>>>(b);
     ctx->launches += 2;
     CU(cudaGetLastError());
-    dbg::BsSummary *hs = (dbg::BsSummary *)hsb.p;
+    dbg::BsSummary *hs = (dbg::BsSummary *)sl.h_bs.p;
     CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::BsSummary), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (hs->n_split == 0) return DBG_OK;
     // fork: everything that is not split, on the auxiliary stream
     a.skip = taken;
     a.skip2 = b.flag;
+    AuxJoin join{ctx, s};
     CU(cudaEventRecord(ctx->aux_fork, s));
     CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
     {
-        int rc = launch_inflate_plain(ctx, a, d_counter, ctx->aux_stream, slot);
+        int rc = launch_inflate_plain(ctx, sl, a, 0, ctx->aux_stream);
+        cudaError_t er = cudaEventRecord(ctx->aux_join, ctx->aux_stream);
+        join.armed = er == cudaSuccess;
         if (rc) return rc;
+        CU(er);
     }
-    CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
     *regular_done = true;
     // region size: 64 KiB when that already gives every resident warp a few regions, else smaller (more, shorter
     // chunks: the latency of a lone long stream is the decode time of its longest chunk)
@@ -488,9 +557,9 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     while (region > ctx->bsplit_region_min && hs->split_in / region < 4ull * b.resident_warps) region >>= 1;
     b.region_bytes = region;
     const uint32_t T = (uint32_t)(hs->split_in / region) + hs->n_split;  // upper bound of the region count
-    CU(br.reserve((size_t)T * (4 + 8 + 8 + 8 + 4 + 4 + 4) + 256));
-    CU(cudaMemsetAsync(br.p, 0, (size_t)T * (4 + 8 + 8 + 8 + 4 + 4 + 4), s));
-    b.cand = (uint64_t *)br.p;
+    CU(sl.bs_region.reserve((size_t)T * (4 + 8 + 8 + 8 + 4 + 4 + 4) + 256));
+    CU(cudaMemsetAsync(sl.bs_region.p, 0, (size_t)T * (4 + 8 + 8 + 8 + 4 + 4 + 4), s));
+    b.cand = (uint64_t *)sl.bs_region.p;
     b.exit_bits = b.cand + T;
     b.c_out_off = b.exit_bits + T;
     b.chunk_stream = (uint32_t *)(b.c_out_off + T);
@@ -501,8 +570,8 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     uint32_t tpb = ctx->bsplit_tok_per_byte;
     while (tpb > 1 && (uint64_t)tpb * 4 * hs->split_in > ctx->bsplit_tok_max_bytes) tpb >>= 1;
     if (tpb && (uint64_t)tpb * 4 * hs->split_in <= ctx->bsplit_tok_max_bytes) {
-        if (ctx->d_bs_tok[slot].reserve((size_t)tpb * 4 * hs->split_in + 256) == cudaSuccess) {
-            b.tok = (uint32_t *)ctx->d_bs_tok[slot].p;
+        if (sl.bs_tok.reserve((size_t)tpb * 4 * hs->split_in + 256) == cudaSuccess) {
+            b.tok = (uint32_t *)sl.bs_tok.p;
             b.tok_per_byte = tpb;
         } else {
             (void)cudaGetLastError();  // no room for tokens: the second pass decodes the Huffman codes again
@@ -526,10 +595,10 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
     ctx->bs_streams += hs->n_split - hs->n_pruned - hs->n_fallback;
     ctx->bs_fallbacks += hs->n_fallback;
     if (hs->cells_used) {
-        CU(bc.reserve((size_t)hs->cells_used * 2 + 256));
-        b.cells = (uint16_t *)bc.p;
+        CU(sl.bs_cells.reserve((size_t)hs->cells_used * 2 + 256));
+        b.cells = (uint16_t *)sl.bs_cells.p;
         dbg::bs_decode_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b);
-        // cells -> bytes with the split-stream path's resolve kernels
+        // cells -> bytes with the resolve kernels
         dbg::SplitBatch r{};
         r.out_base = a.out_base; r.out_off = a.out_off; r.out_size = a.out_size; r.status = a.status; r.n = n;
         r.split_flag = b.flag; r.redo = b.redo; r.chunk_base = b.chunk_base; r.nchunks = b.nchunks; r.cell_base = b.cell_base;
@@ -547,22 +616,24 @@ static int run_bsplit(dbg_ctx *ctx, int slot, dbg::InflateBatch a, uint32_t *d_c
         again.skip2 = nullptr;
         again.only = b.redo;
         again.order = nullptr;  // and no device-made order either: the first pass may still be reading that buffer
-        int rc = launch_inflate_plain(ctx, again, d_counter + 1, s, slot, false);
+        int rc = launch_inflate_plain(ctx, sl, again, 1, s, false);
         if (rc) return rc;
     }
-    CU(cudaStreamWaitEvent(s, ctx->aux_join, 0));  // join
-    return DBG_OK;
+    return DBG_OK;  // ~AuxJoin makes `s` wait for the auxiliary stream
 }
 
-static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter, cudaStream_t s, int slot = 0)
+// All decode paths for one batch of raw DEFLATE streams. `intra` = the paths that cut long streams into pieces may
+// be used (they synchronise the host with `s`).
+static int launch_inflate(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t s, bool intra_fx, bool intra_bs)
 {
+    CU(sl.counter.reserve(8 * sizeof(uint32_t)));
     a.skip = nullptr;
     a.skip2 = nullptr;
     const uint32_t *fx_redo = nullptr;
     uint32_t n_redo = 0;
-    if (ctx->fx && slot == 0 && ctx->bsplit_allowed) {  // (the scratch of this path is per context: single-wave calls only)
+    if (ctx->fx && intra_fx) {
         const uint32_t *skip = nullptr;
-        int rc = run_fx(ctx, a, s, &skip, &fx_redo, &n_redo);
+        int rc = run_fx(ctx, sl, a, s, &skip, &fx_redo, &n_redo);
         if (rc) return rc;
         a.skip = skip;
     }
@@ -573,31 +644,33 @@ static int launch_inflate(dbg_ctx *ctx, dbg::InflateBatch a, uint32_t *d_counter
         again.skip = nullptr;
         again.only = fx_redo;
         again.order = nullptr;
-        int rc = launch_inflate_plain(ctx, again, d_counter + 2, s, slot, false);
+        int rc = launch_inflate_plain(ctx, sl, again, 2, s, false);
         if (rc) return rc;
     }
-    if (ctx->bsplit && ctx->bsplit_allowed) {
+    if (ctx->bsplit && intra_bs) {
         bool done = false;
-        int rc = run_bsplit(ctx, slot, a, d_counter, s, a.skip, &done);
+        int rc = run_bsplit(ctx, sl, a, s, a.skip, &done);
         if (rc || done) return rc;
     }
-    return launch_inflate_plain(ctx, a, d_counter, s, slot);
+    return launch_inflate_plain(ctx, sl, a, 0, s);
 }
 
-static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+// Raw deflate (gz == false) or gzip members (gz == true) of one slot.
+static int inflate_device_slot(dbg_ctx *ctx, Slot &sl, bool gz, bool intra, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                                const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
                                const uint64_t *d_out_cap, uint64_t *d_out_size, uint32_t *d_status,
-                               const uint32_t *d_order, cudaStream_t s, uint64_t *gz_off, uint64_t *gz_size,
-                               uint32_t *gz_pre)
+                               const uint32_t *d_order, cudaStream_t s)
 {
-    CU(ctx->d_counter.reserve(8 * dbg_ctx::MAX_WAVES * sizeof(uint32_t)));
-    uint32_t *counter = (uint32_t *)ctx->d_counter.p + 8 * slot;
-    if (gz_off) {
+    if (gz) {
+        CU(sl.meta.reserve(n * 20 + 64));
+        uint64_t *gz_off = (uint64_t *)sl.meta.p;
+        uint64_t *gz_size = gz_off + n;
+        uint32_t *gz_pre = (uint32_t *)(gz_size + n);
         dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, gz_off, gz_size, gz_pre);
         ctx->launches++;
         CU(cudaGetLastError());
         dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
-        int rc = launch_inflate(ctx, a, counter, s, slot);
+        int rc = launch_inflate(ctx, sl, a, s, intra, intra);
         if (rc || !ctx->verify) return rc;
         uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
         dbg::gz_verify_kernel<<<ctas, dbg::SCAN_WARPS * 32, 0, s>>>(d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_size, d_status,
@@ -607,8 +680,55 @@ static int inflate_device_slot(dbg_ctx *ctx, int slot, uint64_t n, const uint8_t
         return DBG_OK;
     }
     dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
-    return launch_inflate(ctx, a, counter, s, slot);
+    return launch_inflate(ctx, sl, a, s, intra, intra);
 }
+
+static int png_device_slot(dbg_ctx *ctx, Slot &sl, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                           const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_out_cap,
+                           uint32_t *d_status, uint64_t total_in_bytes, uint64_t total_rgba_bytes, cudaStream_t s)
+{
+    CU(sl.png_scratch.reserve(dbg::png_scratch_bytes(n, total_in_bytes, total_rgba_bytes)));
+    dbg::PngLayout lay = dbg::png_layout((uint8_t *)sl.png_scratch.p, n, total_in_bytes, total_rgba_bytes);
+    // 1. container walk + CRC-32 + IDAT gather (one warp per image)
+    dbg::PngBatch pb{d_in, d_in_off, d_in_size, d_out_cap, (uint32_t)n, lay};
+    int rc;
+    {
+        ProfScope prof(ctx, s, DBG_PROF_PNG_SCAN);
+        rc = dbg::png_launch_scan(pb, ctx->sm_count, s);
+    }
+    ctx->launches += 4;
+    if (rc) CU((cudaError_t)rc);
+    // 2. inflate the zlib payloads into the filtered-scanline buffers
+    // z_off holds absolute addresses: a single-IDAT image is inflated straight from the file
+    dbg::InflateBatch a{nullptr, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
+                        lay.pre_status, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t)n};
+    rc = launch_inflate(ctx, sl, a, s, true, true);
+    if (rc) return rc;
+    if (ctx->verify) {
+        uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
+        dbg::png_adler_kernel<<<ctas, dbg::SCAN_WARPS * 32, 0, s>>>(pb);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    // 3. un-filter (+ palette / RGB expansion) straight into the caller's RGBA
+    {
+        ProfScope prof(ctx, s, DBG_PROF_PNG_UNFILTER);
+        rc = dbg::png_launch_unfilter(pb, d_out, d_out_off, d_status, ctx->sm_count, s);
+    }
+    ctx->launches += 2;
+    if (rc) CU((cudaError_t)rc);
+    return DBG_OK;
+}
+
+// The device-resident entry points share slot 0. A call on another stream than the previous one must not touch that
+// scratch while the previous call's kernels still use it: every call waits (on the device) for the event the
+// previous one left behind, and leaves its own -- also when it fails half way.
+struct SlotGuard {
+    Slot &sl;
+    cudaStream_t s;
+    SlotGuard(Slot &slot, cudaStream_t st) : sl(slot), s(st) { cudaStreamWaitEvent(s, sl.done, 0); }
+    ~SlotGuard() { cudaEventRecord(sl.done, s); }
+};
 
 extern "C" int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                                         const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off,
@@ -622,11 +742,11 @@ extern "C" int dbg_inflate_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t 
         set_err(ctx, "dbg_inflate_batch_device: bad arguments");
         return DBG_ERR_ARG;
     }
-    ctx->bsplit_allowed = true;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    return inflate_device_slot(ctx, 0, n, d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, d_order,
-                               s, nullptr, nullptr, nullptr);
+    SlotGuard guard(ctx->slot[0], s);
+    return inflate_device_slot(ctx, ctx->slot[0], false, true, n, d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size,
+                               d_status, d_order, s);
 }
 
 extern "C" int dbg_decode_gz_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -641,15 +761,11 @@ extern "C" int dbg_decode_gz_batch_device(dbg_ctx *ctx, uint64_t n, const uint8_
         set_err(ctx, "dbg_decode_gz_batch_device: bad arguments");
         return DBG_ERR_ARG;
     }
-    ctx->bsplit_allowed = true;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    CU(ctx->d_meta.reserve(n * 20 + 64));
-    uint64_t *p_off = (uint64_t *)ctx->d_meta.p;
-    uint64_t *p_size = p_off + n;
-    uint32_t *pre = (uint32_t *)(p_size + n);
-    return inflate_device_slot(ctx, 0, n, d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, d_order,
-                               s, p_off, p_size, pre);
+    SlotGuard guard(ctx->slot[0], s);
+    return inflate_device_slot(ctx, ctx->slot[0], true, true, n, d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size,
+                               d_status, d_order, s);
 }
 
 extern "C" uint64_t dbg_png_scratch_bytes(uint64_t n, uint64_t total_in_bytes, uint64_t total_rgba_bytes)
@@ -670,32 +786,9 @@ extern "C" int dbg_decode_png_batch_device(dbg_ctx *ctx, uint64_t n, const uint8
     }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    CU(ctx->d_counter.reserve(8 * dbg_ctx::MAX_WAVES * sizeof(uint32_t)));
-    CU(ctx->d_png_scratch.reserve(dbg::png_scratch_bytes(n, total_in_bytes, total_rgba_bytes)));
-    dbg::PngLayout lay = dbg::png_layout((uint8_t *)ctx->d_png_scratch.p, n, total_in_bytes, total_rgba_bytes);
-
-    // 1. container walk + CRC-32 + IDAT gather (one warp per image)
-    dbg::PngBatch pb{d_in, d_in_off, d_in_size, d_out_cap, (uint32_t)n, lay};
-    int rc = dbg::png_launch_scan(pb, ctx->sm_count, s);
-    ctx->launches += 4;
-    if (rc) CU((cudaError_t)rc);
-    // 2. inflate the compacted zlib payloads into the filtered-scanline buffers
-    // z_off holds absolute addresses: a single-IDAT image is inflated straight from the file
-    dbg::InflateBatch a{nullptr, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
-                        lay.pre_status, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t)n};
-    rc = launch_inflate(ctx, a, (uint32_t *)ctx->d_counter.p, s);
-    if (rc) return rc;
-    if (ctx->verify) {
-        uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
-        dbg::png_adler_kernel<<<ctas, dbg::SCAN_WARPS * 32, 0, s>>>(pb);
-        ctx->launches++;
-        CU(cudaGetLastError());
-    }
-    // 3. un-filter (+ palette / RGB expansion) straight into the caller's RGBA
-    rc = dbg::png_launch_unfilter(pb, d_out, d_out_off, d_status, ctx->sm_count, s);
-    ctx->launches += 2;
-    if (rc) CU((cudaError_t)rc);
-    return DBG_OK;
+    SlotGuard guard(ctx->slot[0], s);
+    return png_device_slot(ctx, ctx->slot[0], n, d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_status, total_in_bytes,
+                           total_rgba_bytes, s);
 }
 
 // -------------------------------------------------------------- host batches --
@@ -718,6 +811,203 @@ static inline uint64_t sched_weight(int kind, const uint8_t *p, uint64_t size)
     return ((p[at] >> 1) & 3) == 0 ? size / 64 : size;
 }
 
+// The packed path proper. `cuts` are the wave boundaries (item indices, cuts.front() == 0, cuts.back() == n); the
+// items of a wave must lie in index order, without overlap, in both host arenas (one upload and one download per
+// wave). The waves are packed next to each other in the context's device arenas, wherever they lie on the host, so
+// a caller may pass any sub-set of a large arena (the multi-device entry point does). `intra` = the intra-stream
+// paths may be used (gzip / deflate; PNG waves always use them).
+static int packed_waves(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off, const uint64_t *in_size,
+                        uint8_t *h_out, const uint64_t *out_off, const uint64_t *out_cap, uint64_t *out_size, uint32_t *status,
+                        const std::vector<uint64_t> &cuts, bool intra)
+{
+    const int nw = (int)cuts.size() - 1;
+    cudaStream_t s = ctx->stream;
+    // descriptor block: in_off, in_size, out_off, out_cap, out_size (u64 x n each), status + order (u32 x n each)
+    const size_t desc_bytes = n * (5 * 8 + 2 * 4);
+    CU(ctx->h_desc.reserve(desc_bytes));
+    CU(ctx->d_desc.reserve(desc_bytes));
+    uint64_t *hd = (uint64_t *)ctx->h_desc.p;
+    uint32_t *h_status = (uint32_t *)(hd + 5 * n);
+    uint32_t *h_order = h_status + n;
+    uint64_t *dd = (uint64_t *)ctx->d_desc.p;
+    uint32_t *d_status = (uint32_t *)(dd + 5 * n);
+    uint32_t *d_order = d_status + n;
+    // device placement of the waves + device-side offsets of the items
+    struct Wave { uint64_t b, e, hi0, hi1, ho0, ho1, di, dout, tot_in, tot_out; };
+    std::vector<Wave> wv(nw);
+    uint64_t din = 0, dout = 0;
+    for (int k = 0; k < nw; k++) {
+        Wave &w = wv[k];
+        w.b = cuts[k];
+        w.e = cuts[k + 1];
+        w.hi0 = in_off[w.b] & ~(uint64_t)15;  // keep every item's address modulo 16
+        w.hi1 = in_off[w.e - 1] + in_size[w.e - 1];
+        w.ho0 = out_off[w.b] & ~(uint64_t)15;
+        w.ho1 = out_off[w.e - 1] + out_cap[w.e - 1];
+        w.di = din;
+        w.dout = dout;
+        w.tot_in = w.tot_out = 0;
+        din += align_up(w.hi1 - w.hi0 + 64, 256);
+        dout += align_up(w.ho1 - w.ho0 + 64, 256);
+        for (uint64_t i = w.b; i < w.e; i++) {
+            hd[i] = in_off[i] - w.hi0 + w.di;
+            hd[n + i] = in_size[i];
+            hd[2 * n + i] = out_off[i] - w.ho0 + w.dout;
+            hd[3 * n + i] = out_cap[i];
+            w.tot_in += in_size[i];
+            w.tot_out += out_cap[i];
+        }
+        // per-wave largest-first order (indices relative to the wave)
+        uint32_t *o = h_order + w.b;
+        const uint64_t m = w.e - w.b;
+        std::vector<uint64_t> wt(m);
+        for (uint64_t i = 0; i < m; i++) wt[i] = sched_weight(kind, h_in + in_off[w.b + i], in_size[w.b + i]) + out_cap[w.b + i] / 32;
+        std::iota(o, o + m, 0u);
+        std::stable_sort(o, o + m, [&](uint32_t x, uint32_t y) { return wt[x] > wt[y]; });
+    }
+    CU(ctx->d_in.reserve(din + 64));
+    CU(ctx->d_out.reserve(dout + 64));
+    uint8_t *d_in = (uint8_t *)ctx->d_in.p, *d_out = (uint8_t *)ctx->d_out.p;
+    CU(cudaMemcpyAsync(dd, hd, 4 * n * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(ctx->wave_ready, s));
+    const bool trace = getenv("DBG_WAVE_TRACE") != nullptr;  // debugging aid: per-wave timeline on stderr
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(3 * nw + 1);
+        for (auto &e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[3 * nw], s);
+    }
+    // Issued breadth-first (all uploads, then all kernels, then all downloads): the streams share a limited
+    // number of hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and with wave-by-wave issue the
+    // upload of wave k+8 sits behind the download of wave k, i.e. behind wave k's kernels (measured with
+    // DBG_WAVE_TRACE: the second half of the waves did not start before the first half had finished).
+    int rc = DBG_OK;
+    for (int k = 0; k < nw && rc == DBG_OK; k++) {
+        const Wave &w = wv[k];
+        Slot &sl = ctx->slot[k];
+        cudaStream_t ws = sl.stream;
+        cudaError_t e = cudaStreamWaitEvent(ws, ctx->wave_ready, 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ws, sl.done, 0);  // a device-resident call may still be using this slot's scratch
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + w.di, h_in + w.hi0, w.hi1 - w.hi0, cudaMemcpyHostToDevice, ws);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_in + w.di + (w.hi1 - w.hi0), 0, 64, ws);  // what readers see behind the last item
+        if (e != cudaSuccess) {
+            set_err(ctx, "packed batch, upload of wave %d: %s", k, cudaGetErrorString(e));
+            rc = DBG_ERR_CUDA;
+        }
+        if (trace) cudaEventRecord(tev[3 * k], ws);
+    }
+    for (int k = 0; k < nw && rc == DBG_OK; k++) {
+        const Wave &w = wv[k];
+        Slot &sl = ctx->slot[k];
+        const uint64_t b = w.b, m = w.e - w.b;
+        if (kind == 2)
+            rc = png_device_slot(ctx, sl, m, d_in, dd + b, dd + n + b, d_out, dd + 2 * n + b, dd + 3 * n + b, d_status + b, w.tot_in,
+                                 w.tot_out, sl.stream);
+        else
+            rc = inflate_device_slot(ctx, sl, kind == 1, intra, m, d_in, dd + b, dd + n + b, d_out, dd + 2 * n + b, dd + 3 * n + b,
+                                     dd + 4 * n + b, d_status + b, d_order + b, sl.stream);
+        if (trace) cudaEventRecord(tev[3 * k + 1], sl.stream);
+        // PNG waves synchronise the host (lane-serial path), so their downloads are issued wave by wave: the download
+        // of wave k then overlaps the kernels of wave k + 1
+        if (kind == 2 && rc == DBG_OK) {
+            if (cudaMemcpyAsync(h_out + w.ho0, d_out + w.dout, w.ho1 - w.ho0, cudaMemcpyDeviceToHost, sl.stream) != cudaSuccess) rc = DBG_ERR_CUDA;
+            if (trace) cudaEventRecord(tev[3 * k + 2], sl.stream);
+        }
+    }
+    if (kind != 2)
+        for (int k = 0; k < nw && rc == DBG_OK; k++) {
+            const Wave &w = wv[k];
+            if (cudaMemcpyAsync(h_out + w.ho0, d_out + w.dout, w.ho1 - w.ho0, cudaMemcpyDeviceToHost, ctx->slot[k].stream) != cudaSuccess)
+                rc = DBG_ERR_CUDA;
+            if (trace) cudaEventRecord(tev[3 * k + 2], ctx->slot[k].stream);
+        }
+    // also on failure: nothing of this call may still be running when it returns
+    for (int k = 0; k < nw; k++) {
+        cudaEventRecord(ctx->slot[k].done, ctx->slot[k].stream);
+        if (cudaStreamSynchronize(ctx->slot[k].stream) != cudaSuccess && rc == DBG_OK) rc = DBG_ERR_CUDA;
+    }
+    if (rc == DBG_ERR_CUDA && !ctx->err[0]) set_err(ctx, "packed batch: %s", cudaGetErrorString(cudaGetLastError()));
+    if (trace) {
+        for (int k = 0; k < nw; k++) {
+            float a = 0, b2 = 0, c = 0;
+            cudaEventElapsedTime(&a, tev[3 * nw], tev[3 * k]);
+            cudaEventElapsedTime(&b2, tev[3 * nw], tev[3 * k + 1]);
+            cudaEventElapsedTime(&c, tev[3 * nw], tev[3 * k + 2]);
+            fprintf(stderr, "wave %2d: h2d done %7.2f ms, kernels done %7.2f ms, d2h done %7.2f ms\n", k, a, b2, c);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hd + 4 * n, dd + 4 * n, n * 8 + n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(status, h_status, n * 4);
+    if (kind == 2) {
+        for (uint64_t i = 0; i < n; i++) out_size[i] = status[i] == 0 ? out_cap[i] : 0;
+    } else {
+        memcpy(out_size, hd + 4 * n, n * 8);
+    }
+    return DBG_OK;
+}
+
+// One item, or a handful: the download waits for the sizes and moves only what was produced (the reference's
+// decode_gz() sizes its buffer at 35 x the input, decode_gz.c:245-247; copying that back would dominate the call).
+static int packed_small(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off, const uint64_t *in_size,
+                        uint8_t *h_out, const uint64_t *out_off, const uint64_t *out_cap, uint64_t *out_size, uint32_t *status)
+{
+    cudaStream_t s = ctx->stream;
+    Slot &sl = ctx->slot[0];
+    const size_t desc_bytes = n * (5 * 8 + 2 * 4);
+    CU(ctx->h_desc.reserve(desc_bytes));
+    CU(ctx->d_desc.reserve(desc_bytes));
+    uint64_t *hd = (uint64_t *)ctx->h_desc.p, *dd = (uint64_t *)ctx->d_desc.p;
+    uint32_t *h_status = (uint32_t *)(hd + 5 * n), *d_status = (uint32_t *)(dd + 5 * n);
+    uint64_t din = 0, dout = 0, tot_in = 0, tot_out = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        hd[i] = din + (in_off[i] & 15);
+        hd[n + i] = in_size[i];
+        hd[2 * n + i] = dout;
+        hd[3 * n + i] = out_cap[i];
+        din += align_up((in_off[i] & 15) + in_size[i] + 64, 256);
+        dout += align_up(out_cap[i] + 64, 256);
+        tot_in += in_size[i];
+        tot_out += out_cap[i];
+    }
+    CU(ctx->d_in.reserve(din + 64));
+    CU(ctx->d_out.reserve(dout + 64));
+    uint8_t *d_in = (uint8_t *)ctx->d_in.p, *d_out = (uint8_t *)ctx->d_out.p;
+    SlotGuard guard(sl, s);
+    CU(cudaMemcpyAsync(dd, hd, 4 * n * 8, cudaMemcpyHostToDevice, s));
+    for (uint64_t i = 0; i < n; i++) {
+        CU(cudaMemcpyAsync(d_in + hd[i], h_in + in_off[i], in_size[i], cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(d_in + hd[i] + in_size[i], 0, 64, s));
+    }
+    int rc;
+    if (kind == 2)
+        rc = png_device_slot(ctx, sl, n, d_in, dd, dd + n, d_out, dd + 2 * n, dd + 3 * n, d_status, tot_in, tot_out, s);
+    else
+        rc = inflate_device_slot(ctx, sl, kind == 1, true, n, d_in, dd, dd + n, d_out, dd + 2 * n, dd + 3 * n, dd + 4 * n, d_status,
+                                 nullptr, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hd + 4 * n, dd + 4 * n, n * 8 + n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (uint64_t i = 0; i < n; i++) {
+        status[i] = h_status[i];
+        out_size[i] = kind == 2 ? (status[i] == 0 ? out_cap[i] : 0) : hd[4 * n + i];
+        if (status[i] == 0 && out_size[i])
+            CU(cudaMemcpyAsync(h_out + out_off[i], d_out + hd[2 * n + i], std::min(out_size[i], out_cap[i]), cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    return DBG_OK;
+}
+
+static bool items_in_order(uint64_t n, const uint64_t *in_off, const uint64_t *in_size, const uint64_t *out_off, const uint64_t *out_cap)
+{
+    for (uint64_t i = 1; i < n; i++)
+        if (in_off[i] < in_off[i - 1] + in_size[i - 1] || out_off[i] < out_off[i - 1] + out_cap[i - 1]) return false;
+    return true;
+}
+
 extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
                                        const uint64_t *in_size, uint8_t *h_out, const uint64_t *out_off,
                                        const uint64_t *out_cap, uint64_t *out_size, uint32_t *status)
@@ -730,141 +1020,89 @@ extern "C" int dbg_decode_batch_packed(dbg_ctx *ctx, int kind, uint64_t n, const
         return DBG_ERR_ARG;
     }
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    uint64_t in_span = 0, out_span = 0, tot_in = 0, tot_out = 0;
-    for (uint64_t i = 0; i < n; i++) {
-        in_span = std::max(in_span, in_off[i] + in_size[i]);
-        out_span = std::max(out_span, out_off[i] + out_cap[i]);
-        tot_in += in_size[i];
-        tot_out += out_cap[i];
-    }
-    // descriptor block: in_off, in_size, out_off, out_cap, out_size (u64 x n each), status + order (u32 x n each)
-    size_t desc_bytes = n * (5 * 8 + 2 * 4);
-    CU(ctx->h_desc.reserve(desc_bytes));
-    CU(ctx->d_desc.reserve(desc_bytes));
-    CU(ctx->d_in.reserve(in_span + 64));
-    CU(ctx->d_out.reserve(out_span + 64));
-    uint64_t *hd = (uint64_t *)ctx->h_desc.p;
-    memcpy(hd, in_off, n * 8);
-    memcpy(hd + n, in_size, n * 8);
-    memcpy(hd + 2 * n, out_off, n * 8);
-    memcpy(hd + 3 * n, out_cap, n * 8);
-    uint32_t *h_status = (uint32_t *)(hd + 5 * n);
-    uint32_t *h_order = h_status + n;
-    uint64_t *dd = (uint64_t *)ctx->d_desc.p;
-    uint32_t *d_status = (uint32_t *)(dd + 5 * n);
-    uint32_t *d_order = d_status + n;
-    // ---- waves: when the items sit in index order in both arenas, the batch is cut into up to
-    // MAX_WAVES contiguous waves, each on its own stream (H2D -> kernels -> D2H), so the copy
-    // engines and the SMs overlap. Otherwise (or for PNG, whose scratch is per batch) one wave.
-    bool mono = kind != 2;
-    for (uint64_t i = 1; i < n && mono; i++)
-        mono = in_off[i] >= in_off[i - 1] + in_size[i - 1] && out_off[i] >= out_off[i - 1] + out_cap[i - 1];
-    int nw = mono ? (int)std::min<uint64_t>(ctx->waves, std::max<uint64_t>(1, n / 256)) : 1;
-    if (n < ctx->split_max_streams) nw = 1;  // small batches may take the split-stream path, which owns per-context scratch
-    if (nw > 1 && ctx->bsplit) {
-        // a batch with streams long enough for the block-split path (same rule as bs_classify_kernel) runs
-        // as one wave: that path synchronises the host twice, which would serialise concurrent waves
-        const uint64_t resident = (uint64_t)ctx->sm_count * ctx->inflate_ctas_per_sm * dbg::INFLATE_WARPS_PER_CTA;
-        const uint64_t thr = std::max<uint64_t>(ctx->bsplit_min_bytes, tot_in / resident * ctx->bsplit_factor_q / 4);
-        for (uint64_t i = 0; i < n && nw > 1; i++)
-            if (in_size[i] >= thr) nw = 1;
-    }
-    ctx->bsplit_allowed = nw == 1;
-    CU(cudaMemcpyAsync(dd, hd, 4 * n * 8, cudaMemcpyHostToDevice, s));
-    if (kind == 1) CU(ctx->d_meta.reserve(n * 20 + 64));
-    uint64_t *gz_off = kind == 1 ? (uint64_t *)ctx->d_meta.p : nullptr;
-    uint64_t *gz_size = gz_off ? gz_off + n : nullptr;
-    uint32_t *gz_pre = gz_off ? (uint32_t *)(gz_size + n) : nullptr;
-    if (nw == 1) {
-        std::vector<uint64_t> wt(n);
-        for (uint64_t i = 0; i < n; i++) wt[i] = sched_weight(kind, h_in + in_off[i], in_size[i]) + out_cap[i] / 32;
-        std::iota(h_order, h_order + n, 0u);
-        std::stable_sort(h_order, h_order + n, [&](uint32_t a, uint32_t b) { return wt[a] > wt[b]; });
-        CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(ctx->d_in.p, h_in, in_span, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
-        int rc;
-        if (kind == 2)
-            rc = dbg_decode_png_batch_device(ctx, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p,
-                                             dd + 2 * n, dd + 3 * n, d_status, tot_in, tot_out, s);
-        else
-            rc = inflate_device_slot(ctx, 0, n, (const uint8_t *)ctx->d_in.p, dd, dd + n, (uint8_t *)ctx->d_out.p, dd + 2 * n,
-                                     dd + 3 * n, dd + 4 * n, d_status, d_order, s, gz_off, gz_size, gz_pre);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(h_out, ctx->d_out.p, out_span, cudaMemcpyDeviceToHost, s));
-    } else {
-        // per-wave largest-first order (indices relative to the wave)
-        std::vector<uint64_t> cut(nw + 1);
-        for (int k = 0; k <= nw; k++) cut[k] = n * (uint64_t)k / nw;
-        for (int k = 0; k < nw; k++) {
-            uint32_t *o = h_order + cut[k];
-            uint64_t m = cut[k + 1] - cut[k], b = cut[k];
-            std::vector<uint64_t> wt(m);
-            for (uint64_t i = 0; i < m; i++) wt[i] = sched_weight(kind, h_in + in_off[b + i], in_size[b + i]) + out_cap[b + i] / 32;
-            std::iota(o, o + m, 0u);
-            std::stable_sort(o, o + m, [&](uint32_t x, uint32_t y) { return wt[x] > wt[y]; });
-        }
-        CU(cudaMemcpyAsync(d_order, h_order, n * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_span, 0, 64, s));
-        CU(cudaEventRecord(ctx->wave_ready, s));
-        const bool trace = getenv("DBG_WAVE_TRACE") != nullptr;  // debugging aid: per-wave timeline on stderr
-        std::vector<cudaEvent_t> tev;
-        if (trace) {
-            tev.resize(3 * nw + 1);
-            for (auto &e : tev) cudaEventCreate(&e);
-            cudaEventRecord(tev[3 * nw], s);
-        }
-        // Issued breadth-first (all uploads, then all kernels, then all downloads): the streams share a limited
-        // number of hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and with wave-by-wave issue the
-        // upload of wave k+8 sits behind the download of wave k, i.e. behind wave k's kernels (measured with
-        // DBG_WAVE_TRACE: the second half of the waves did not start before the first half had finished).
-        for (int k = 0; k < nw; k++) {
-            cudaStream_t ws = ctx->wave_stream[k];
-            uint64_t b = cut[k], e = cut[k + 1];
-            uint64_t i0 = in_off[b], i1 = in_off[e - 1] + in_size[e - 1];
-            CU(cudaStreamWaitEvent(ws, ctx->wave_ready, 0));
-            CU(cudaMemcpyAsync((uint8_t *)ctx->d_in.p + i0, h_in + i0, i1 - i0, cudaMemcpyHostToDevice, ws));
-            if (trace) cudaEventRecord(tev[3 * k], ws);
-        }
-        for (int k = 0; k < nw; k++) {
-            cudaStream_t ws = ctx->wave_stream[k];
-            uint64_t b = cut[k], e = cut[k + 1], m = e - b;
-            int rc = inflate_device_slot(ctx, k, m, (const uint8_t *)ctx->d_in.p, dd + b, dd + n + b, (uint8_t *)ctx->d_out.p,
-                                         dd + 2 * n + b, dd + 3 * n + b, dd + 4 * n + b, d_status + b, d_order + b, ws,
-                                         gz_off ? gz_off + b : nullptr, gz_off ? gz_size + b : nullptr,
-                                         gz_off ? gz_pre + b : nullptr);
-            if (rc) return rc;
-            if (trace) cudaEventRecord(tev[3 * k + 1], ws);
-        }
-        for (int k = 0; k < nw; k++) {
-            cudaStream_t ws = ctx->wave_stream[k];
-            uint64_t b = cut[k], e = cut[k + 1];
-            uint64_t o0 = out_off[b], o1 = out_off[e - 1] + out_cap[e - 1];
-            CU(cudaMemcpyAsync(h_out + o0, (uint8_t *)ctx->d_out.p + o0, o1 - o0, cudaMemcpyDeviceToHost, ws));
-            if (trace) cudaEventRecord(tev[3 * k + 2], ws);
-        }
-        for (int k = 0; k < nw; k++) CU(cudaStreamSynchronize(ctx->wave_stream[k]));
-        if (trace) {
-            for (int k = 0; k < nw; k++) {
-                float a = 0, b2 = 0, c = 0;
-                cudaEventElapsedTime(&a, tev[3 * nw], tev[3 * k]);
-                cudaEventElapsedTime(&b2, tev[3 * nw], tev[3 * k + 1]);
-                cudaEventElapsedTime(&c, tev[3 * nw], tev[3 * k + 2]);
-                fprintf(stderr, "wave %2d: h2d done %7.2f ms, kernels done %7.2f ms, d2h done %7.2f ms\n", k, a, b2, c);
-            }
-            for (auto &e : tev) cudaEventDestroy(e);
-        }
-    }
-    ctx->bsplit_allowed = true;
-    CU(cudaMemcpyAsync(hd + 4 * n, dd + 4 * n, n * 8 + n * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    memcpy(status, h_status, n * 4);
+    ctx->err[0] = 0;
+    const bool mono = items_in_order(n, in_off, in_size, out_off, out_cap);
+    if (n <= 4 || !mono) return packed_small(ctx, kind, n, h_in, in_off, in_size, h_out, out_off, out_cap, out_size, status);
+    uint64_t tot_in = 0;
+    for (uint64_t i = 0; i < n; i++) tot_in += in_size[i];
+    // ---- waves: contiguous item ranges, each on its own stream and scratch slot (H2D -> kernels -> D2H), so that
+    // the copy engines and the SMs overlap
+    int nw;
+    bool intra = false;
     if (kind == 2) {
-        for (uint64_t i = 0; i < n; i++) out_size[i] = status[i] == 0 ? out_cap[i] : 0;
+        // PNG: a wave should still fill the GPU (>= 64 MB of files)
+        nw = (int)std::min<uint64_t>(std::min<uint64_t>(ctx->png_waves, n), std::max<uint64_t>(1, tot_in / (64ull << 20)));
     } else {
-        memcpy(out_size, hd + 4 * n, n * 8);
+        nw = (int)std::min<uint64_t>(ctx->waves, std::max<uint64_t>(1, n / 256));
+        if (n < ctx->small_batch) nw = 1;  // small batches: one wave, the intra-stream paths may take its long streams
+        if (nw > 1 && ctx->bsplit) {
+            // a batch with streams long enough for the block-split path (same rule as bs_classify_kernel) runs
+            // as one wave: that path synchronises the host twice, which would serialise concurrent waves
+            const uint64_t resident = (uint64_t)ctx->sm_count * ctx->inflate_ctas_per_sm * dbg::INFLATE_WARPS_PER_CTA;
+            const uint64_t thr = std::max<uint64_t>(ctx->bsplit_min_bytes, tot_in / resident * ctx->bsplit_factor_q / 4);
+            for (uint64_t i = 0; i < n && nw > 1; i++)
+                if (in_size[i] >= thr) nw = 1;
+        }
+        intra = nw == 1;
     }
+    std::vector<uint64_t> cuts(nw + 1);
+    if (kind == 2) {  // PNG waves of equal bytes (images of one batch may differ a lot in size)
+        cuts[0] = 0;
+        uint64_t acc = 0, i = 0;
+        for (int k = 1; k < nw; k++) {
+            const uint64_t want = tot_in * (uint64_t)k / nw;
+            while (i < n && acc < want) acc += in_size[i++];
+            cuts[k] = std::max<uint64_t>(i, cuts[k - 1] + 1);
+            if (cuts[k] > n - (uint64_t)(nw - k)) cuts[k] = n - (uint64_t)(nw - k);
+        }
+        cuts[nw] = n;
+    } else {
+        for (int k = 0; k <= nw; k++) cuts[k] = n * (uint64_t)k / nw;
+    }
+    return packed_waves(ctx, kind, n, h_in, in_off, in_size, h_out, out_off, out_cap, out_size, status, cuts, intra);
+}
+
+// One gzip member into memory obtained from the caller's allocator once its size is known (the drop-in decode_gz()
+// is built on this: the reference allocates 35 x the input up front, decode_gz.c:245-247). `cap` bounds the output.
+extern "C" int dbg_decode_gz_alloc(dbg_ctx *ctx, const uint8_t *in, uint64_t in_size, uint64_t cap, void *(*alloc)(size_t),
+                                   uint8_t **out, uint64_t *out_size, uint32_t *good)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (!in || !alloc || !out || !out_size || !good) return DBG_ERR_ARG;
+    *out = nullptr;
+    *out_size = 0;
+    *good = 0;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    Slot &sl = ctx->slot[0];
+    CU(ctx->h_desc.reserve(64));
+    CU(ctx->d_desc.reserve(64));
+    CU(ctx->d_in.reserve(in_size + 128));
+    CU(ctx->d_out.reserve(cap + 64));
+    uint64_t *hd = (uint64_t *)ctx->h_desc.p, *dd = (uint64_t *)ctx->d_desc.p;
+    hd[0] = 0; hd[1] = in_size; hd[2] = 0; hd[3] = cap; hd[4] = 0; hd[5] = 0;
+    {
+        SlotGuard guard(sl, s);
+        CU(cudaMemcpyAsync(dd, hd, 48, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(ctx->d_in.p, in, in_size, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync((uint8_t *)ctx->d_in.p + in_size, 0, 64, s));
+        int rc = inflate_device_slot(ctx, sl, true, true, 1, (const uint8_t *)ctx->d_in.p, dd, dd + 1, (uint8_t *)ctx->d_out.p, dd + 2,
+                                     dd + 3, dd + 4, (uint32_t *)(dd + 5), nullptr, s);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(hd + 4, dd + 4, 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    if (*(uint32_t *)(hd + 5) != 0) return DBG_OK;  // good = 0
+    const uint64_t sz = hd[4];
+    uint8_t *buf = (uint8_t *)alloc((size_t)(sz ? sz : 1));
+    if (!buf) return DBG_ERR_NOMEM;
+    if (sz) {
+        CU(cudaMemcpyAsync(buf, ctx->d_out.p, sz, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    *out = buf;
+    *out_size = sz;
+    *good = 1;
     return DBG_OK;
 }
 
@@ -883,19 +1121,35 @@ static int run_pointer_batch(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *
     std::vector<uint64_t> in_off(n), out_off(n), sizes(n);
     uint64_t ti = 0, to = 0;
     for (uint64_t i = 0; i < n; i++) {
+        if (in_size[i] && !in[i]) {
+            set_err(ctx, "batch call: item %llu has a NULL input", (unsigned long long)i);
+            return DBG_ERR_ARG;
+        }
         in_off[i] = ti;
         ti += align_up(in_size[i] + 16, 16);
         out_off[i] = to;
         to += align_up(out_cap[i], 16);
     }
+    if (n <= 4) {
+        // a call or two (the scalar drop-in API): no staging copy on the host -- the buffers are used where they are
+        // (pageable memory: the driver stages them), item by item
+        int rc = DBG_OK;
+        for (uint64_t i = 0; i < n && rc == DBG_OK; i++) {
+            const uint64_t zero = 0;
+            uint64_t osz = 0;
+            if (!out[i] && out_cap[i]) {
+                set_err(ctx, "batch call: item %llu has a NULL output", (unsigned long long)i);
+                return DBG_ERR_ARG;
+            }
+            rc = packed_small(ctx, kind, 1, in[i], &zero, &in_size[i], out[i], &zero, &out_cap[i], &osz, &status[i]);
+            if (out_size) out_size[i] = osz;
+        }
+        return rc;
+    }
     CU(ctx->h_in.reserve(ti + 64));
     CU(ctx->h_out.reserve(to + 64));
     uint8_t *hi = (uint8_t *)ctx->h_in.p;
     for (uint64_t i = 0; i < n; i++) {
-        if (in_size[i] && !in[i]) {
-            set_err(ctx, "batch call: item %llu has a NULL input", (unsigned long long)i);
-            return DBG_ERR_ARG;
-        }
         memcpy(hi + in_off[i], in[i], in_size[i]);
         memset(hi + in_off[i] + in_size[i], 0, align_up(in_size[i] + 16, 16) - in_size[i]);
     }
@@ -938,13 +1192,184 @@ extern "C" int dbg_decode_png_batch(dbg_ctx *ctx, uint64_t n, const uint8_t *con
     return rc;
 }
 
+// -------------------------------------------------------------- multi-device --
+// One batch over several GPUs of one box: the items are independent, so the batch is cut into runs
+// of consecutive items, the runs are dealt to the devices longest-processing-time first by estimated decode time,
+// and every device decodes its runs as waves of its own packed path, driven by one host thread per device. No
+// exchange step, no collective. The reference's only provision for concurrency is the thread_id slot
+// (inflate.c:22-23, decode_png.c:559-560).
+struct dbg_multi {
+    std::vector<dbg_ctx *> ctx;
+    char err[512] = "";
+};
+
+extern "C" void dbg_multi_destroy(dbg_multi *m)
+{
+    if (!m) return;
+    for (dbg_ctx *c : m->ctx) dbg_destroy(c);
+    delete m;
+}
+
+extern "C" dbg_multi *dbg_multi_create(int n_devices, const int *device_ids)
+{
+    const int have = dbg_device_count();
+    if (have <= 0) {
+        if (have == 0) set_err(nullptr, "no CUDA device visible -- this library has no CPU path");
+        return nullptr;
+    }
+    if (n_devices <= 0) n_devices = have;
+    dbg_multi *m = new dbg_multi();
+    for (int k = 0; k < n_devices; k++) {
+        dbg_ctx *c = dbg_create(device_ids ? device_ids[k] : k);
+        if (!c) {
+            dbg_multi_destroy(m);
+            return nullptr;
+        }
+        m->ctx.push_back(c);
+    }
+    return m;
+}
+
+extern "C" int dbg_multi_device_count(const dbg_multi *m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" dbg_ctx *dbg_multi_ctx(dbg_multi *m, int k) { return (m && k >= 0 && k < (int)m->ctx.size()) ? m->ctx[k] : nullptr; }
+extern "C" const char *dbg_multi_last_error(const dbg_multi *m) { return m ? m->err : g_err; }
+
+// Estimated decode time of an item, in arbitrary units: compressed bytes (a stream that opens with a stored block is a
+// plain copy) plus a share of the output (match copying, un-filtering).
+static inline uint64_t item_cost(int kind, const uint8_t *p, uint64_t size, uint64_t cap)
+{
+    return sched_weight(kind, p, size) + cap / (kind == 2 ? 4 : 32) + 4096;
+}
+
+// The partition alone (exported so that callers and tests can see it): device_of_item[i] = index of the device that
+// gets item i. Returns the number of runs. Runs never split an item; when the items do not lie in index order in the
+// arenas every item is a run of its own.
+extern "C" int dbg_multi_partition(int n_devices, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
+                                   const uint64_t *in_size, const uint64_t *out_off, const uint64_t *out_cap,
+                                   uint32_t *device_of_item, uint64_t *device_cost)
+{
+    if (n_devices <= 0 || !in_off || !in_size || !out_off || !out_cap || !device_of_item) return DBG_ERR_ARG;
+    std::vector<uint64_t> cost(n);
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        cost[i] = item_cost(kind, h_in ? h_in + in_off[i] : nullptr, h_in ? in_size[i] : 0, out_cap[i]) + (h_in ? 0 : in_size[i]);
+        total += cost[i];
+    }
+    const bool mono = items_in_order(n, in_off, in_size, out_off, out_cap);
+    const uint64_t target = std::max<uint64_t>(1, total / ((uint64_t)n_devices * 8));  // ~8 runs per device
+    struct Run { uint64_t b, e, cost; };
+    std::vector<Run> runs;
+    for (uint64_t i = 0; i < n;) {
+        Run r{i, i, 0};
+        do {
+            r.cost += cost[r.e++];
+        } while (mono && r.e < n && r.cost + cost[r.e] / 2 < target);
+        runs.push_back(r);
+        i = r.e;
+    }
+    std::vector<size_t> by(runs.size());
+    std::iota(by.begin(), by.end(), (size_t)0);
+    std::stable_sort(by.begin(), by.end(), [&](size_t a, size_t b) { return runs[a].cost > runs[b].cost; });
+    std::vector<uint64_t> load(n_devices, 0);
+    for (size_t k : by) {
+        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[d] += runs[k].cost;
+        for (uint64_t i = runs[k].b; i < runs[k].e; i++) device_of_item[i] = (uint32_t)d;
+    }
+    if (device_cost)
+        for (int d = 0; d < n_devices; d++) device_cost[d] = load[d];
+    return (int)runs.size();
+}
+
+extern "C" int dbg_decode_batch_packed_multi(dbg_multi *m, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
+                                             const uint64_t *in_size, uint8_t *h_out, const uint64_t *out_off,
+                                             const uint64_t *out_cap, uint64_t *out_size, uint32_t *status, uint32_t *device_of_item)
+{
+    if (!m || m->ctx.empty()) return DBG_ERR_NO_DEVICE;
+    if (n == 0) return DBG_OK;
+    if (!h_in || !in_off || !in_size || !h_out || !out_off || !out_cap || !out_size || !status || kind < 0 || kind > 2 ||
+        n > 0x7fffffffull) {
+        snprintf(m->err, sizeof(m->err), "dbg_decode_batch_packed_multi: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    const int nd = (int)m->ctx.size();
+    if (nd == 1) {
+        if (device_of_item) memset(device_of_item, 0, n * 4);
+        int rc = dbg_decode_batch_packed(m->ctx[0], kind, n, h_in, in_off, in_size, h_out, out_off, out_cap, out_size, status);
+        if (rc) memcpy(m->err, m->ctx[0]->err, sizeof(m->err));
+        return rc;
+    }
+    std::vector<uint32_t> dev(n);
+    dbg_multi_partition(nd, kind, n, h_in, in_off, in_size, out_off, out_cap, dev.data(), nullptr);
+    if (device_of_item) memcpy(device_of_item, dev.data(), n * 4);
+    const bool mono = items_in_order(n, in_off, in_size, out_off, out_cap);
+    std::vector<int> rcs(nd, DBG_OK);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++) {
+        th.emplace_back([&, d]() {
+            // this device's items, in index order, as a batch of its own; a wave per run of consecutive items
+            std::vector<uint64_t> idx, cuts;
+            for (uint64_t i = 0; i < n; i++)
+                if (dev[i] == (uint32_t)d) {
+                    if (idx.empty() || idx.back() + 1 != i) cuts.push_back(idx.size());
+                    idx.push_back(i);
+                }
+            if (idx.empty()) return;
+            cuts.push_back(idx.size());
+            const uint64_t k = idx.size();
+            std::vector<uint64_t> io(k), is(k), oo(k), oc(k), os(k);
+            std::vector<uint32_t> st(k);
+            for (uint64_t j = 0; j < k; j++) {
+                io[j] = in_off[idx[j]];
+                is[j] = in_size[idx[j]];
+                oo[j] = out_off[idx[j]];
+                oc[j] = out_cap[idx[j]];
+            }
+            dbg_ctx *ctx = m->ctx[d];
+            int rc;
+            if (cudaSetDevice(ctx->device) != cudaSuccess) {
+                rc = DBG_ERR_CUDA;
+            } else if (!mono || k <= 4) {
+                rc = packed_small(ctx, kind, k, h_in, io.data(), is.data(), h_out, oo.data(), oc.data(), os.data(), st.data());
+            } else {
+                // a wave per run, at most MAX_WAVES waves per call (a wave never spans bytes of another device's items:
+                // its download would overwrite them on the host)
+                rc = DBG_OK;
+                const size_t nruns = cuts.size() - 1;
+                for (size_t r0 = 0; r0 < nruns && rc == DBG_OK; r0 += dbg_ctx::MAX_WAVES) {
+                    const size_t r1 = std::min(nruns, r0 + (size_t)dbg_ctx::MAX_WAVES);
+                    const uint64_t j0 = cuts[r0], j1 = cuts[r1];
+                    std::vector<uint64_t> sub(cuts.begin() + r0, cuts.begin() + r1 + 1);
+                    for (auto &c : sub) c -= j0;
+                    ctx->err[0] = 0;
+                    rc = packed_waves(ctx, kind, j1 - j0, h_in, io.data() + j0, is.data() + j0, h_out, oo.data() + j0, oc.data() + j0,
+                                      os.data() + j0, st.data() + j0, sub, kind == 2 || nruns == 1);
+                }
+            }
+            rcs[d] = rc;
+            if (rc == DBG_OK)
+                for (uint64_t j = 0; j < k; j++) {
+                    out_size[idx[j]] = os[j];
+                    status[idx[j]] = st[j];
+                }
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < nd; d++)
+        if (rcs[d]) {
+            snprintf(m->err, sizeof(m->err), "device %d: %s", m->ctx[d]->device, m->ctx[d]->err);
+            return rcs[d];
+        }
+    return DBG_OK;
+}
+
 // ----------------------------------------------------------------------- BMP --
 // decode_bmp.c:105-372: header checks + BGRA <-> RGBA swizzle (bmp_kernels.cuh).
 static int bmp_launch(dbg_ctx *ctx, bool encode, dbg::BmpBatch b, cudaStream_t s)
 {
     const uint64_t n = b.n;
-    CU(ctx->d_meta.reserve(n * sizeof(dbg::BmpItem) + (n + 1) * sizeof(uint32_t) + 64));
-    b.items = (dbg::BmpItem *)ctx->d_meta.p;
+    CU(ctx->slot[0].meta.reserve(n * sizeof(dbg::BmpItem) + (n + 1) * sizeof(uint32_t) + 64));
+    b.items = (dbg::BmpItem *)ctx->slot[0].meta.p;
     b.tile_base = (uint32_t *)(b.items + n);
     const unsigned blocks = (unsigned)((n + 127) / 128);
     if (encode) dbg::bmp_encode_plan_kernel<<<blocks, 128, 0, s>>>(b);

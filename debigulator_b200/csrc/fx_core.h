@@ -141,10 +141,46 @@ struct FxRun {
     uint32_t flag;      // CH_RUN while running, else CH_EOB / CH_Q2 / CH_ERR + status
 };
 
+// Token writer of one lane: single stores up to the first 16-byte boundary, then four tokens per store (every
+// lane writes somewhere else, so a 4-byte store costs the memory system what a 16-byte one does).
+struct TokOut {
+    uint32_t *p;
+    uint32_t q0, q1, q2;
+    uint32_t k;
+    DBG_DEVM void open(uint32_t *dst)
+    {
+        p = dst;
+        q0 = q1 = q2 = 0;
+        k = 0;
+    }
+    DBG_DEVM void put(uint32_t t)
+    {
+        if (k == 3) {
+            simt::st_u32x4(p, q0, q1, q2, t);
+            p += 4;
+            k = 0;
+        } else if (k == 0 && ((uintptr_t)p & 15)) {
+            *p++ = t;
+        } else {
+            q0 = q1;
+            q1 = q2;
+            q2 = t;
+            k++;
+        }
+    }
+    DBG_DEVM void close()
+    {
+        if (k == 3) *p++ = q0;
+        if (k >= 2) *p++ = q1;
+        if (k >= 1) *p++ = q2;
+        k = 0;
+    }
+};
+
 // Decodes symbols while rel < stop. `q2r` is the rule-Q2 limit relative to the chunk (no symbol may start at
-// or past it). EMIT writes the tokens to tok[ntok...].
+// or past it). EMIT hands the tokens to the lane's writer.
 template <bool EMIT>
-DBG_DEV void fx_run(const FxLuts *L, LaneBits &br, FxRun &r, uint32_t stop, uint32_t q2r, uint32_t *tok)
+DBG_DEV void fx_run(const FxLuts *L, LaneBits &br, FxRun &r, uint32_t stop, uint32_t q2r, TokOut *tok)
 {
     while (r.flag == CH_RUN && r.rel < stop) {
         if (r.rel >= q2r) {
@@ -164,7 +200,7 @@ DBG_DEV void fx_run(const FxLuts *L, LaneBits &br, FxRun &r, uint32_t stop, uint
             r.flag = CH_EOB;
             break;
         }
-        if (EMIT) tok[r.ntok] = t;
+        if (EMIT) tok->put(t);
         r.ntok++;
         r.out += len;
     }
@@ -292,7 +328,10 @@ DBG_DEV uint32_t fx_tokens_lane(const FxLuts *L, const uint8_t *in, uint64_t in_
     r.out = 0;
     r.ntok = 0;
     r.flag = CH_RUN;
-    fx_run<true>(L, br, r, exit_rel, q2r, tok);
+    TokOut w;
+    w.open(tok);
+    fx_run<true>(L, br, r, exit_rel, q2r, &w);
+    w.close();
     *out_bytes = r.out;
     *ntok = r.ntok;
     return r.flag;

@@ -162,22 +162,20 @@ extern "C" DecodedData *decode_gz(uint8_t *compressed_bytes, uint32_t compressed
     if (!compressed_bytes || compressed_bytes_size < 18) return r;
     dbg_ctx *ctx = slot_ctx(0);
     if (!ctx) return r;
-    // decode_gz.c:245 sizes the output as left*35 + 1,000,000; ISIZE (mod 2^32)
-    // from the trailer is used when it asks for more than that guess.
-    uint64_t guess = (uint64_t)compressed_bytes_size * 35 + 1000000ull;
+    // decode_gz.c:245 sizes the output as left*35 + 1,000,000. ISIZE (mod 2^32) from the trailer raises that bound when
+    // it is believable: DEFLATE cannot expand by more than 1032:1, so a larger claim is not honoured (an 18-byte file
+    // must not make this call reserve 4 GiB). The buffer handed to the caller is allocated once the size is known.
+    uint64_t cap = (uint64_t)compressed_bytes_size * 35 + 1000000ull;
     const uint8_t *t = compressed_bytes + compressed_bytes_size - 4;
-    uint64_t isize = (uint64_t)t[0] | ((uint64_t)t[1] << 8) | ((uint64_t)t[2] << 16) | ((uint64_t)t[3] << 24);
-    uint64_t cap = guess > isize ? guess : isize;
-    if (cap > 0xffffffffull) cap = 0xffffffffull;
-    uint8_t *buf = (uint8_t *)g_gz_malloc((size_t)cap);
-    if (!buf) return r;
-    const uint8_t *in[1] = {compressed_bytes};
-    uint8_t *out[1] = {buf};
-    uint64_t in_size[1] = {compressed_bytes_size}, caps[1] = {cap}, sz[1] = {0};
-    uint32_t good[1] = {0};
-    if (dbg_decode_gz_batch(ctx, 1, in, in_size, out, caps, sz, good) != DBG_OK || !good[0]) return r;
+    const uint64_t isize = (uint64_t)t[0] | ((uint64_t)t[1] << 8) | ((uint64_t)t[2] << 16) | ((uint64_t)t[3] << 24);
+    if (isize > cap && isize <= (uint64_t)compressed_bytes_size * 1032 + 1024) cap = isize;
+    if (cap > 0xffffffffull - 2048) cap = 0xffffffffull - 2048;  // the decoder's own limit (inflate_core.h)
+    uint8_t *buf = nullptr;
+    uint64_t sz = 0;
+    uint32_t good = 0;
+    if (dbg_decode_gz_alloc(ctx, compressed_bytes, compressed_bytes_size, cap, g_gz_malloc, &buf, &sz, &good) != DBG_OK || !good) return r;
     r->data = (char *)buf;
-    r->data_size = (uint32_t)sz[0];
+    r->data_size = (uint32_t)sz;
     r->good = 1;
     return r;
 }

@@ -74,6 +74,7 @@ DBG_DEV void cp_async16_stream(void *smem_dst, const void *gsrc, int src_bytes)
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes), "l"(pol)
                  : "memory");
 }
+DBG_DEV void st_u32x4(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d); }  // p 16-byte aligned
 DBG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 DBG_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
@@ -184,6 +185,7 @@ DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return *p; }
 DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return *p; }
 
 DBG_DEV void cp_async16_stream(void *smem_dst, const void *gsrc, int src_bytes) { cp_async16(smem_dst, gsrc, src_bytes); }
+DBG_DEV void st_u32x4(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 DBG_DEV void cp_async_commit() {}
 DBG_DEV void cp_async_wait_all() {}
 

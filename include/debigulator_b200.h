@@ -73,8 +73,10 @@ enum {
 int dbg_version(void);
 int dbg_device_count(void); /* >= 0, or a DBG_ERR_* code */
 
-/* One context per GPU (one process per GPU in multi-GPU runs). A context owns its device scratch, pinned
- * staging buffers and streams; it is not thread-safe -- use one context per host thread. */
+/* One context per GPU (one process per GPU in multi-GPU runs, or dbg_multi below). A context owns its device scratch,
+ * pinned staging buffers and streams; it is not thread-safe -- use one context per host thread. Device-resident
+ * calls on different streams are ordered by the library itself (each waits, on the device, for the previous one to
+ * be done with the shared scratch). */
 dbg_ctx *dbg_create(int device);
 void dbg_destroy(dbg_ctx *ctx);
 const char *dbg_last_error(const dbg_ctx *ctx); /* ctx may be NULL */
@@ -153,12 +155,52 @@ int dbg_bsplit_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *fallbacks)
  * chunk entry points that needed more than one decode run (strictly periodic symbol streams). Diagnostics only. */
 int dbg_fx_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *handed_back, uint64_t *extra_runs);
 
-/* Optional timing of the dominant kernel (inflate): after dbg_profile_enable(ctx, 1)
- * every inflate launch is bracketed by CUDA events on its own stream;
- * dbg_profile_read() waits for them, returns the summed device time and the
- * number of launches, and resets the counters. */
+/* Optional timing of the kernel groups, for roofline reports: after dbg_profile_enable(ctx, 1) every group below is
+ * bracketed by CUDA events on the stream it runs on. dbg_profile_read_tag() waits for the brackets of one group and
+ * returns their summed device time and their number; dbg_profile_read() does that for DBG_PROF_INFLATE and resets
+ * the recording (dbg_profile_enable(ctx, 1) resets it too). */
+enum {
+    DBG_PROF_INFLATE = 0,      /* inflate_batch_kernel: one warp per stream */
+    DBG_PROF_FX_SIZES = 1,     /* lane-serial path: head + sizes + chain kernels */
+    DBG_PROF_FX_EXPAND = 2,    /* lane-serial path: tokens + expansion + resolve kernels */
+    DBG_PROF_PNG_SCAN = 3,     /* PNG chunk walk, CRC-32, IDAT gather */
+    DBG_PROF_PNG_UNFILTER = 4  /* PNG scanline reconstruction */
+};
 int dbg_profile_enable(dbg_ctx *ctx, int on);
 int dbg_profile_read(dbg_ctx *ctx, double *total_ms, uint64_t *launches);
+int dbg_profile_read_tag(dbg_ctx *ctx, int tag, double *total_ms, uint64_t *launches);
+
+/* Releases the scratch memory the context keeps between calls: 16-bit cells (2 bytes per output byte of the streams
+ * on the chunk-parallel paths), tokens (4 bytes per symbol; block-split path: up to 16 bytes per compressed byte,
+ * capped at 24 GiB), PNG scanline buffers (1.25 x the RGBA bytes of a batch) and the staging arenas of the host API.
+ * All of it is grow-only otherwise. Waits for the device. */
+int dbg_trim(dbg_ctx *ctx);
+
+/* One gzip member, decoded into memory obtained from `alloc` once the size is known (the drop-in decode_gz() of
+ * decode_gz.h is built on this). cap = largest output accepted. *good = 0 leaves *out NULL. */
+int dbg_decode_gz_alloc(dbg_ctx *ctx, const uint8_t *in, uint64_t in_size, uint64_t cap, void *(*alloc)(size_t),
+                        uint8_t **out, uint64_t *out_size, uint32_t *good);
+
+/* ---- several GPUs of one box, one batch ---------------------------------------------------------
+ * The items of a batch are independent: the batch is cut into runs of consecutive items, the runs are dealt to the
+ * devices longest-processing-time first by estimated decode time, and every device decodes its runs with its own
+ * context, stream set and host thread. No exchange step, no collective. The reference's only provision for
+ * concurrency is the thread_id slot (inflate.c:22-23, decode_png.c:559-560). */
+typedef struct dbg_multi dbg_multi;
+dbg_multi *dbg_multi_create(int n_devices, const int *device_ids); /* n_devices <= 0: all; device_ids NULL: 0..n-1 */
+void dbg_multi_destroy(dbg_multi *m);
+int dbg_multi_device_count(const dbg_multi *m);
+dbg_ctx *dbg_multi_ctx(dbg_multi *m, int k); /* the k-th device's context (counters, tunables) */
+const char *dbg_multi_last_error(const dbg_multi *m);
+/* Same contract as dbg_decode_batch_packed(); device_of_item (may be NULL) receives the device index of every item. */
+int dbg_decode_batch_packed_multi(dbg_multi *m, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
+                                  const uint64_t *in_size, uint8_t *h_out, const uint64_t *out_off, const uint64_t *out_cap,
+                                  uint64_t *out_size, uint32_t *status, uint32_t *device_of_item);
+/* The partition alone (pure host code; needs no GPU): device index per item, estimated cost per device (may be
+ * NULL). h_in may be NULL (costs then come from the sizes only). Returns the number of runs, or DBG_ERR_ARG. */
+int dbg_multi_partition(int n_devices, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
+                        const uint64_t *in_size, const uint64_t *out_off, const uint64_t *out_cap, uint32_t *device_of_item,
+                        uint64_t *device_cost);
 
 /* ---- BMP (decode_bmp.h:14-36; decode_bmp.c:105-372) --------------------------
  * 32-bit BGRA BMP <-> RGBA8, the reference's decode_BMP / encode_BMP batched. Decode accepts what the

@@ -286,3 +286,147 @@ def test_optin_png_adler_verification(ctx):
         assert res[0][3] == img.tobytes() and res[1][3] == img.tobytes()
     finally:
         ctx.set_verify(False)
+
+
+# ------------------------------------------------------------------ round 2: waves, multi-device, stream order --
+def _png_batch(n, w=192, h=160, unique=12):
+    uniq = [corpus.png_cfg3(i, w, h) for i in range(unique)]
+    files = [uniq[i % unique][0] for i in range(n)]
+    want = [uniq[i % unique][1] for i in range(n)]
+    return files, want
+
+
+def _pack(files, caps, pad=16):
+    in_off, out_off, ti, to = [], [], 0, 0
+    for f, c in zip(files, caps):
+        in_off.append(ti)
+        ti += (len(f) + pad + 15) // 16 * 16
+        out_off.append(to)
+        to += (c + 15) // 16 * 16
+    h_in = np.zeros(ti + 64, np.uint8)
+    for f, o in zip(files, in_off):
+        h_in[o:o + len(f)] = np.frombuffer(f, np.uint8)
+    return h_in, np.array(in_off, np.uint64), np.array([len(f) for f in files], np.uint64), np.zeros(to + 64, np.uint8), \
+        np.array(out_off, np.uint64), np.array(caps, np.uint64)
+
+
+def test_packed_png_waves(ctx, monkeypatch):
+    """PNG through the packed host API in several overlapped waves (per-wave scratch, per-wave lane-serial path)."""
+    monkeypatch.setenv("DBG_PNG_WAVES", "8")
+    c = dbg.Context(0)
+    # > 64 MB of files so that the batch is really cut into waves
+    files, want = _png_batch(96, 1024, 768, 6)
+    files[5] = files[5][:-20]                      # truncated: IEND missing
+    bad = bytearray(files[7])
+    bad[len(bad) // 2] ^= 0x10
+    files[7] = bytes(bad)                          # IDAT bit flip -> CRC mismatch
+    caps = [1024 * 768 * 4] * len(files)
+    h_in, in_off, in_size, h_out, out_off, out_cap = _pack(files, caps)
+    assert int(in_size.sum()) > 2 * (64 << 20)
+    fx0 = c.fx_stats()
+    osz, st = c.decode_packed(dbg.api.KIND_PNG, h_in, in_off, in_size, h_out, out_off, out_cap)
+    assert st[5] != 0 and st[7] != 0 and osz[5] == 0
+    for i in range(len(files)):
+        if i in (5, 7):
+            continue
+        assert st[i] == 0 and osz[i] == caps[i], (i, st[i])
+        o = int(out_off[i])
+        assert h_out[o:o + caps[i]].tobytes() == want[i], i
+    assert c.fx_stats()[0] - fx0[0] >= 90          # the waves used the lane-serial path
+    c.close()
+
+
+def test_packed_multi_two_contexts_one_gpu(ref):
+    """dbg_decode_batch_packed_multi with two contexts (both on cuda:0, so the partition, the per-device threads and the
+    sub-set waves all run on a one-GPU box): gzip members and PNGs, every item against the reference."""
+    m = dbg.MultiContext(2, [0, 0])
+    assert m.n_devices == 2
+    members = [corpus.gz_member_cfg2(i, 1 << 17) for i in range(600)]
+    caps = [len(d) + len(g) + 64 for g, d in members]
+    h_in, in_off, in_size, h_out, out_off, out_cap = _pack([g for g, _ in members], caps)
+    osz, st, dev = m.decode_packed(dbg.api.KIND_GZ, h_in, in_off, in_size, h_out, out_off, out_cap)
+    assert set(dev.tolist()) == {0, 1}
+    assert abs(int((dev == 0).sum()) - 300) < 120
+    for i, (g, d) in enumerate(members):
+        assert st[i] == 0 and osz[i] == len(d), i
+        o = int(out_off[i])
+        assert h_out[o:o + len(d)].tobytes() == d, i
+    rg, rout = ref.decode_gz(members[3][0], caps[3])
+    assert rg == 1 and rout == members[3][1]
+    files, want = _png_batch(40, 640, 480, 8)
+    caps = [640 * 480 * 4] * len(files)
+    h_in, in_off, in_size, h_out, out_off, out_cap = _pack(files, caps)
+    osz, st, dev = m.decode_packed(dbg.api.KIND_PNG, h_in, in_off, in_size, h_out, out_off, out_cap)
+    assert set(dev.tolist()) == {0, 1}
+    for i in range(len(files)):
+        assert st[i] == 0, i
+        o = int(out_off[i])
+        assert h_out[o:o + caps[i]].tobytes() == want[i], i
+    assert m.fx_stats(0)[0] + m.fx_stats(1)[0] == 40
+    m.close()
+
+
+def test_device_calls_on_two_streams_share_scratch_safely(ctx):
+    """Two device-resident calls issued back to back on DIFFERENT streams, neither synchronised in between: the
+    second must not disturb the first one's work queue and descriptors (per-context scratch)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    members = [corpus.gz_member_cfg2(i, 1 << 18) for i in range(64)]
+    n = 512
+    caps = [(1 << 18) + 4096] * n
+    h_in, in_off, in_size, _, out_off, out_cap = _pack([members[i % 64][0] for i in range(n)], caps)
+    i64 = lambda a: torch.from_numpy(np.asarray(a, np.uint64).view(np.int64)).to(dev)
+    d_in = torch.from_numpy(h_in).to(dev)
+    a_off, a_sz, o_off, o_cap = i64(in_off), i64(in_size), i64(out_off), i64(out_cap)
+    outs, sizes, sts = [], [], []
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    for s in streams:
+        outs.append(torch.zeros(int(out_off[-1] + out_cap[-1]) + 64, dtype=torch.uint8, device=dev))
+        sizes.append(torch.zeros(n, dtype=torch.int64, device=dev))
+        sts.append(torch.full((n,), 77, dtype=torch.int32, device=dev))
+    for k, s in enumerate(streams):
+        ctx.inflate_device(d_in, a_off, a_sz, outs[k], o_off, o_cap, sizes[k], sts[k], None, stream=s.cuda_stream, gz=True)
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert int(sts[k].abs().sum().item()) == 0, k
+        assert bool((sizes[k] == (1 << 18)).all().item()), k
+    assert torch.equal(outs[0], outs[1])
+    got = outs[0].cpu().numpy()
+    for i in (0, 1, 2, 3, 63, 511):
+        o = int(out_off[i])
+        assert got[o:o + (1 << 18)].tobytes() == members[i % 64][1], i
+
+
+def test_scalar_gz_lying_isize_and_trim(L, ctx):
+    """An 18-byte-header member whose ISIZE claims 4 GiB must not make the drop-in decode_gz() reserve that (the bound
+    is what DEFLATE can expand to); dbg_trim releases the scratch and the context keeps working."""
+    import struct
+    import zlib
+    L.init_decode_gz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.decode_gz.argtypes = [C.c_void_p, C.c_uint32]
+
+    class DD(C.Structure):
+        _fields_ = [("data", C.c_void_p), ("data_size", C.c_uint32), ("good", C.c_uint32)]
+    L.decode_gz.restype = C.POINTER(DD)
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    sizes = []
+    MALLOC = C.CFUNCTYPE(C.c_void_p, C.c_size_t)
+
+    def my_malloc(nbytes):
+        sizes.append(nbytes)
+        return libc.malloc(C.c_size_t(nbytes))
+    cb = MALLOC(my_malloc)
+    L.init_decode_gz(cb, None, None)
+    data = corpus.word_salad(30000, 9)
+    g = bytearray(corpus.gzip_frame(corpus.raw_deflate(data, 6), data))
+    g[-4:] = struct.pack("<I", 0xfffffff0)        # ISIZE lies
+    ib = C.create_string_buffer(bytes(g), len(g))
+    r = L.decode_gz(ib, len(g))
+    assert r.contents.good == 1 and r.contents.data_size == len(data)
+    assert C.string_at(r.contents.data, len(data)) == data
+    assert max(sizes) <= len(data) + 64           # the struct and an exact-size buffer, nothing speculative
+    ctx.trim()
+    (good, out), = ctx.decode_gz_batch([bytes(corpus.gzip_frame(corpus.raw_deflate(data, 6), data))], [len(data) + 64])
+    assert good == 1 and out == data

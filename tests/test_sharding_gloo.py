@@ -17,10 +17,20 @@ def test_lpt_partition_properties():
         flat = sorted(i for s in shards for i in s)
         assert flat == list(range(len(sizes)))
         loads = [sum(sizes[i] for i in s) for s in shards]
-        assert max(loads) - min(loads) <= max(sizes)
+        # runs of ~1/8 of a device's share, dealt longest first: the loads differ by less than one run
+        assert max(loads) - min(loads) <= sum(sizes) / (8 * world) + 2 * max(sizes) + 8 * 4096, (world, loads)
     assert lpt_partition([], 2) == [[], []]
     order = schedule_order(sizes)
     assert [sizes[i] for i in order] == sorted(sizes, reverse=True)
+
+
+def test_partition_few_huge_items():
+    """BASELINE config 4 shape: 256 equal images over 8 devices -> 32 each; and one dominant item gets a device alone."""
+    shards = lpt_partition([150_000_000] * 256, 8, out_cap=[268_435_456] * 256, kind=2)
+    assert sorted(len(s) for s in shards) == [32] * 8
+    shards = lpt_partition([10_000_000] + [100_000] * 64, 2)
+    big = [s for s in shards if 0 in s][0]
+    assert len(big) < 20
 
 
 def _worker(rank, world, port, q):
