@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <numeric>
 #include <thread>
 #include <utility>
@@ -62,6 +64,9 @@ struct Buf {
 struct Slot {
     cudaStream_t stream = nullptr;   // the wave's stream
     cudaEvent_t done = nullptr;      // recorded behind the last work that used this slot's scratch
+    cudaEvent_t uploaded = nullptr;  // packed host API: the wave's input has arrived
+    cudaStream_t aux_stream = nullptr;  // the warp-per-stream kernel runs here beside the block-split kernels
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     Buf counter;                     // work-queue heads
     Buf meta;                        // derived descriptors (gzip payloads, BMP items)
     Buf png_scratch;                 // PNG: per-image meta, task queues, compacted IDAT, filtered scanlines
@@ -86,9 +91,9 @@ struct dbg_ctx {
     int waves = 16;      // waves the packed host API cuts a large gzip / deflate batch into (cfg2 end to end: 2 -> 23.5, 4 -> 25.8, 8 -> 26.7, 16 -> 27.4 GB/s)
     int png_waves = 8;   // the same for PNG batches (every wave synchronises the host twice on the lane-serial path)
     cudaEvent_t wave_ready = nullptr;
-    cudaStream_t aux_stream = nullptr;  // the warp-per-stream kernel runs here beside the block-split kernels
-    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
-    uint64_t launches = 0;
+    cudaStream_t up_stream = nullptr;   // packed host API: all uploads, in wave order (one queue, so they finish in that order)
+    std::atomic<uint64_t> launches{0};
+    std::mutex prof_mu;
     char err[512] = "";
     // optional per-launch timing of the dominant (inflate) kernel, for roofline reports
     bool profiling = false;
@@ -108,8 +113,8 @@ struct dbg_ctx {
     bool verify = false;            // opt-in: check gzip CRC32 / ISIZE trailers, zlib Adler-32
     uint32_t inflate_ctas_per_sm = dbg::INFLATE_CTAS_PER_SM;  // resident streams per SM = 4x this (tunable: L2 footprint)
     // counters
-    uint64_t bs_streams = 0, bs_fallbacks = 0;
-    uint64_t fx_streams = 0, fx_redo = 0, fx_extra = 0;
+    std::atomic<uint64_t> bs_streams{0}, bs_fallbacks{0};
+    Buf d_stats;                    // lane-serial path: streams decoded / handed back / extra survivors, counted on the device
     // host-API staging
     Buf d_in, d_out, d_desc;       // arenas + descriptor tables
     Buf h_in, h_out, h_desc;       // pinned mirrors
@@ -138,6 +143,11 @@ extern "C" int dbg_version(void) { return 200; }
 
 extern "C" int dbg_device_count(void)
 {
+    // The packed host API overlaps up to 16 waves on streams of their own. Streams share the device's hardware queues
+    // (8 by default) and waves on one queue wait for each other: measured 196 ms per cfg2 call with 8 queues, 153 ms
+    // with 32. The variable is read when the CUDA context is made, so this only helps when the library is the first
+    // CUDA user of the process; otherwise set it in the environment. Never overrides the caller's value.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) {
@@ -149,7 +159,7 @@ extern "C" int dbg_device_count(void)
 
 extern "C" const char *dbg_last_error(const dbg_ctx *ctx) { return ctx ? ctx->err : g_err; }
 extern "C" int dbg_ctx_device(const dbg_ctx *ctx) { return ctx ? ctx->device : -1; }
-extern "C" uint64_t dbg_kernel_launches(const dbg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t dbg_kernel_launches(const dbg_ctx *ctx) { return ctx ? ctx->launches.load() : 0ull; }
 
 extern "C" void dbg_destroy(dbg_ctx *ctx);
 
@@ -177,15 +187,25 @@ extern "C" dbg_ctx *dbg_create(int device)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     // every stream, event and kernel attribute is needed: a half-made context would run waves on the legacy stream
-    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    // The wave streams are created first and back to back: streams are mapped to the device's hardware queues
+    // (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) in creation order, and waves that share a queue wait for each other
+    // (measured: with the auxiliary streams created in between, the 16 waves of a cfg2 call ran in two groups of 8,
+    // 196 ms per call instead of 155).
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < dbg_ctx::MAX_WAVES && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < dbg_ctx::MAX_WAVES && e == cudaSuccess; i++) {
-        e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot[i].done, cudaEventDisableTiming);
+        Slot &sl = ctx->slot[i];
+        e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sl.aux_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.aux_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.aux_join, cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->wave_ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = ctx->d_stats.reserve(64);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_stats.p, 0, 64);
     const size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
@@ -219,21 +239,24 @@ extern "C" void dbg_destroy(dbg_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    Buf *all[] = {&ctx->d_in, &ctx->d_out, &ctx->d_desc, &ctx->h_in, &ctx->h_out, &ctx->h_desc};
+    Buf *all[] = {&ctx->d_in, &ctx->d_out, &ctx->d_desc, &ctx->h_in, &ctx->h_out, &ctx->h_desc, &ctx->d_stats};
     for (Buf *b : all) b->release();
     for (int i = 0; i < dbg_ctx::MAX_WAVES; i++) {
         ctx->slot[i].release();
-        if (ctx->slot[i].stream) cudaStreamDestroy(ctx->slot[i].stream);
-        if (ctx->slot[i].done) cudaEventDestroy(ctx->slot[i].done);
+        Slot &sl = ctx->slot[i];
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+        if (sl.aux_stream) cudaStreamDestroy(sl.aux_stream);
+        if (sl.aux_fork) cudaEventDestroy(sl.aux_fork);
+        if (sl.aux_join) cudaEventDestroy(sl.aux_join);
     }
     for (auto &pe : ctx->prof_events) {
         cudaEventDestroy(pe.first);
         cudaEventDestroy(pe.second);
     }
     if (ctx->wave_ready) cudaEventDestroy(ctx->wave_ready);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
-    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
-    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -249,9 +272,14 @@ extern "C" int dbg_bsplit_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t 
 extern "C" int dbg_fx_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *handed_back, uint64_t *extra_runs)
 {
     if (!ctx) return DBG_ERR_NO_DEVICE;
-    if (streams) *streams = ctx->fx_streams;
-    if (handed_back) *handed_back = ctx->fx_redo;
-    if (extra_runs) *extra_runs = ctx->fx_extra;
+    // counted on the device (the packed PNG path never waits for them); reading them waits for the device
+    uint64_t v[3] = {0, 0, 0};
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(v, ctx->d_stats.p, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return DBG_ERR_CUDA;
+    if (streams) *streams = v[0];
+    if (handed_back) *handed_back = v[1];
+    if (extra_runs) *extra_runs = v[2];
     return DBG_OK;
 }
 
@@ -329,6 +357,7 @@ struct ProfScope {
     ProfScope(dbg_ctx *c, cudaStream_t st, int tag) : ctx(c), s(st)
     {
         if (!ctx->profiling) return;
+        std::lock_guard<std::mutex> lock(ctx->prof_mu);  // the waves of a PNG batch are driven by threads of their own
         if (ctx->prof_used == ctx->prof_events.size()) {
             cudaEvent_t a = nullptr, b = nullptr;
             if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
@@ -372,12 +401,22 @@ static int launch_inflate_plain(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, int
 // fx_kernels.cuh. Two small device->host reads (how many streams / bytes; exact token and cell counts), so `s`
 // is synchronised twice. *skip_out = per-stream flags of the streams handled here, *redo_out = those handed
 // back (flag set as well) for a second warp-per-stream pass; *n_redo tells whether there are any.
-static int run_fx(dbg_ctx *ctx, Slot &sl, const dbg::InflateBatch &a, cudaStream_t s, const uint32_t **skip_out,
-                  const uint32_t **redo_out, uint32_t *n_redo)
+// What a caller that has the batch on the HOST knows up front (packed API): with it the scratch can be sized by upper
+// bounds and nothing is read back from the device, so the call never waits for the stream.
+struct FxHints {
+    bool have = false;
+    uint64_t total_in = 0;     // compressed bytes of the batch (an upper bound of those on this path)
+    uint64_t max_in = 0;       // the longest stream
+    uint64_t cells_bound = 0;  // sum of the streams' output sizes (upper bound)
+};
+
+static int run_fx(dbg_ctx *ctx, Slot &sl, const dbg::InflateBatch &a, cudaStream_t s, const FxHints &hints, const uint32_t **skip_out,
+                  const uint32_t **redo_out, uint32_t *n_redo, bool *all_taken)
 {
     *skip_out = nullptr;
     *redo_out = nullptr;
     *n_redo = 0;
+    *all_taken = false;
     const uint32_t n = a.n;
     CU(sl.h_fx.reserve(sizeof(dbg::FxSummary)));
     CU(sl.fx_stream.reserve(256 + (size_t)n * (2 * 8 + 6 * 4) + 256));
@@ -386,6 +425,7 @@ static int run_fx(dbg_ctx *ctx, Slot &sl, const dbg::InflateBatch &a, cudaStream
     b.in_base = a.in_base; b.in_off = a.in_off; b.in_size = a.in_size;
     b.out_base = a.out_base; b.out_off = a.out_off; b.out_cap = a.out_cap;
     b.out_size = a.out_size; b.status = a.status; b.pre_status = a.pre_status; b.n = n;
+    b.stats = (uint64_t *)ctx->d_stats.p;
     b.summary = (dbg::FxSummary *)p;
     b.cell_base = (uint64_t *)(p + 256);
     b.tok_base = b.cell_base + n;
@@ -401,9 +441,15 @@ static int run_fx(dbg_ctx *ctx, Slot &sl, const dbg::InflateBatch &a, cudaStream
     ctx->launches++;
     CU(cudaGetLastError());
     dbg::FxSummary *hs = (dbg::FxSummary *)sl.h_fx.p;
-    CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::FxSummary), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (hs->n_fx == 0) return DBG_OK;
+    if (hints.have) {
+        hs->n_fx = n;
+        hs->fx_in = hints.total_in;
+        hs->max_in = hints.max_in;
+    } else {
+        CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::FxSummary), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (hs->n_fx == 0) return DBG_OK;
+    }
     // chunk = what one lane decodes: 16 KiB, halved (down to 2 KiB) while the batch has fewer chunks than the
     // GPU has lanes to give; group = what one warp expands and the unit of the marker / resolve scheme:
     // 256 KiB of compressed data, smaller for small batches (more warps), larger for very long streams (the
@@ -454,16 +500,32 @@ static int run_fx(dbg_ctx *ctx, Slot &sl, const dbg::InflateBatch &a, cudaStream
         dbg::fx_fill_kernel<<<n, 128, 0, s>>>(b);
         dbg::fx_head_kernel<<<warp_grid, dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
         dbg::fx_sizes_kernel<<<lane_grid, dbg::FX_LANE_THREADS, 0, s>>>(b);
-        dbg::fx_chain_kernel<<<std::min<uint32_t>((n + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 8),
-                               dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
     }
-    ctx->launches += 5;
+    ctx->launches += 4;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::FxSummary), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (hs->cells_used) {
-        CU(sl.cells.reserve((size_t)hs->cells_used * 2 + 256));
-        CU(sl.fx_tok.reserve((size_t)hs->tok_used * 4 + 256));
+    // the chain kernel hands a stream back when the cells / tokens do not fit: exact sizes after a read-back, else
+    // upper bounds (a token takes at least 8 bits of a fixed-Huffman stream)
+    if (hints.have) {
+        b.cells_cap = hints.cells_bound;
+        b.tok_cap = hs->fx_in + n;
+        CU(sl.cells.reserve((size_t)b.cells_cap * 2 + 256));
+        CU(sl.fx_tok.reserve((size_t)b.tok_cap * 4 + 256));
+    } else {
+        b.cells_cap = b.tok_cap = ~0ull;
+    }
+    dbg::fx_chain_kernel<<<std::min<uint32_t>((n + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 8),
+                           dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (!hints.have) {
+        CU(cudaMemcpyAsync(hs, b.summary, sizeof(dbg::FxSummary), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    if (hints.have || hs->cells_used) {
+        if (!hints.have) {
+            CU(sl.cells.reserve((size_t)hs->cells_used * 2 + 256));
+            CU(sl.fx_tok.reserve((size_t)hs->tok_used * 4 + 256));
+        }
         b.cells = (uint16_t *)sl.cells.p;
         b.tok = (uint32_t *)sl.fx_tok.p;
         ProfScope prof(ctx, s, DBG_PROF_FX_EXPAND);
@@ -483,22 +545,20 @@ static int run_fx(dbg_ctx *ctx, Slot &sl, const dbg::InflateBatch &a, cudaStream
     }
     *skip_out = b.flag;
     *redo_out = b.redo;
-    *n_redo = hs->n_redo;
-    ctx->fx_streams += hs->n_fx - hs->n_redo;
-    ctx->fx_redo += hs->n_redo;
-    ctx->fx_extra += hs->n_extra;
+    *n_redo = hints.have ? 1u : hs->n_redo;  // not known without the read-back: the second pass is launched, and finds nothing to do
+    *all_taken = !hints.have && hs->n_fx == n && hs->n_redo == 0;
     return DBG_OK;
 }
 
 // Joins the auxiliary stream into `s` when run_bsplit leaves early: the kernel forked onto it reads the caller's
 // buffers and the slot's work queue, so nothing the caller enqueues next may overtake it.
 struct AuxJoin {
-    dbg_ctx *ctx;
+    Slot &sl;
     cudaStream_t s;
     bool armed = false;
     ~AuxJoin()
     {
-        if (armed) cudaStreamWaitEvent(s, ctx->aux_join, 0);
+        if (armed) cudaStreamWaitEvent(s, sl.aux_join, 0);
     }
 };
 
@@ -540,12 +600,12 @@ static int run_bsplit(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t 
     // fork: everything that is not split, on the auxiliary stream
     a.skip = taken;
     a.skip2 = b.flag;
-    AuxJoin join{ctx, s};
-    CU(cudaEventRecord(ctx->aux_fork, s));
-    CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+    AuxJoin join{sl, s};
+    CU(cudaEventRecord(sl.aux_fork, s));
+    CU(cudaStreamWaitEvent(sl.aux_stream, sl.aux_fork, 0));
     {
-        int rc = launch_inflate_plain(ctx, sl, a, 0, ctx->aux_stream);
-        cudaError_t er = cudaEventRecord(ctx->aux_join, ctx->aux_stream);
+        int rc = launch_inflate_plain(ctx, sl, a, 0, sl.aux_stream);
+        cudaError_t er = cudaEventRecord(sl.aux_join, sl.aux_stream);
         join.armed = er == cudaSuccess;
         if (rc) return rc;
         CU(er);
@@ -624,7 +684,8 @@ static int run_bsplit(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t 
 
 // All decode paths for one batch of raw DEFLATE streams. `intra` = the paths that cut long streams into pieces may
 // be used (they synchronise the host with `s`).
-static int launch_inflate(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t s, bool intra_fx, bool intra_bs)
+static int launch_inflate(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t s, bool intra_fx, bool intra_bs,
+                          const FxHints &hints = FxHints())
 {
     CU(sl.counter.reserve(8 * sizeof(uint32_t)));
     a.skip = nullptr;
@@ -633,9 +694,11 @@ static int launch_inflate(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStrea
     uint32_t n_redo = 0;
     if (ctx->fx && intra_fx) {
         const uint32_t *skip = nullptr;
-        int rc = run_fx(ctx, sl, a, s, &skip, &fx_redo, &n_redo);
+        bool all_taken = false;
+        int rc = run_fx(ctx, sl, a, s, hints, &skip, &fx_redo, &n_redo, &all_taken);
         if (rc) return rc;
         a.skip = skip;
+        if (all_taken) return DBG_OK;  // (a batch of stb-written PNGs) nothing is left for the other paths
     }
     if (n_redo) {
         // streams the lane-serial path handed back: a warp-per-stream pass of their own (a.skip keeps them out of
@@ -647,7 +710,7 @@ static int launch_inflate(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStrea
         int rc = launch_inflate_plain(ctx, sl, again, 2, s, false);
         if (rc) return rc;
     }
-    if (ctx->bsplit && intra_bs) {
+    if (ctx->bsplit && intra_bs && !hints.have) {  // (with hints the caller has seen that every stream is a fixed block)
         bool done = false;
         int rc = run_bsplit(ctx, sl, a, s, a.skip, &done);
         if (rc || done) return rc;
@@ -685,7 +748,8 @@ static int inflate_device_slot(dbg_ctx *ctx, Slot &sl, bool gz, bool intra, uint
 
 static int png_device_slot(dbg_ctx *ctx, Slot &sl, uint64_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                            const uint64_t *d_in_size, uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_out_cap,
-                           uint32_t *d_status, uint64_t total_in_bytes, uint64_t total_rgba_bytes, cudaStream_t s)
+                           uint32_t *d_status, uint64_t total_in_bytes, uint64_t total_rgba_bytes, cudaStream_t s,
+                           const FxHints &hints = FxHints())
 {
     CU(sl.png_scratch.reserve(dbg::png_scratch_bytes(n, total_in_bytes, total_rgba_bytes)));
     dbg::PngLayout lay = dbg::png_layout((uint8_t *)sl.png_scratch.p, n, total_in_bytes, total_rgba_bytes);
@@ -702,7 +766,7 @@ static int png_device_slot(dbg_ctx *ctx, Slot &sl, uint64_t n, const uint8_t *d_
     // z_off holds absolute addresses: a single-IDAT image is inflated straight from the file
     dbg::InflateBatch a{nullptr, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
                         lay.pre_status, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t)n};
-    rc = launch_inflate(ctx, sl, a, s, true, true);
+    rc = launch_inflate(ctx, sl, a, s, true, true, hints);
     if (rc) return rc;
     if (ctx->verify) {
         uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
@@ -811,6 +875,36 @@ static inline uint64_t sched_weight(int kind, const uint8_t *p, uint64_t size)
     return ((p[at] >> 1) & 3) == 0 ? size / 64 : size;
 }
 
+// Host-side look at a PNG batch: true when every file has a plausible IHDR and its first IDAT opens with a zlib header
+// followed by a FINAL FIXED-Huffman block (what stb_image_write emits, stb_write.h:913-916). est[i] = w*h*4 + h + 1, the
+// reference's bound of the filtered scanlines (decode_png.c:965-968). Nothing is decided here about validity: the
+// device-side chunk walk does that; a file that merely looks right costs nothing but scratch.
+static bool png_all_stb_shaped(uint64_t n, const uint8_t *h_in, const uint64_t *in_off, const uint64_t *in_size, std::vector<uint64_t> &est)
+{
+    est.resize(n);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *f = h_in + in_off[i];
+        const uint64_t size = in_size[i];
+        if (size < 8 + 25 + 12 + 3) return false;
+        auto be = [&](uint64_t at) { return ((uint64_t)f[at] << 24) | ((uint64_t)f[at + 1] << 16) | ((uint64_t)f[at + 2] << 8) | f[at + 3]; };
+        const uint64_t w = be(16), h = be(20);
+        if (w == 0 || h == 0 || w * h * 4 + h + 1 >= (1ull << 32)) return false;
+        est[i] = w * h * 4 + h + 1;
+        uint64_t pos = 8;
+        bool found = false;
+        for (int c = 0; c < 64 && pos + 12 <= size; c++) {
+            const uint64_t len = be(pos);
+            if (f[pos + 4] == 'I' && f[pos + 5] == 'D' && f[pos + 6] == 'A' && f[pos + 7] == 'T') {
+                found = len >= 3 && pos + 11 <= size && (f[pos + 10] & 7) == 3;
+                break;
+            }
+            pos += 12 + len;
+        }
+        if (!found) return false;
+    }
+    return true;
+}
+
 // The packed path proper. `cuts` are the wave boundaries (item indices, cuts.front() == 0, cuts.back() == n); the
 // items of a wave must lie in index order, without overlap, in both host arenas (one upload and one download per
 // wave). The waves are packed next to each other in the context's device arenas, wherever they lie on the host, so
@@ -820,6 +914,10 @@ static int packed_waves(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in,
                         uint8_t *h_out, const uint64_t *out_off, const uint64_t *out_cap, uint64_t *out_size, uint32_t *status,
                         const std::vector<uint64_t> &cuts, bool intra)
 {
+    // PNG: per-image size of the filtered scanlines when every file of the batch is stb-shaped (else empty)
+    std::vector<uint64_t> png_est;
+    if (kind == 2 && png_all_stb_shaped(n, h_in, in_off, in_size, png_est) == false) png_est.clear();
+    const uint64_t *png_hints = png_est.empty() ? nullptr : png_est.data();
     const int nw = (int)cuts.size() - 1;
     cudaStream_t s = ctx->stream;
     // descriptor block: in_off, in_size, out_off, out_cap, out_size (u64 x n each), status + order (u32 x n each)
@@ -882,38 +980,61 @@ static int packed_waves(dbg_ctx *ctx, int kind, uint64_t n, const uint8_t *h_in,
     // number of hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and with wave-by-wave issue the
     // upload of wave k+8 sits behind the download of wave k, i.e. behind wave k's kernels (measured with
     // DBG_WAVE_TRACE: the second half of the waves did not start before the first half had finished).
+    // The uploads all go through ONE stream, in wave order: spread over the waves' streams they complete in whatever
+    // order the copy queues pick (measured with DBG_WAVE_TRACE: 0, 4, 1, 5, ...), and a wave that is processed early
+    // would wait for an upload that was queued late.
     int rc = DBG_OK;
+    // PNG: the uploads all go through ONE stream (see above); gzip / deflate: through the waves' own streams (measured:
+    // 155 ms per cfg2 call against 193 ms through one upload stream -- the kernels of 16 waves then start in two groups)
+    const bool one_up = kind == 2;
+    if (one_up && cudaStreamWaitEvent(ctx->up_stream, ctx->wave_ready, 0) != cudaSuccess) rc = DBG_ERR_CUDA;
     for (int k = 0; k < nw && rc == DBG_OK; k++) {
         const Wave &w = wv[k];
         Slot &sl = ctx->slot[k];
-        cudaStream_t ws = sl.stream;
-        cudaError_t e = cudaStreamWaitEvent(ws, ctx->wave_ready, 0);
+        cudaStream_t ws = sl.stream, us = one_up ? ctx->up_stream : ws;
+        cudaError_t e = one_up ? cudaSuccess : cudaStreamWaitEvent(ws, ctx->wave_ready, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + w.di, h_in + w.hi0, w.hi1 - w.hi0, cudaMemcpyHostToDevice, us);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_in + w.di + (w.hi1 - w.hi0), 0, 64, us);  // what readers see behind the last item
+        if (e == cudaSuccess && one_up) e = cudaEventRecord(sl.uploaded, us);
+        if (e == cudaSuccess && one_up) e = cudaStreamWaitEvent(ws, sl.uploaded, 0);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ws, sl.done, 0);  // a device-resident call may still be using this slot's scratch
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + w.di, h_in + w.hi0, w.hi1 - w.hi0, cudaMemcpyHostToDevice, ws);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_in + w.di + (w.hi1 - w.hi0), 0, 64, ws);  // what readers see behind the last item
         if (e != cudaSuccess) {
             set_err(ctx, "packed batch, upload of wave %d: %s", k, cudaGetErrorString(e));
             rc = DBG_ERR_CUDA;
         }
         if (trace) cudaEventRecord(tev[3 * k], ws);
     }
-    for (int k = 0; k < nw && rc == DBG_OK; k++) {
+    for (int k = 0; k < nw && rc == DBG_OK && kind == 2; k++) {
+        // PNG: when the host has seen that every file is what stb writes (one IDAT, one final fixed-Huffman block),
+        // the lane-serial path gets its sizes as hints and the wave is enqueued without ever waiting for the device:
+        // the waves then run first in, first out, and the download of one overlaps the kernels of the next. A mixed
+        // batch takes the read-back route (two host waits per wave).
         const Wave &w = wv[k];
         Slot &sl = ctx->slot[k];
         const uint64_t b = w.b, m = w.e - w.b;
-        if (kind == 2)
-            rc = png_device_slot(ctx, sl, m, d_in, dd + b, dd + n + b, d_out, dd + 2 * n + b, dd + 3 * n + b, d_status + b, w.tot_in,
-                                 w.tot_out, sl.stream);
-        else
-            rc = inflate_device_slot(ctx, sl, kind == 1, intra, m, d_in, dd + b, dd + n + b, d_out, dd + 2 * n + b, dd + 3 * n + b,
-                                     dd + 4 * n + b, d_status + b, d_order + b, sl.stream);
-        if (trace) cudaEventRecord(tev[3 * k + 1], sl.stream);
-        // PNG waves synchronise the host (lane-serial path), so their downloads are issued wave by wave: the download
-        // of wave k then overlaps the kernels of wave k + 1
-        if (kind == 2 && rc == DBG_OK) {
-            if (cudaMemcpyAsync(h_out + w.ho0, d_out + w.dout, w.ho1 - w.ho0, cudaMemcpyDeviceToHost, sl.stream) != cudaSuccess) rc = DBG_ERR_CUDA;
-            if (trace) cudaEventRecord(tev[3 * k + 2], sl.stream);
+        FxHints hints;
+        hints.have = png_hints != nullptr;
+        if (hints.have) {
+            hints.total_in = w.tot_in;
+            for (uint64_t i = w.b; i < w.e; i++) {
+                hints.max_in = std::max(hints.max_in, in_size[i]);
+                hints.cells_bound += png_hints[i];
+            }
         }
+        rc = png_device_slot(ctx, sl, m, d_in, dd + b, dd + n + b, d_out, dd + 2 * n + b, dd + 3 * n + b, d_status + b, w.tot_in,
+                             w.tot_out, sl.stream, hints);
+        if (trace) cudaEventRecord(tev[3 * k + 1], sl.stream);
+        if (rc == DBG_OK && cudaMemcpyAsync(h_out + w.ho0, d_out + w.dout, w.ho1 - w.ho0, cudaMemcpyDeviceToHost, sl.stream) != cudaSuccess)
+            rc = DBG_ERR_CUDA;
+        if (trace) cudaEventRecord(tev[3 * k + 2], sl.stream);
+    }
+    for (int k = 0; k < nw && rc == DBG_OK && kind != 2; k++) {
+        const Wave &w = wv[k];
+        Slot &sl = ctx->slot[k];
+        const uint64_t b = w.b, m = w.e - w.b;
+        rc = inflate_device_slot(ctx, sl, kind == 1, intra, m, d_in, dd + b, dd + n + b, d_out, dd + 2 * n + b, dd + 3 * n + b,
+                                 dd + 4 * n + b, d_status + b, d_order + b, sl.stream);
+        if (trace) cudaEventRecord(tev[3 * k + 1], sl.stream);
     }
     if (kind != 2)
         for (int k = 0; k < nw && rc == DBG_OK; k++) {

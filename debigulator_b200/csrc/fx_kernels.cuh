@@ -44,6 +44,8 @@ struct FxBatch {
     uint32_t chunk_bytes;        // compressed bytes per chunk (one lane each)
     uint32_t group_chunks;       // chunks per group (one expansion warp and one marker domain each)
     uint32_t extra_cap;
+    uint64_t cells_cap, tok_cap;  // capacities of the cell / token buffers (a stream that does not fit is handed back)
+    uint64_t *stats;              // per context, never reset: [0] streams decoded here, [1] handed back, [2] extra survivors
     FxSummary *summary;
     // per stream
     uint32_t *flag;         // 1 = on this path
@@ -126,7 +128,10 @@ __global__ void __launch_bounds__(FX_WARPS_PER_CTA * 32) fx_head_kernel(FxBatch 
         uint32_t base = 0;
         if (ln == 0) {
             b.nsurv[t] = ns;
-            if (ns > 1) base = atomicAdd(&b.summary->n_extra, ns - 1);
+            if (ns > 1) {
+                base = atomicAdd(&b.summary->n_extra, ns - 1);
+                atomicAdd((unsigned long long *)&b.stats[2], (unsigned long long)(ns - 1));
+            }
         }
         if (ns > 1) {  // rare: more than one chain is left; every one of them becomes a work item
             base = simt::shfl(base, 0);
@@ -270,17 +275,34 @@ __global__ void __launch_bounds__(FX_WARPS_PER_CTA * 32) fx_chain_kernel(FxBatch
             b.g_flag[gb + g] = gf;
         }
         if (ln == 0) {
+            uint64_t cb = 0, tb = 0;
+            if (!redo && st == ST_OK) {
+                // room in the cell / token buffers? (sized exactly by the host when it read the counters back, by an
+                // upper bound / an estimate when it did not wait for them)
+                cb = atomicAdd((unsigned long long *)&b.summary->cells_used, (unsigned long long)pos);
+                tb = atomicAdd((unsigned long long *)&b.summary->tok_used, (unsigned long long)tok);
+                if (cb + pos > b.cells_cap || tb + tok > b.tok_cap) redo = true;
+            }
             if (redo) {
                 b.redo[s] = 1;
                 b.cell_base[s] = 0;
                 b.tok_base[s] = 0;
                 atomicAdd(&b.summary->n_redo, 1u);
+                atomicAdd((unsigned long long *)&b.stats[1], 1ull);
             } else {
                 b.status[s] = st;
                 b.out_size[s] = st == ST_OK ? pos : 0;
-                const bool go_on = st == ST_OK;
-                b.cell_base[s] = go_on ? atomicAdd((unsigned long long *)&b.summary->cells_used, (unsigned long long)pos) : 0;
-                b.tok_base[s] = go_on ? atomicAdd((unsigned long long *)&b.summary->tok_used, (unsigned long long)tok) : 0;
+                b.cell_base[s] = cb;
+                b.tok_base[s] = tb;
+                atomicAdd((unsigned long long *)&b.stats[0], 1ull);
+            }
+        }
+        redo = simt::shfl(redo ? 1u : 0u, 0) != 0;
+        if (redo) {  // (decided after the groups were written) nothing of this stream may be expanded
+            for (uint32_t g = ln; g < ng; g += 32) {
+                b.g_flag[gb + g] = CH_IDLE;
+                b.g_out_len[gb + g] = 0;
+                b.g_ntok[gb + g] = 0;
             }
         }
         simt::syncwarp();

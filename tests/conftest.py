@@ -35,7 +35,14 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def manifest():
     with open(os.path.join(GOLDEN, "manifest.json")) as f:
-        return json.load(f)
+        m = json.load(f)
+    # round-2 additions (tests/golden/make_golden_r2.py): negative / edge vectors and four more fixtures
+    with open(os.path.join(GOLDEN, "manifest_r2.json")) as f:
+        r2 = json.load(f)
+    m["png"] += r2["png"]
+    m["gz"] += r2["gz"]
+    m["fixtures"].update(r2["fixtures"])
+    return m
 
 
 @pytest.fixture(scope="session")

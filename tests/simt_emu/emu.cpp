@@ -404,6 +404,7 @@ static void png_body(void *p)
     if (st == dbg::ST_OK) {
         uint64_t est = (uint64_t)info.w * info.h * 4 + info.h + 1, ssize = 0;
         st = dbg::inflate_warp(a->ism, zp, zs, a->scan, est, &ssize);
+        simt::syncwarp();  // a kernel boundary in the product: the last deferred match store of one lane is read by another below
         if (st == dbg::ST_OK) {
             uint64_t need = (uint64_t)info.h * ((uint64_t)info.w * info.bpp + 1);
             if (a->scan[0] > 4) st = dbg::ST_PNG_FILTER;
