@@ -75,6 +75,8 @@ def load_library():
     L.dbg_bsplit_stats.restype = i32
     L.dbg_fx_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.dbg_fx_stats.restype = i32
+    L.dbg_lane_stats.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.dbg_lane_stats.restype = i32
     L.dbg_synchronize.argtypes = [vp]
     L.dbg_synchronize.restype = i32
     for name in ("dbg_inflate_batch", "dbg_decode_gz_batch"):
@@ -202,6 +204,12 @@ class Context:
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         self._check(self.L.dbg_fx_stats(self.h, C.byref(a), C.byref(b), C.byref(c)), "dbg_fx_stats")
         return int(a.value), int(b.value), int(c.value)
+
+    def lane_stats(self):
+        """(attempts, whole blocks, prefixes, chunks expanded from tokens, chunks decoded twice) of the block-split path."""
+        v = (C.c_uint32 * 5)()
+        self._check(self.L.dbg_lane_stats(self.h, v), "dbg_lane_stats")
+        return tuple(int(x) for x in v)
 
     def synchronize(self):
         self._check(self.L.dbg_synchronize(self.h), "dbg_synchronize")

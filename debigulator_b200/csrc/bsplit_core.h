@@ -228,7 +228,7 @@ DBG_DEV uint64_t find_block_start(SearchSmem *q, const uint16_t *kraft12, const 
 template <int SINK>
 DBG_DEV ChunkResult decode_block_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint64_t start_bit, uint64_t stop_bit,
                                        uint16_t *cells, uint32_t cell_cap, uint64_t abs_base, uint32_t *tok = nullptr,
-                                       uint32_t tok_cap = 0)
+                                       uint32_t tok_cap = 0, bool lanes = false, uint32_t *lb_stats = nullptr)
 {
     ChunkResult r;
     Window w;
@@ -247,6 +247,8 @@ DBG_DEV ChunkResult decode_block_chunk(InflateSmem *sm, const uint8_t *in, uint6
     k.tok = tok;
     k.ntok = 0;
     k.tok_cap = tok_cap;
+    k.lanes = lanes;
+    k.lb_stats = lb_stats;
     uint32_t end = BLK_FINAL;
     const uint32_t st = inflate_blocks<SINK>(w, g, sm, k, stop_bit == BS_NONE ? BS_NONE : stop_bit + off, end);
     if (SINK == SINK_U16) flush_pending16(k.pd);

@@ -60,6 +60,10 @@ struct BsBatch {
     uint64_t *tok_stream_base;  // per stream: first token slot
     uint32_t *c_ntok;           // per region: symbols seen by the count pass
     uint32_t tok_per_byte;      // token slots per compressed byte; a chunk that needs more is Huffman-decoded again
+    uint32_t lanes;             // the count pass may decode blocks lane-parallel (lane_decode_block, inflate_core.h)
+    uint32_t dyn_all;           // every stream of >= min_bytes that opens with a dynamic block takes this path
+    uint32_t *lb_stats;         // per context, never reset: attempts / whole blocks / prefixes of lane_decode_block,
+                                // [3] chunks whose tokens were expanded, [4] chunks decoded a second time instead
 };
 
 // Token area of the chunk that starts at stream bit `start` and ends at the next hint (or the stream end).
@@ -90,6 +94,9 @@ __global__ void bs_classify_kernel(BsBatch b)
     const uint64_t size = b.in_size[s], cap = b.out_cap[s];
     uint64_t thr = (b.summary->total_in / b.resident_warps) * b.factor_q / 4;
     if (thr < b.min_bytes) thr = b.min_bytes;
+    // lane-parallel count pass: a stream that opens with a DYNAMIC block is worth this path whatever its size (its block
+    // headers are found by the search, so every block gets its own warp and its own 32 lanes)
+    if (b.dyn_all && size >= b.min_bytes && ((b.pre_status && b.pre_status[s]) ? 0u : ((b.in_base[b.in_off[s]] >> 1) & 3)) == 2) thr = b.min_bytes;
     uint32_t flag = 0;
     const bool ok = (!b.pre_status || b.pre_status[s] == 0) && (!b.taken || b.taken[s] == 0) && size >= thr && cap >= size &&
                     size < (1ull << 31) && cap < (1ull << 32) - 1024;
@@ -196,7 +203,8 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_count_kernel(BsBatch
         ChunkResult r;
         if (b.tok)
             r = decode_block_chunk<SINK_TOKENS>(sm, b.in_base + b.in_off[s], b.in_size[s], start, next, nullptr, 0, 0,
-                                                b.tok + bs_tok_base(b, s, start), bs_tok_cap(b, s, start, next));
+                                                b.tok + bs_tok_base(b, s, start), bs_tok_cap(b, s, start, next), b.lanes != 0,
+                                                b.lb_stats);
         else
             r = decode_block_chunk<SINK_COUNT>(sm, b.in_base + b.in_off[s], b.in_size[s], start, next, nullptr, 0, 0);
         if (simt::lane() == 0) {
@@ -229,7 +237,15 @@ __global__ void bs_chain_kernel(BsBatch b)
             b.c_out_len[t] = 0;
             continue;
         }
-        if (cand != expected) {  // the previous chunk stepped over this hint: not a block boundary
+        if (cand < expected) {
+            // the previous chunk stepped over this hint: it was no block boundary. That chunk went on to the first real
+            // boundary behind it (bs_count_kernel decodes "to the first block boundary at or past the next hint"), so
+            // the hint is simply dropped; the chain goes on with the chunk that starts where the previous one ended.
+            b.c_flag[t] = CH_IDLE;
+            b.c_out_len[t] = 0;
+            continue;
+        }
+        if (cand != expected) {  // a gap: no chunk starts where the previous one ended
             fail = true;
             b.c_flag[t] = CH_IDLE;
             b.c_out_len[t] = 0;
@@ -288,11 +304,13 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_decode_kernel(BsBatc
             // every symbol of this chunk was recorded by the count pass: expand the tokens
             const uint32_t st = expand_tokens_warp(b.tok + bs_tok_base(b, s, b.cand[t]), b.c_ntok[t], cells, b.c_out_off[t],
                                                    &r.out_bytes);
+            if (simt::lane() == 0 && b.lb_stats) atomicAdd(&b.lb_stats[3], 1u);
             r.flag = st ? CH_ERR + st : b.c_flag[t];
             if (st) r.out_bytes = b.c_out_len[t];
         } else {
             r = decode_block_chunk<SINK_U16>(sm, b.in_base + b.in_off[s], b.in_size[s], b.cand[t], stop, cells, b.c_out_len[t],
                                              b.c_out_off[t]);
+            if (simt::lane() == 0 && b.lb_stats) atomicAdd(&b.lb_stats[4], 1u);
         }
         if (simt::lane() == 0) {
             uint32_t st = ST_OK;

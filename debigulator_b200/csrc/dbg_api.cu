@@ -106,6 +106,9 @@ struct dbg_ctx {
     uint32_t bsplit_tok_per_byte = 4;             // token slots per compressed byte (0 = no tokens: decode twice)
     uint64_t bsplit_tok_max_bytes = 24ull << 30;  // the token area never grows beyond this
     bool bsplit = true;
+    bool bsplit_lanes = true;       // the count pass decodes Huffman blocks lane-parallel (lane_decode_block)
+    int bsplit_all = 0;             // 1: every stream of >= bsplit_min_bytes takes the block-split path, not only the batch's
+                                    // outliers; 2: every such stream that opens with a dynamic block
     uint64_t bsplit_min_bytes = dbg::BS_MIN_BYTES;
     uint32_t bsplit_factor_q = 8;
     uint32_t bsplit_region = dbg::REGION_BYTES, bsplit_region_min = 16384;
@@ -204,8 +207,8 @@ extern "C" dbg_ctx *dbg_create(int device)
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->wave_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = ctx->d_stats.reserve(64);
-    if (e == cudaSuccess) e = cudaMemset(ctx->d_stats.p, 0, 64);
+    if (e == cudaSuccess) e = ctx->d_stats.reserve(128);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_stats.p, 0, 128);
     const size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dbg::inflate_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85);
@@ -222,6 +225,8 @@ extern "C" dbg_ctx *dbg_create(int device)
     if (const char *v = getenv("DBG_WAVES")) ctx->waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(v)));
     if (const char *v = getenv("DBG_PNG_WAVES")) ctx->png_waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(v)));
     if (const char *v = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(v) != 0;
+    if (const char *v = getenv("DBG_BSPLIT_LANES")) ctx->bsplit_lanes = atoi(v) != 0;
+    if (const char *v = getenv("DBG_BSPLIT_ALL")) ctx->bsplit_all = atoi(v);
     if (const char *v = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(v));
     if (const char *v = getenv("DBG_BSPLIT_TOKENS")) ctx->bsplit_tok_per_byte = (uint32_t)std::min(8, std::max(0, atoi(v)));
     if (const char *v = getenv("DBG_BSPLIT_REGION")) ctx->bsplit_region = (uint32_t)std::min(1 << 20, std::max(4096, atoi(v)));
@@ -280,6 +285,18 @@ extern "C" int dbg_fx_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *han
     if (streams) *streams = v[0];
     if (handed_back) *handed_back = v[1];
     if (extra_runs) *extra_runs = v[2];
+    return DBG_OK;
+}
+
+// Diagnostics of the block-split path's count / expansion passes, counted on the device: v[0] blocks where the
+// lane-parallel decode was attempted, v[1] blocks it decoded whole, v[2] blocks it decoded a prefix of, v[3] chunks
+// whose tokens were expanded, v[4] chunks that had to be Huffman-decoded a second time. Waits for the device.
+extern "C" int dbg_lane_stats(const dbg_ctx *ctx, uint32_t v[5])
+{
+    if (!ctx || !v) return DBG_ERR_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(v, (uint64_t *)ctx->d_stats.p + 4, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return DBG_ERR_CUDA;
     return DBG_OK;
 }
 
@@ -579,7 +596,14 @@ static int run_bsplit(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t 
     b.out_size = a.out_size; b.status = a.status; b.pre_status = a.pre_status; b.taken = taken; b.n = n;
     b.resident_warps = (uint32_t)ctx->sm_count * ctx->inflate_ctas_per_sm * dbg::INFLATE_WARPS_PER_CTA;
     b.min_bytes = ctx->bsplit_min_bytes;
-    b.factor_q = ctx->bsplit_factor_q;
+    b.lanes = (ctx->bsplit_lanes && ctx->bsplit_tok_per_byte) ? 1u : 0u;
+    b.lb_stats = (uint32_t *)((uint64_t *)ctx->d_stats.p + 4);
+    // which streams: those that would keep one warp busy clearly longer than the batch's fair share (factor_q / 4 x batch
+    // bytes / resident warps). With lane-parallel blocks EVERY stream of >= min_bytes could take this path (DBG_BSPLIT_ALL=1),
+    // but measured on cfg2 that loses: search + count + expansion + resolve cost ~40 warp instructions per symbol, against
+    // ~64 for the plain warp-per-stream kernel that needs no second pass, no cells and no tokens
+    b.factor_q = ctx->bsplit_all == 1 ? 0u : ctx->bsplit_factor_q;
+    b.dyn_all = (ctx->bsplit_all == 2 && b.lanes) ? 1u : 0u;
     b.summary = (dbg::BsSummary *)p;
     b.cell_base = (uint64_t *)(p + 256);
     b.tok_stream_base = b.cell_base + n;
@@ -637,6 +661,7 @@ static int run_bsplit(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t 
             (void)cudaGetLastError();  // no room for tokens: the second pass decodes the Huffman codes again
         }
     }
+    if (!b.tok) b.lanes = 0;
     const size_t smem = sizeof(dbg::InflateSmem) * dbg::BS_WARPS_PER_CTA;
     const uint32_t grid = std::min<uint32_t>((T + dbg::BS_WARPS_PER_CTA - 1) / dbg::BS_WARPS_PER_CTA,
                                              (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);

@@ -55,50 +55,6 @@ DBG_DEV void fx_build_luts(FxLuts *L, uint32_t tid, uint32_t nthreads)
     for (uint32_t i = tid; i < 32; i += nthreads) L->dist[i] = make_entry<K_DIST>(simt::brev(i) >> 27, 5);
 }
 
-// Per-lane bit reader straight over global memory (every lane is somewhere else in the batch, so there is
-// nothing to stage cooperatively; consecutive words of one lane hit the same L1 line).
-struct LaneBits {
-    const uint32_t *a;  // 4-byte aligned address at or below the stream start
-    uint32_t boff;      // bit offset of the stream start inside a[0]
-    uint32_t last;      // index of the last word before the 16-byte boundary at or after the stream end (readable by contract,
-                        // the same bytes the warp-per-stream reader sees); words past it read as zero
-    uint32_t widx;      // next word to fetch
-    uint32_t nb;        // valid bits in buf (>= 32 whenever a symbol is decoded)
-    uint64_t buf;       // next stream bits, LSB first
-
-    DBG_DEVM uint32_t word(uint32_t i) const { return i <= last ? simt::ldg_u32(a + i) : 0u; }
-    DBG_DEVM void open(const uint8_t *in, uint64_t in_size)
-    {
-        const uintptr_t p = (uintptr_t)in;
-        a = (const uint32_t *)(p & ~(uintptr_t)3);
-        boff = 8 * (uint32_t)(p & 3);
-        last = (uint32_t)((((p + in_size + 15) & ~(uintptr_t)15) - (p & ~(uintptr_t)3)) >> 2) - 1;
-    }
-    DBG_DEVM void seek(uint64_t stream_bit)
-    {
-        const uint64_t abit = stream_bit + boff;
-        widx = (uint32_t)(abit >> 5);
-        const uint32_t sh = (uint32_t)abit & 31;
-        const uint64_t two = (uint64_t)word(widx) | ((uint64_t)word(widx + 1) << 32);
-        buf = two >> sh;
-        nb = 64 - sh;
-        widx += 2;
-    }
-    DBG_DEVM void refill()
-    {
-        if (nb <= 32) {
-            buf |= (uint64_t)word(widx) << nb;
-            widx++;
-            nb += 32;
-        }
-    }
-    DBG_DEVM void drop(uint32_t n)
-    {
-        buf >>= n;
-        nb -= n;
-    }
-};
-
 // One symbol at the reader's position. Returns its kind; *nbits = code + extra bits, *len = output bytes,
 // *tok = its token (TOKEN_MATCH | length << 16 | distance - 1, or the literal byte).
 enum : uint32_t { FXK_LIT = 0, FXK_MATCH = 1, FXK_EOB = 2, FXK_BAD = 3 };
@@ -139,42 +95,6 @@ struct FxRun {
     uint32_t out;       // bytes produced
     uint32_t ntok;      // symbols seen (end-of-block not counted)
     uint32_t flag;      // CH_RUN while running, else CH_EOB / CH_Q2 / CH_ERR + status
-};
-
-// Token writer of one lane: single stores up to the first 16-byte boundary, then four tokens per store (every
-// lane writes somewhere else, so a 4-byte store costs the memory system what a 16-byte one does).
-struct TokOut {
-    uint32_t *p;
-    uint32_t q0, q1, q2;
-    uint32_t k;
-    DBG_DEVM void open(uint32_t *dst)
-    {
-        p = dst;
-        q0 = q1 = q2 = 0;
-        k = 0;
-    }
-    DBG_DEVM void put(uint32_t t)
-    {
-        if (k == 3) {
-            simt::st_u32x4(p, q0, q1, q2, t);
-            p += 4;
-            k = 0;
-        } else if (k == 0 && ((uintptr_t)p & 15)) {
-            *p++ = t;
-        } else {
-            q0 = q1;
-            q1 = q2;
-            q2 = t;
-            k++;
-        }
-    }
-    DBG_DEVM void close()
-    {
-        if (k == 3) *p++ = q0;
-        if (k >= 2) *p++ = q1;
-        if (k >= 1) *p++ = q2;
-        k = 0;
-    }
 };
 
 // Decodes symbols while rel < stop. `q2r` is the rule-Q2 limit relative to the chunk (no symbol may start at

@@ -461,6 +461,8 @@ struct Sink {
     uint64_t abs_base;  // SINK_U16: stream output offset of out16[0] (markers may not reach before the stream)
     uint32_t *tok;      // SINK_TOKENS: token area, `tok_cap` entries; ntok keeps counting past it (= overflow)
     uint32_t ntok, tok_cap;
+    bool lanes;         // SINK_TOKENS: blocks may be decoded lane-parallel (lane_decode_block)
+    uint32_t *lb_stats; // optional counters of lane_decode_block: [0] attempts, [1] whole blocks, [2] prefixes
     PendingStore pd;
 };
 
@@ -783,6 +785,329 @@ DBG_DEV void copy_stored_u16(uint16_t *dst, const uint8_t *src, uint32_t len)
     for (uint32_t i = (uint32_t)simt::lane(); i < len; i += 32) dst[i] = src[i];
 }
 
+// Per-lane bit reader straight over global memory (every lane is somewhere else in the batch, so there is
+// nothing to stage cooperatively; consecutive words of one lane hit the same L1 line).
+struct LaneBits {
+    const uint32_t *a;  // 4-byte aligned address at or below the stream start
+    uint32_t boff;      // bit offset of the stream start inside a[0]
+    uint32_t last;      // index of the last word before the 16-byte boundary at or after the stream end (readable by contract,
+                        // the same bytes the warp-per-stream reader sees); words past it read as zero
+    uint32_t widx;      // next word to fetch
+    uint32_t nb;        // valid bits in buf (>= 32 whenever a symbol is decoded)
+    uint64_t buf;       // next stream bits, LSB first
+
+    DBG_DEVM uint32_t word(uint32_t i) const { return i <= last ? simt::ldg_u32(a + i) : 0u; }
+    DBG_DEVM void open(const uint8_t *in, uint64_t in_size)
+    {
+        const uintptr_t p = (uintptr_t)in;
+        a = (const uint32_t *)(p & ~(uintptr_t)3);
+        boff = 8 * (uint32_t)(p & 3);
+        last = (uint32_t)((((p + in_size + 15) & ~(uintptr_t)15) - (p & ~(uintptr_t)3)) >> 2) - 1;
+    }
+    DBG_DEVM void seek(uint64_t stream_bit)
+    {
+        const uint64_t abit = stream_bit + boff;
+        widx = (uint32_t)(abit >> 5);
+        const uint32_t sh = (uint32_t)abit & 31;
+        const uint64_t two = (uint64_t)word(widx) | ((uint64_t)word(widx + 1) << 32);
+        buf = two >> sh;
+        nb = 64 - sh;
+        widx += 2;
+    }
+    DBG_DEVM void refill()
+    {
+        if (nb <= 32) {
+            buf |= (uint64_t)word(widx) << nb;
+            widx++;
+            nb += 32;
+        }
+    }
+    DBG_DEVM void drop(uint32_t n)
+    {
+        buf >>= n;
+        nb -= n;
+    }
+};
+
+// Token writer of one lane: single stores up to the first 16-byte boundary, then four tokens per store (every
+// lane writes somewhere else, so a 4-byte store costs the memory system what a 16-byte one does).
+struct TokOut {
+    uint32_t *p;
+    uint32_t q0, q1, q2;
+    uint32_t k;
+    DBG_DEVM void open(uint32_t *dst)
+    {
+        p = dst;
+        q0 = q1 = q2 = 0;
+        k = 0;
+    }
+    DBG_DEVM void put(uint32_t t)
+    {
+        if (k == 3) {
+            simt::st_u32x4(p, q0, q1, q2, t);
+            p += 4;
+            k = 0;
+        } else if (k == 0 && ((uintptr_t)p & 15)) {
+            *p++ = t;
+        } else {
+            q0 = q1;
+            q1 = q2;
+            q2 = t;
+            k++;
+        }
+    }
+    DBG_DEVM void close()
+    {
+        if (k == 3) *p++ = q0;
+        if (k >= 2) *p++ = q1;
+        if (k >= 1) *p++ = q2;
+        k = 0;
+    }
+};
+
+// How a decode run over part of a stream ended (chunk-parallel paths).
+enum : uint32_t { CH_RUN = 0, CH_EOB = 1, CH_Q2 = 2, CH_IDLE = 3, CH_ERR = 16 };  // CH_ERR + status
+
+// ------------------------------------------------ lane-parallel block decode --
+// The symbol walk above spends ~64 warp instructions per symbol because 32 lanes cooperate on ONE position of the
+// stream. When the symbols only have to be RECORDED (SINK_TOKENS: the sizes pass of the block-split path; a later
+// kernel expands the tokens), the lanes can instead each decode a piece of the block on their own, ~70 thread
+// instructions per symbol, i.e. ~2-3 warp instructions:
+//
+//   extent   the bits from the block's first symbol to where the block is presumed to end (the caller's stop bit =
+//            the next block-boundary hint, capped) are cut into up to 32 equal sub-chunks, one per lane.
+//   merge    lane j > 0 does not know where a symbol starts in its sub-chunk. A symbol is at most 48 bits long
+//            (15 + 5 + 15 + 13), so one of the first 48 bit positions is a real symbol start. The lane sweeps the set
+//            of positions reachable from ANY of those 48 starts in increasing order (a 64-bit reach mask anchored at the
+//            lowest one: decode there, add "position + symbol length", move on), so every position is decoded once
+//            however many of the 48 chains run through it. Huffman chains merge quickly; the sweep stops as soon as ONE
+//            reachable position is left: every chain that is still alive runs through it -- the lane's entry point.
+//            Nothing is guessed: if the chains have not merged half way through the sub-chunk, the lanes are not used.
+//   runs     lane j decodes from its entry point to lane j + 1's, recording tokens into its own stretch of the chunk's
+//            token area. It must arrive there EXACTLY (its path entered sub-chunk j + 1 on one of the 48 starts).
+//   chain    from lane 0 (the real start of the block) along the lanes until the run that meets end-of-block; what
+//            the later lanes decoded (bits behind the end of the block) is dropped. The runs' tokens are moved
+//            together. Anything irregular on that chain (bad code, the rule-Q2 limit, a run that misses its target, a
+//            token stretch that is too small) makes the caller decode the block again the ordinary way, so the status
+//            and every byte are those of decode_symbols().
+// The concatenated runs are the sequential decode: each starts where the previous one ended and all use one step
+// function with the block's own tables (LUTs + slow_decode for codes longer than the LUT index, rule Q5 included).
+constexpr uint32_t LB_MIN_SUB = 2048;         // smallest sub-chunk, bits
+constexpr uint32_t LB_MAX_EXTENT = 1u << 20;  // largest presumed extent, bits (128 KiB of compressed data)
+constexpr uint32_t LB_NOHINT_EXTENT = 3u << 17;  // presumed extent when the caller has no hint, bits (48 KiB)
+constexpr uint32_t LB_MERGE_BITS = 1024;      // chains that have not merged after this many bits are given up
+constexpr uint32_t LB_STARTS = 48;            // candidate entry offsets per sub-chunk = longest possible symbol
+enum : uint32_t { LBK_LIT = 0, LBK_MATCH = 1, LBK_EOB = 2, LBK_BAD = 3 };
+
+// One symbol with the block's tables; consumes it. *nbits = its length, *len = output bytes, *tok = its token.
+DBG_DEV uint32_t lb_symbol(const InflateSmem *sm, const BlockTables &bt, LaneBits &br, uint32_t *nbits, uint32_t *len, uint32_t *tok)
+{
+    br.refill();  // >= 33 bits: literal/length code (<= 15) + extra bits (<= 5)
+    uint32_t x = (uint32_t)br.buf;
+    uint32_t e = sm->lit_lut[x & ((1u << LIT_ROOT) - 1)];
+    if ((e & 15) == 0) {
+        e = slow_decode<K_LITLEN, uint16_t>(x, LIT_ROOT, bt.lit_max, sm->lit_sorted, sm->lit_first, sm->lit_offs, sm->lit_cnt);
+        if (!e) return LBK_BAD;
+    }
+    const uint32_t l1 = e & 15;
+    *len = 1;
+    *tok = e >> 16;
+    *nbits = l1;
+    if (e & E_LIT) {
+        br.drop(l1);
+        return LBK_LIT;
+    }
+    if (e & E_EOB) {
+        br.drop(l1);
+        return LBK_EOB;
+    }
+    if (!(e & E_BASE)) return LBK_BAD;  // litlen 286 / 287
+    const uint32_t xb = (e >> 8) & 31;
+    const uint32_t ln = (e >> 16) + ((x >> l1) & ((1u << xb) - 1));
+    br.drop(l1 + xb);
+    br.refill();  // distance code (<= 15) + extra bits (<= 13)
+    x = (uint32_t)br.buf;
+    uint32_t e2 = sm->dist_lut[x & ((1u << DIST_ROOT) - 1)];
+    if ((e2 & 15) == 0) {
+        e2 = slow_decode<K_DIST, uint8_t>(x, DIST_ROOT, bt.dist_max, sm->dist_sorted, sm->dist_first, sm->dist_offs, sm->dist_cnt);
+        if (!e2) return LBK_BAD;
+    }
+    if (!(e2 & E_BASE)) return LBK_BAD;  // distance symbols 30 / 31
+    const uint32_t l2 = e2 & 15, xb2 = (e2 >> 8) & 31;
+    const uint32_t dist = (e2 >> 16) + ((x >> l2) & ((1u << xb2) - 1));
+    br.drop(l2 + xb2);
+    *nbits = l1 + xb + l2 + xb2;
+    *len = ln;
+    *tok = TOKEN_MATCH | (ln << 16) | (dist - 1);
+    return LBK_MATCH;
+}
+
+// Entry point of the sub-chunk that starts at ring bit `s0`: the one position all chains from its first LB_STARTS
+// bit offsets run through, or ~0 when they have not merged within `give_up` bits (or all of them died).
+DBG_DEV uint64_t lb_merge_point(const InflateSmem *sm, const BlockTables &bt, const uint8_t *base16, uint64_t end_byte, uint64_t s0,
+                                uint32_t give_up, uint64_t q2_limit)
+{
+    LaneBits br;
+    br.open(base16, end_byte);
+    br.seek(s0);
+    uint64_t reach = (1ull << LB_STARTS) - 1;  // bit i: position anchor + i is reachable
+    uint64_t anchor = s0;
+    for (uint32_t steps = 0; steps < 2 * LB_STARTS + give_up / 2; steps++) {
+        if (reach == 0) return ~0ull;
+        const uint32_t lo32 = (uint32_t)reach;
+        const uint32_t p = lo32 ? (uint32_t)simt::ffs(lo32) - 1 : 31 + (uint32_t)simt::ffs((uint32_t)(reach >> 32));
+        if ((reach >> p) == 1) return anchor + p;  // one position left
+        // move the window to the lowest reachable position
+        if (p) {
+            uint32_t r = p;
+            if (r > 32) {
+                br.refill();
+                br.drop(32);
+                r -= 32;
+            }
+            br.refill();
+            br.drop(r);
+            anchor += p;
+            reach >>= p;
+        }
+        if (anchor - s0 > give_up) return ~0ull;
+        reach &= ~1ull;
+        if (anchor >= q2_limit) continue;  // no symbol may start here (rule Q2): this chain ends
+        LaneBits t = br;  // decode without consuming
+        uint32_t nbits, len, tok;
+        const uint32_t kind = lb_symbol(sm, bt, t, &nbits, &len, &tok);
+        if (kind == LBK_LIT || kind == LBK_MATCH) reach |= 1ull << nbits;  // (end-of-block and bad codes end a chain)
+    }
+    return ~0ull;
+}
+
+enum : uint32_t { LB_UNUSED = 0, LB_DONE = 1, LB_PARTIAL = 2 };
+#ifdef DBG_SIMT_EMU
+static uint32_t g_lb_done = 0, g_lb_tried = 0, g_lb_partial = 0;  // emulator only: outcome counts of lane_decode_block
+#endif
+
+// Lane-parallel decode of the Huffman block whose first symbol is at the window position (tables built).
+//   LB_DONE     the whole block: its tokens are appended to k.tok, k.pos / k.ntok advanced, the window stands behind
+//               the end-of-block code;
+//   LB_PARTIAL  the same for a prefix of the block: the window stands on the symbol where the caller goes on with
+//               decode_symbols() (same tables);
+//   LB_UNUSED   nothing has changed.
+// `counters` (optional): [0] attempts, [1] whole blocks, [2] prefixes.
+DBG_DEV uint32_t lane_decode_block(Window &w, const StreamIn &g, InflateSmem *sm, const BlockTables &bt, Sink &k, uint64_t stop_bit)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint64_t p0 = w.abs_bits();
+    const uint64_t in_end = 8 * g.end_byte;
+    const bool hinted = stop_bit < in_end;
+    const uint64_t ext_end = hinted ? stop_bit : in_end;
+    if (ext_end <= p0) return LB_UNUSED;
+    uint64_t ext = ext_end - p0;
+    // without a hint the block ends somewhere in the rest of the stream: presume what compressors write (zlib closes a
+    // block after 16 K symbols, 30-50 KB); what lies behind the block's end is decoded in vain
+    const uint32_t cap = hinted ? LB_MAX_EXTENT : LB_NOHINT_EXTENT;
+    if (ext > cap) ext = cap;
+    if (ext < 4 * LB_MIN_SUB || k.ntok >= k.tok_cap) return LB_UNUSED;
+    uint32_t sub = ((uint32_t)ext + 31) / 32;
+    if (sub < LB_MIN_SUB) sub = LB_MIN_SUB;
+    sub = (sub + 31) & ~31u;
+    const uint32_t L = ((uint32_t)ext + sub - 1) / sub;  // lanes in use, 4..32
+    const uint32_t stride = (k.tok_cap - k.ntok) / L;    // token slots per lane
+    if (stride < sub / 16) return LB_UNUSED;
+#ifdef DBG_SIMT_EMU
+    if (ln == 0) g_lb_tried++;
+#else
+    if (ln == 0 && k.lb_stats) atomicAdd(&k.lb_stats[0], 1u);
+#endif
+    // merge points. A lane whose chains do not merge (it may be looking at the NEXT block's bits, coded with other
+    // tables) has none; the chain below simply ends before it.
+    uint64_t entry = p0;
+    const uint32_t give_up = sub / 2 < LB_MERGE_BITS ? sub / 2 : LB_MERGE_BITS;
+    if (ln > 0 && ln < L) entry = lb_merge_point(sm, bt, w.base, g.end_byte, p0 + (uint64_t)ln * sub, give_up, g.q2_limit);
+    if (ln >= L) entry = ~0ull;
+    const uint32_t e_lo = simt::shfl_down((uint32_t)entry, 1), e_hi = simt::shfl_down((uint32_t)(entry >> 32), 1);
+    uint64_t target = ((uint64_t)e_hi << 32) | e_lo;  // the next lane's entry point
+    const bool has_target = ln + 1 < L && target != ~0ull;
+    // without one the run may still meet the block's end inside its own sub-chunk
+    if (!has_target) target = p0 + (uint64_t)(ln + 1) * sub + LB_STARTS;
+    // runs
+    uint32_t n = 0, out = 0;
+    uint32_t flag = CH_IDLE;  // CH_RUN: arrived exactly at the next entry point; CH_EOB: met end-of-block; else: the chain ends before this lane
+    uint64_t pos = entry;
+    uint32_t *area = k.tok + k.ntok + (uint64_t)ln * stride;
+    if (entry != ~0ull) {
+        LaneBits br;
+        br.open(w.base, g.end_byte);
+        br.seek(entry);
+        TokOut wr;
+        wr.open(area);
+        flag = CH_RUN;
+        while (pos < target) {
+            if (pos >= g.q2_limit || n >= stride) {
+                flag = CH_ERR;
+                break;
+            }
+            uint32_t nbits, len, tok;
+            const uint32_t kind = lb_symbol(sm, bt, br, &nbits, &len, &tok);
+            if (kind == LBK_BAD) {
+                flag = CH_ERR;
+                break;
+            }
+            pos += nbits;
+            if (kind == LBK_EOB) {
+                flag = CH_EOB;
+                break;
+            }
+            wr.put(tok);
+            n++;
+            out += len;
+        }
+        wr.close();
+        if (flag == CH_RUN && (pos != target || !has_target)) flag = CH_ERR;  // missed the next entry point / nothing to arrive at
+    }
+    // chain: lanes 0 .. the first one that did not simply arrive at its target
+    const uint32_t stops = simt::ballot(flag != CH_RUN);  // never empty: the last lane has no target
+    const uint32_t stop_lane = (uint32_t)simt::ffs(stops) - 1;
+    const bool whole = simt::shfl(flag, (int)stop_lane) == CH_EOB;
+    const uint32_t used = whole ? stop_lane + 1 : stop_lane;  // runs that count
+    if (used == 0) return LB_UNUSED;
+    uint32_t in = ln < used ? n : 0u, io = ln < used ? out : 0u;
+    const uint32_t mine = in;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t yn = simt::shfl_up(in, d), yo = simt::shfl_up(io, d);
+        if (ln >= (uint32_t)d) {
+            in += yn;
+            io += yo;
+        }
+    }
+    const uint32_t total_n = simt::shfl(in, 31), total_out = simt::shfl(io, 31);
+    // where the caller goes on: behind end-of-block, or on the entry point of the first run that does not count
+    const uint64_t resume = whole ? pos : entry;
+    const uint32_t r_lo = simt::shfl((uint32_t)resume, (int)stop_lane), r_hi = simt::shfl((uint32_t)(resume >> 32), (int)stop_lane);
+    // move the runs' tokens together (run 0 is in place); forward copies, the loads of a step before its stores
+    simt::syncwarp();
+    uint32_t *base = k.tok + k.ntok;
+    for (uint32_t j = 1; j < used; j++) {
+        const uint32_t cnt = simt::shfl(mine, (int)j), dst0 = simt::shfl(in - mine, (int)j);
+        const uint32_t *src = base + (uint64_t)j * stride;
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+            const uint32_t i = i0 + ln;
+            const uint32_t v = i < cnt ? src[i] : 0u;
+            simt::syncwarp();
+            if (i < cnt) base[dst0 + i] = v;
+            simt::syncwarp();
+        }
+    }
+    k.ntok += total_n;
+    k.pos += total_out;
+    w.seek_bits(((uint64_t)r_hi << 32) | r_lo);
+#ifdef DBG_SIMT_EMU
+    if (ln == 0) (whole ? g_lb_done : g_lb_partial)++;
+#else
+    if (ln == 0 && k.lb_stats) atomicAdd(&k.lb_stats[whole ? 1 : 2], 1u);
+#endif
+    return whole ? LB_DONE : LB_PARTIAL;
+}
+
 // The block loop of inflate() (inflate.c:896-1950): decodes blocks from the window position, which
 // must be a block header, until the final block has ended (BLK_FINAL), rule Q2 ended the stream
 // (BLK_Q2), or a block boundary at or past ring-coordinate bit `stop_bit` has been reached (BLK_STOP,
@@ -842,6 +1167,13 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
             uint32_t st = read_huffman_tables(w, sm, btype, bt);
             if (st) return st;
             uint32_t why = END_EOB;
+            if (SINK == SINK_TOKENS && k.lanes) {
+                // whole block: next header; a prefix: decode_symbols() below goes on where the lanes stopped
+                if (lane_decode_block(w, g, sm, bt, k, stop_bit) == LB_DONE) {
+                    if (!more) return ST_OK;
+                    continue;
+                }
+            }
             st = decode_symbols<SINK>(w, sm, bt, k, why);
             if (st) return st;
             if (why == END_LIMIT) {  // rule Q2
@@ -880,6 +1212,8 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     k.pd.on = false;
     k.tok = nullptr;
     k.ntok = k.tok_cap = 0;
+    k.lanes = false;
+    k.lb_stats = nullptr;
     uint32_t end;
     const uint32_t st = inflate_blocks<SINK_BYTES>(w, g, sm, k, ~0ull, end);
     if (st) return st;
@@ -911,7 +1245,6 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
 //   resolve   one CTA per stream, chunk after chunk: cells -> bytes, markers
 //             read the already finished output.
 enum { CHUNK_BYTES = 32768 };  // smallest chunk; the host doubles it (up to 8x) for very large batches, see run_split
-enum : uint32_t { CH_RUN = 0, CH_EOB = 1, CH_Q2 = 2, CH_IDLE = 3, CH_ERR = 16 };  // CH_ERR + status
 
 // Lane-local fixed-Huffman size decode of the symbol at ring bit `pos`:
 // returns the symbol's bit length (0 = undecodable) and its output bytes in
@@ -1047,6 +1380,8 @@ DBG_DEV ChunkResult decode_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in
     k.pd.on = false;
     k.tok = nullptr;
     k.ntok = k.tok_cap = 0;
+    k.lanes = false;
+    k.lb_stats = nullptr;
     uint32_t why = END_EOB;
     uint32_t st = decode_symbols<SINK>(w, sm, bt, k, why);
     if (SINK == SINK_U16) flush_pending16(k.pd);

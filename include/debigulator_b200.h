@@ -155,6 +155,11 @@ int dbg_bsplit_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *fallbacks)
  * chunk entry points that needed more than one decode run (strictly periodic symbol streams). Diagnostics only. */
 int dbg_fx_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *handed_back, uint64_t *extra_runs);
 
+/* Diagnostics of the block-split path, counted on the device (waits for it): v[0] Huffman blocks where the lane-parallel
+ * decode was attempted, v[1] blocks it decoded whole, v[2] blocks it decoded a prefix of, v[3] chunks
+ * whose recorded tokens were expanded, v[4] chunks that were Huffman-decoded a second time instead. */
+int dbg_lane_stats(const dbg_ctx *ctx, uint32_t v[5]);
+
 /* Optional timing of the kernel groups, for roofline reports: after dbg_profile_enable(ctx, 1) every group below is
  * bracketed by CUDA events on the stream it runs on. dbg_profile_read_tag() waits for the brackets of one group and
  * returns their summed device time and their number; dbg_profile_read() does that for DBG_PROF_INFLATE and resets

@@ -112,6 +112,7 @@ extern "C" uint32_t emu_inflate(const uint8_t *in, uint64_t in_size, uint8_t *ou
     memset(arena, 0xA5, (arena_sz + 15) & ~(size_t)15);
     uint8_t *src = arena + 16 + (misalign & 15);
     memcpy(src, in, in_size);
+    memset(src + in_size, 0, 16);  // what the host API puts behind every item (and the reference binding behind its input)
     dbg::InflateSmem *sm = (dbg::InflateSmem *)aligned_alloc(16, sizeof(dbg::InflateSmem));
     memset(sm, 0xCD, sizeof(*sm));
     InflateArgs a;
@@ -256,6 +257,7 @@ struct BsArgs {
     int mode;  // 0 search, 1 count, 2 decode, 3 expand tokens
     uint32_t *tok;
     uint32_t tok_cap, ntok, exp_bytes[32], exp_st[32];
+    int lanes;
     uint64_t lo, hi, start, stop;
     uint16_t *cells;
     uint32_t cell_cap;
@@ -269,7 +271,7 @@ static void bs_body(void *p)
     int l = simt::lane();
     if (a->mode == 0) a->found[l] = dbg::find_block_start(a->q, a->kraft, a->in, a->in_size, a->lo, a->hi);
     else if (a->mode == 1 && a->tok)
-        a->res[l] = dbg::decode_block_chunk<dbg::SINK_TOKENS>(a->sm, a->in, a->in_size, a->start, a->stop, nullptr, 0, 0, a->tok, a->tok_cap);
+        a->res[l] = dbg::decode_block_chunk<dbg::SINK_TOKENS>(a->sm, a->in, a->in_size, a->start, a->stop, nullptr, 0, 0, a->tok, a->tok_cap, a->lanes != 0);
     else if (a->mode == 1) a->res[l] = dbg::decode_block_chunk<dbg::SINK_COUNT>(a->sm, a->in, a->in_size, a->start, a->stop, nullptr, 0, 0);
     else if (a->mode == 3) a->exp_st[l] = dbg::expand_tokens_warp(a->tok, a->ntok, a->cells, a->abs_base, &a->exp_bytes[l]);
     else a->res[l] = dbg::decode_block_chunk<dbg::SINK_U16>(a->sm, a->in, a->in_size, a->start, a->stop, a->cells, a->cell_cap, a->abs_base);
@@ -279,13 +281,15 @@ static void bs_body(void *p)
 // region by region through the emulator. Returns the status; 0x4000 = the chain did not close (the
 // product would hand the stream back to the warp-per-stream kernel). *n_chunks = hinted regions used.
 extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
-                                       int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks, uint32_t tok_per_byte)
+                                       int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks, uint32_t tok_per_byte,
+                                       int lanes)
 {
     size_t arena_sz = ((size_t)in_size + 64 + 32 + 15) & ~(size_t)15;
     uint8_t *arena = (uint8_t *)aligned_alloc(16, arena_sz);
     memset(arena, 0xA5, arena_sz);
     uint8_t *src = arena + 16 + (misalign & 15);
     memcpy(src, in, in_size);
+    memset(src + in_size, 0, 16);  // what the host API puts behind every item (and the reference binding behind its input)
     dbg::InflateSmem *sm = (dbg::InflateSmem *)aligned_alloc(16, sizeof(dbg::InflateSmem));
     dbg::SearchSmem q;
     static uint16_t kraft[4096];
@@ -298,6 +302,7 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
     uint32_t *tokens = tok_per_byte ? (uint32_t *)malloc(((size_t)tok_per_byte * in_size + 16) * 4) : nullptr;
     BsArgs a;
     a.sm = sm; a.q = &q; a.kraft = kraft; a.in = src; a.in_size = in_size; a.cells = nullptr; a.tok = nullptr; a.tok_cap = 0;
+    a.lanes = lanes;
     uint32_t status = 0;
     for (uint32_t c = 0; c < nreg; c++) {
         cand[c] = 0;
@@ -323,6 +328,7 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
     for (uint32_t c = 0; c < nreg && !status; c++) {
         ooff[c] = pos;
         if (cand[c] == dbg::BS_NONE || ended || fail) { flag[c] = dbg::CH_IDLE; continue; }
+        if (cand[c] < expected) { flag[c] = dbg::CH_IDLE; continue; }  // a hint the previous chunk stepped over: dropped
         if (cand[c] != expected) { fail = true; flag[c] = dbg::CH_IDLE; continue; }
         (*n_chunks)++;
         if (flag[c] >= dbg::CH_ERR) { status = pos + olen[c] > cap ? (uint32_t)dbg::ST_OUT_OVERFLOW : flag[c] - dbg::CH_ERR; ended = true; flag[c] = dbg::CH_IDLE; continue; }
@@ -364,6 +370,13 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
     }
     free(cand); free(exitb); free(ooff); free(olen); free(flag); free(ntok); free(tokens); free(sm); free(arena);
     return status;
+}
+
+extern "C" void emu_lane_block_stats(uint32_t *tried, uint32_t *done, int reset)
+{
+    *tried = dbg::g_lb_tried;
+    *done = dbg::g_lb_done + dbg::g_lb_partial;
+    if (reset) dbg::g_lb_tried = dbg::g_lb_done = dbg::g_lb_partial = 0;
 }
 
 // ------------------------------------------------------------------- PNG -----
