@@ -254,11 +254,12 @@ def png_corpus(w, h, n_unique, filt, share_tag=None, rank=0, world=1, barrier=No
 
 
 def bench_png(ctx, dbg, dev, torch, name, n, w, h, uniq, peak, steps=3, e2e=True, cpu=True, world=1, max_over_ranks=lambda x: x,
-              barrier=lambda: None):
+              barrier=lambda: None, e2e_images=None):
     from debigulator_b200 import corpus
     n_unique = len(uniq)
     offs, sizes, in_total = pack([u[0] for u in uniq], n)
     rgba = w * h * 4
+    ne = min(n, e2e_images or n)  # images of the end-to-end leg (all of them unless host memory is short at N > 1)
     pinned = e2e
     h_in_t = torch.empty(in_total + 64, dtype=torch.uint8)
     if pinned:
@@ -339,34 +340,37 @@ def bench_png(ctx, dbg, dev, torch, name, n, w, h, uniq, peak, steps=3, e2e=True
                                                "the un-filter (+ 8 B per symbol of tokens, not counted); 4wh written",
                         "kernel_groups_ms": groups}}
     if e2e:
-        h_out_t = torch.empty(n * rgba, dtype=torch.uint8).pin_memory()
+        h_out_t = torch.empty(ne * rgba, dtype=torch.uint8).pin_memory()
         h_out = h_out_t.numpy()
-        ctx.decode_packed(dbg.api.KIND_PNG, h_in, in_off, in_size, h_out, out_off, out_cap)
+        e_in = offs[ne] if ne < n else in_total
+        a4 = (in_off[:ne], in_size[:ne], out_off[:ne], out_cap[:ne])
+        ctx.decode_packed(dbg.api.KIND_PNG, h_in, a4[0], a4[1], h_out, a4[2], a4[3])
         barrier()
         reps = 2
         t0 = time.perf_counter()
         for _ in range(reps):
-            osz, st = ctx.decode_packed(dbg.api.KIND_PNG, h_in, in_off, in_size, h_out, out_off, out_cap)
+            osz, st = ctx.decode_packed(dbg.api.KIND_PNG, h_in, a4[0], a4[1], h_out, a4[2], a4[3])
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0) / reps
-        assert int(st.sum()) == 0 and int(osz.sum()) == n * rgba, f"{name}: e2e failures"
-        for k in (0, 1, n // 2, n - 1):
+        assert int(st.sum()) == 0 and int(osz.sum()) == ne * rgba, f"{name}: e2e failures"
+        for k in (0, 1, ne // 2, ne - 1):
             assert h_out[k * rgba:(k + 1) * rgba].tobytes() == uniq[k % n_unique][1], f"{name}: e2e pixel mismatch"
         # link ceiling: the same arenas copied up and down at once, nothing else running (all ranks together)
         s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         barrier()
         t0 = time.perf_counter()
         with torch.cuda.stream(s_up):
-            d_in.copy_(h_in_t, non_blocking=True)
+            d_in[:e_in].copy_(h_in_t[:e_in], non_blocking=True)
         with torch.cuda.stream(s_dn):
-            h_out_t.copy_(d_out, non_blocking=True)
+            h_out_t.copy_(d_out[:ne * rgba], non_blocking=True)
         torch.cuda.synchronize()
         ct = max_over_ranks(time.perf_counter() - t0)
-        out["e2e"] = {"value": world * n * w * h / dt / 1e6, "unit": "Mpix/s", "rgba_GBps": world * n * rgba / dt / 1e9,
-                      "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(in_total), "d2h_bytes_per_step": int(n * rgba), "steps": reps,
-                      "api": "dbg_decode_batch_packed(kind=PNG), pinned host arenas, overlapped waves",
-                      "link_ceiling": {"h2d_plus_d2h_s": ct, "Mpix_s_if_copies_only": world * n * w * h / ct / 1e6,
-                                       "frac_of_ceiling": ct / dt}}
+        out["e2e"] = {"value": world * ne * w * h / dt / 1e6, "unit": "Mpix/s", "rgba_GBps": world * ne * rgba / dt / 1e9,
+                      "ms_per_step": dt * 1e3, "images_per_gpu": ne, "h2d_bytes_per_step": int(e_in), "d2h_bytes_per_step": int(ne * rgba),
+                      "steps": reps, "api": "dbg_decode_batch_packed(kind=PNG), pinned host arenas, overlapped waves",
+                      "link_ceiling": {"h2d_plus_d2h_s": ct, "Mpix_s_if_copies_only": world * ne * w * h / ct / 1e6,
+                                       "ranks_copying_at_once": world, "per_rank_h2d_GBps": e_in / ct / 1e9,
+                                       "per_rank_d2h_GBps": ne * rgba / ct / 1e9, "frac_of_ceiling": ct / dt}}
         del h_out_t
     if cpu:
         from oracle import checker
@@ -541,8 +545,23 @@ def run_ours(args):
     png = png_large = None
     if args.png:
         uniq3 = png_corpus(PNG_W, PNG_H, PNG_UNIQUE, None, "cfg3" if world > 1 else None, rank, world, barrier)
+        # the end-to-end leg pins ~7.5 MB of host memory per image and rank: all images when the box has room for every
+        # rank's arenas, else half / a quarter of the batch (rank 0 decides for everybody)
+        e2e_n = args.png_images
+        if world > 1:
+            box = [None]
+            if rank == 0:
+                import psutil
+                avail = psutil.virtual_memory().available * 0.7
+                per_image = 4 * PNG_W * PNG_H * 1.85
+                while e2e_n > 256 and world * e2e_n * per_image > avail:
+                    e2e_n //= 2
+                box = [e2e_n]
+            dist.broadcast_object_list(box, src=0)
+            e2e_n = box[0]
         png = bench_png(ctx, dbg, dev, torch, "cfg3", args.png_images, PNG_W, PNG_H, uniq3, peak, e2e=True,
-                        cpu=(rank == 0 and world == 1 and not args.no_cpu), world=world, max_over_ranks=max_over_ranks, barrier=barrier)
+                        cpu=(rank == 0 and world == 1 and not args.no_cpu), world=world, max_over_ranks=max_over_ranks, barrier=barrier,
+                        e2e_images=e2e_n)
         del uniq3
     if args.png_large:
         uniq4 = png_corpus(PNG4_W, PNG4_H, min(PNG4_UNIQUE, args.png_large), 4, "cfg4" if world > 1 else None, rank, world, barrier)

@@ -206,8 +206,9 @@ class Context:
         return int(a.value), int(b.value), int(c.value)
 
     def lane_stats(self):
-        """(attempts, whole blocks, prefixes, chunks expanded from tokens, chunks decoded twice) of the block-split path."""
-        v = (C.c_uint32 * 5)()
+        """dbg_lane_stats: block-split path (rounds, with end-of-block, without, chunks expanded from tokens, chunks decoded
+        twice) + warp-per-stream kernel (rounds, with end-of-block, without)."""
+        v = (C.c_uint32 * 8)()
         self._check(self.L.dbg_lane_stats(self.h, v), "dbg_lane_stats")
         return tuple(int(x) for x in v)
 

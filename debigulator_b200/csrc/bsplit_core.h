@@ -249,6 +249,8 @@ DBG_DEV ChunkResult decode_block_chunk(InflateSmem *sm, const uint8_t *in, uint6
     k.tok_cap = tok_cap;
     k.lanes = lanes;
     k.lb_stats = lb_stats;
+    k.round_bits = LB_ROUND_BITS;
+    k.lane_bad = k.lane_skip = 0;
     uint32_t end = BLK_FINAL;
     const uint32_t st = inflate_blocks<SINK>(w, g, sm, k, stop_bit == BS_NONE ? BS_NONE : stop_bit + off, end);
     if (SINK == SINK_U16) flush_pending16(k.pd);

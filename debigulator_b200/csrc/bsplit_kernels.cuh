@@ -60,9 +60,9 @@ struct BsBatch {
     uint64_t *tok_stream_base;  // per stream: first token slot
     uint32_t *c_ntok;           // per region: symbols seen by the count pass
     uint32_t tok_per_byte;      // token slots per compressed byte; a chunk that needs more is Huffman-decoded again
-    uint32_t lanes;             // the count pass may decode blocks lane-parallel (lane_decode_block, inflate_core.h)
+    uint32_t lanes;             // the count pass may decode blocks lane-parallel (lane_round, inflate_core.h)
     uint32_t dyn_all;           // every stream of >= min_bytes that opens with a dynamic block takes this path
-    uint32_t *lb_stats;         // per context, never reset: attempts / whole blocks / prefixes of lane_decode_block,
+    uint32_t *lb_stats;         // per context, never reset: rounds / rounds with end-of-block / rounds without of lane_round,
                                 // [3] chunks whose tokens were expanded, [4] chunks decoded a second time instead
 };
 

@@ -71,12 +71,13 @@ struct Slot {
     Buf meta;                        // derived descriptors (gzip payloads, BMP items)
     Buf png_scratch;                 // PNG: per-image meta, task queues, compacted IDAT, filtered scanlines
     Buf sched;                       // work-queue order computed on the device when the caller brings none
+    Buf round_tok;                   // token scratch of the warp-per-stream kernel's lane-parallel rounds (64 KiB per resident warp)
     Buf fx_stream, fx_chunks, fx_tok, cells, h_fx;            // lane-serial fixed-block path (fx_kernels.cuh)
     Buf bs_stream, bs_region, bs_cells, bs_tok, h_bs;         // block-split path (bsplit_kernels.cuh)
     Slot() { h_fx.pinned_host = h_bs.pinned_host = true; }
     void release()
     {
-        Buf *all[] = {&counter, &meta, &png_scratch, &sched, &fx_stream, &fx_chunks, &fx_tok, &cells, &h_fx,
+        Buf *all[] = {&counter, &meta, &png_scratch, &sched, &round_tok, &fx_stream, &fx_chunks, &fx_tok, &cells, &h_fx,
                       &bs_stream, &bs_region, &bs_cells, &bs_tok, &h_bs};
         for (Buf *b : all) b->release();
     }
@@ -106,7 +107,9 @@ struct dbg_ctx {
     uint32_t bsplit_tok_per_byte = 4;             // token slots per compressed byte (0 = no tokens: decode twice)
     uint64_t bsplit_tok_max_bytes = 24ull << 30;  // the token area never grows beyond this
     bool bsplit = true;
-    bool bsplit_lanes = true;       // the count pass decodes Huffman blocks lane-parallel (lane_decode_block)
+    bool rounds = true;             // the warp-per-stream kernel decodes Huffman blocks in lane-parallel rounds (DBG_ROUNDS)
+    uint32_t round_bits = dbg::LB_ROUND_BITS;  // their length (DBG_ROUND_BITS)
+    bool bsplit_lanes = true;       // the count pass of the block-split path decodes Huffman blocks lane-parallel
     int bsplit_all = 0;             // 1: every stream of >= bsplit_min_bytes takes the block-split path, not only the batch's
                                     // outliers; 2: every such stream that opens with a dynamic block
     uint64_t bsplit_min_bytes = dbg::BS_MIN_BYTES;
@@ -226,6 +229,8 @@ extern "C" dbg_ctx *dbg_create(int device)
     if (const char *v = getenv("DBG_PNG_WAVES")) ctx->png_waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(v)));
     if (const char *v = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(v) != 0;
     if (const char *v = getenv("DBG_BSPLIT_LANES")) ctx->bsplit_lanes = atoi(v) != 0;
+    if (const char *v = getenv("DBG_ROUNDS")) ctx->rounds = atoi(v) != 0;
+    if (const char *v = getenv("DBG_ROUND_BITS")) ctx->round_bits = (uint32_t)std::min(1 << 20, std::max(8192, atoi(v)));
     if (const char *v = getenv("DBG_BSPLIT_ALL")) ctx->bsplit_all = atoi(v);
     if (const char *v = getenv("DBG_BSPLIT_FACTOR_Q")) ctx->bsplit_factor_q = (uint32_t)std::max(1, atoi(v));
     if (const char *v = getenv("DBG_BSPLIT_TOKENS")) ctx->bsplit_tok_per_byte = (uint32_t)std::min(8, std::max(0, atoi(v)));
@@ -291,11 +296,12 @@ extern "C" int dbg_fx_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *han
 // Diagnostics of the block-split path's count / expansion passes, counted on the device: v[0] blocks where the
 // lane-parallel decode was attempted, v[1] blocks it decoded whole, v[2] blocks it decoded a prefix of, v[3] chunks
 // whose tokens were expanded, v[4] chunks that had to be Huffman-decoded a second time. Waits for the device.
-extern "C" int dbg_lane_stats(const dbg_ctx *ctx, uint32_t v[5])
+extern "C" int dbg_lane_stats(const dbg_ctx *ctx, uint32_t v[8])
 {
     if (!ctx || !v) return DBG_ERR_ARG;
     if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
-        cudaMemcpy(v, (uint64_t *)ctx->d_stats.p + 4, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+        cudaMemcpy(v, (uint64_t *)ctx->d_stats.p + 4, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(v + 5, (uint64_t *)ctx->d_stats.p + 8, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
         return DBG_ERR_CUDA;
     return DBG_OK;
 }
@@ -404,6 +410,15 @@ static int launch_inflate_plain(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, int
     CU(cudaMemsetAsync(a.counter, 0, sizeof(uint32_t), s));
     uint32_t ctas_needed = (a.n + dbg::INFLATE_WARPS_PER_CTA - 1) / dbg::INFLATE_WARPS_PER_CTA;
     uint32_t grid = std::min<uint32_t>(ctas_needed, (uint32_t)ctx->sm_count * ctx->inflate_ctas_per_sm);
+    if (ctx->rounds) {
+        // every warp of the grid gets a token scratch of its own. The auxiliary-stream launch of the block-split path
+        // and the main launch may run side by side: they use different halves.
+        const size_t per_launch = (size_t)ctx->sm_count * ctx->inflate_ctas_per_sm * dbg::INFLATE_WARPS_PER_CTA * dbg::LB_ROUND_TOKENS * 4;
+        CU(sl.round_tok.reserve(3 * per_launch));
+        a.tok_scratch = (uint32_t *)((uint8_t *)sl.round_tok.p + (size_t)counter_idx * per_launch);
+        a.lb_stats = (uint32_t *)((uint64_t *)ctx->d_stats.p + 8);
+        a.round_bits = ctx->round_bits;
+    }
     size_t smem = sizeof(dbg::InflateSmem) * dbg::INFLATE_WARPS_PER_CTA;
     {
         ProfScope prof(ctx, s, DBG_PROF_INFLATE);
@@ -757,7 +772,7 @@ static int inflate_device_slot(dbg_ctx *ctx, Slot &sl, bool gz, bool intra, uint
         dbg::gz_scan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_in_off, d_in_size, (uint32_t)n, gz_off, gz_size, gz_pre);
         ctx->launches++;
         CU(cudaGetLastError());
-        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
+        dbg::InflateBatch a{d_in, gz_off, gz_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, gz_pre, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n, nullptr, nullptr, 0};
         int rc = launch_inflate(ctx, sl, a, s, intra, intra);
         if (rc || !ctx->verify) return rc;
         uint32_t ctas = (uint32_t)std::min<uint64_t>((n + dbg::SCAN_WARPS - 1) / dbg::SCAN_WARPS, (uint64_t)ctx->sm_count * 8);
@@ -767,7 +782,7 @@ static int inflate_device_slot(dbg_ctx *ctx, Slot &sl, bool gz, bool intra, uint
         CU(cudaGetLastError());
         return DBG_OK;
     }
-    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n};
+    dbg::InflateBatch a{d_in, d_in_off, d_in_size, d_out, d_out_off, d_out_cap, d_out_size, d_status, nullptr, nullptr, nullptr, nullptr, d_order, nullptr, (uint32_t)n, nullptr, nullptr, 0};
     return launch_inflate(ctx, sl, a, s, intra, intra);
 }
 
@@ -790,7 +805,7 @@ static int png_device_slot(dbg_ctx *ctx, Slot &sl, uint64_t n, const uint8_t *d_
     // 2. inflate the zlib payloads into the filtered-scanline buffers
     // z_off holds absolute addresses: a single-IDAT image is inflated straight from the file
     dbg::InflateBatch a{nullptr, lay.z_off, lay.z_size, lay.scan, lay.s_off, lay.s_cap, lay.s_size, lay.inf_status,
-                        lay.pre_status, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t)n};
+                        lay.pre_status, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t)n, nullptr, nullptr, 0};
     rc = launch_inflate(ctx, sl, a, s, true, true, hints);
     if (rc) return rc;
     if (ctx->verify) {

@@ -21,9 +21,11 @@
 //     LUT with pre-baked base/extra-bit fields, and a canonical first-code
 //     walk for the rare longer codes -- 5.2 KB of shared memory per warp
 //     instead of the reference's 3 x 792 KB hash maps (inflate.c:112-118).
-//   * streams that are one fixed-Huffman block can also be decoded chunk-
-//     parallel ("split stream", end of this file): exact chunk boundaries from
-//     32-hypothesis transfer tables, 16-bit cells with markers, resolve pass.
+//   * when symbols only have to be recorded (the sizes pass of the block-split
+//     path) a Huffman block is decoded lane-parallel instead: one lane per
+//     sub-chunk behind exact merge points (lane_round below). Streams
+//     that are one fixed-Huffman block are decoded by fx_core.h, one lane per
+//     chunk.
 //
 // Behavioural parity with the reference's silent, no-assert build is kept where
 // the reference has defined behaviour: the premature
@@ -461,8 +463,10 @@ struct Sink {
     uint64_t abs_base;  // SINK_U16: stream output offset of out16[0] (markers may not reach before the stream)
     uint32_t *tok;      // SINK_TOKENS: token area, `tok_cap` entries; ntok keeps counting past it (= overflow)
     uint32_t ntok, tok_cap;
-    bool lanes;         // SINK_TOKENS: blocks may be decoded lane-parallel (lane_decode_block)
-    uint32_t *lb_stats; // optional counters of lane_decode_block: [0] attempts, [1] whole blocks, [2] prefixes
+    bool lanes;         // SINK_TOKENS / SINK_BYTES: Huffman blocks may be decoded lane-parallel (lane_round)
+    uint32_t round_bits;  // SINK_BYTES: round length
+    uint32_t lane_bad, lane_skip;  // back-off: failures in a row / blocks still to leave to the symbol walk
+    uint32_t *lb_stats; // optional counters of lane_round: [0] rounds, [1] rounds that met end-of-block, [2] rounds that did not
     PendingStore pd;
 };
 
@@ -895,6 +899,8 @@ enum : uint32_t { CH_RUN = 0, CH_EOB = 1, CH_Q2 = 2, CH_IDLE = 3, CH_ERR = 16 };
 constexpr uint32_t LB_MIN_SUB = 2048;         // smallest sub-chunk, bits
 constexpr uint32_t LB_MAX_EXTENT = 1u << 20;  // largest presumed extent, bits (128 KiB of compressed data)
 constexpr uint32_t LB_NOHINT_EXTENT = 3u << 17;  // presumed extent when the caller has no hint, bits (48 KiB)
+constexpr uint32_t LB_ROUND_BITS = 3u << 15;   // round length of the byte sink (12 KiB of compressed data, 3,072 bits per lane; measured: cfg2 57.3 ms at 8 KiB, 54.1 at 12, 63.6 at 16)
+constexpr uint32_t LB_ROUND_TOKENS = 16384;   // its token scratch per warp (a round of the densest sensible code: 4 bits per symbol)
 constexpr uint32_t LB_MERGE_BITS = 1024;      // chains that have not merged after this many bits are given up
 constexpr uint32_t LB_STARTS = 48;            // candidate entry offsets per sub-chunk = longest possible symbol
 enum : uint32_t { LBK_LIT = 0, LBK_MATCH = 1, LBK_EOB = 2, LBK_BAD = 3 };
@@ -983,78 +989,80 @@ DBG_DEV uint64_t lb_merge_point(const InflateSmem *sm, const BlockTables &bt, co
 
 enum : uint32_t { LB_UNUSED = 0, LB_DONE = 1, LB_PARTIAL = 2 };
 #ifdef DBG_SIMT_EMU
-static uint32_t g_lb_done = 0, g_lb_tried = 0, g_lb_partial = 0;  // emulator only: outcome counts of lane_decode_block
+static uint32_t g_lb_done = 0, g_lb_tried = 0, g_lb_partial = 0;  // emulator only: outcome counts of lane_round
 #endif
 
-// Lane-parallel decode of the Huffman block whose first symbol is at the window position (tables built).
-//   LB_DONE     the whole block: its tokens are appended to k.tok, k.pos / k.ntok advanced, the window stands behind
-//               the end-of-block code;
-//   LB_PARTIAL  the same for a prefix of the block: the window stands on the symbol where the caller goes on with
-//               decode_symbols() (same tables);
-//   LB_UNUSED   nothing has changed.
-// `counters` (optional): [0] attempts, [1] whole blocks, [2] prefixes.
-DBG_DEV uint32_t lane_decode_block(Window &w, const StreamIn &g, InflateSmem *sm, const BlockTables &bt, Sink &k, uint64_t stop_bit)
+struct LaneRound {
+    uint32_t ntok;     // tokens written to the area, in order, contiguous
+    uint32_t out;      // bytes they produce
+    uint64_t resume;   // ring bit where the decode goes on (LB_DONE: behind the end-of-block code)
+    uint32_t used;     // runs (lanes) that counted
+};
+
+// One lane-parallel round over the Huffman block whose tables are built, from ring bit p0 (a symbol start):
+//   LB_DONE     up to and including end-of-block;
+//   LB_PARTIAL  a prefix of the block: r.resume is the symbol where the caller goes on (another round, or
+//               decode_symbols() with the same tables);
+//   LB_UNUSED   nothing was decoded.
+// `ext` = presumed bits to the end of the block (from a boundary hint, or simply a round length), `area` / `area_cap`
+// = where the tokens go. `stats` (optional): [0] rounds, [1] rounds that met end-of-block, [2] rounds that did not.
+DBG_DEV uint32_t lane_round(const InflateSmem *sm, const BlockTables &bt, const uint8_t *base16, const StreamIn &g, uint64_t p0, uint64_t ext,
+                            uint32_t *area, uint32_t area_cap, LaneRound &r, uint32_t *stats)
 {
     const uint32_t ln = (uint32_t)simt::lane();
-    const uint64_t p0 = w.abs_bits();
-    const uint64_t in_end = 8 * g.end_byte;
-    const bool hinted = stop_bit < in_end;
-    const uint64_t ext_end = hinted ? stop_bit : in_end;
-    if (ext_end <= p0) return LB_UNUSED;
-    uint64_t ext = ext_end - p0;
-    // without a hint the block ends somewhere in the rest of the stream: presume what compressors write (zlib closes a
-    // block after 16 K symbols, 30-50 KB); what lies behind the block's end is decoded in vain
-    const uint32_t cap = hinted ? LB_MAX_EXTENT : LB_NOHINT_EXTENT;
-    if (ext > cap) ext = cap;
-    if (ext < 4 * LB_MIN_SUB || k.ntok >= k.tok_cap) return LB_UNUSED;
+    r.ntok = 0;
+    r.out = 0;
+    r.resume = p0;
+    r.used = 0;
+    if (ext > LB_MAX_EXTENT) ext = LB_MAX_EXTENT;
+    if (ext < 4 * LB_MIN_SUB) return LB_UNUSED;
     uint32_t sub = ((uint32_t)ext + 31) / 32;
     if (sub < LB_MIN_SUB) sub = LB_MIN_SUB;
     sub = (sub + 31) & ~31u;
     const uint32_t L = ((uint32_t)ext + sub - 1) / sub;  // lanes in use, 4..32
-    const uint32_t stride = (k.tok_cap - k.ntok) / L;    // token slots per lane
+    const uint32_t stride = area_cap / L;                // token slots per lane
     if (stride < sub / 16) return LB_UNUSED;
 #ifdef DBG_SIMT_EMU
     if (ln == 0) g_lb_tried++;
 #else
-    if (ln == 0 && k.lb_stats) atomicAdd(&k.lb_stats[0], 1u);
+    if (ln == 0 && stats) atomicAdd(&stats[0], 1u);
 #endif
     // merge points. A lane whose chains do not merge (it may be looking at the NEXT block's bits, coded with other
     // tables) has none; the chain below simply ends before it.
     uint64_t entry = p0;
     const uint32_t give_up = sub / 2 < LB_MERGE_BITS ? sub / 2 : LB_MERGE_BITS;
-    if (ln > 0 && ln < L) entry = lb_merge_point(sm, bt, w.base, g.end_byte, p0 + (uint64_t)ln * sub, give_up, g.q2_limit);
+    if (ln > 0 && ln < L) entry = lb_merge_point(sm, bt, base16, g.end_byte, p0 + (uint64_t)ln * sub, give_up, g.q2_limit);
     if (ln >= L) entry = ~0ull;
     const uint32_t e_lo = simt::shfl_down((uint32_t)entry, 1), e_hi = simt::shfl_down((uint32_t)(entry >> 32), 1);
     uint64_t target = ((uint64_t)e_hi << 32) | e_lo;  // the next lane's entry point
     const bool has_target = ln + 1 < L && target != ~0ull;
-    // without one the run may still meet the block's end inside its own sub-chunk
-    if (!has_target) target = p0 + (uint64_t)(ln + 1) * sub + LB_STARTS;
+    // a run without one goes to the first symbol boundary behind its own sub-chunk (it may meet end-of-block on the way)
+    if (!has_target) target = p0 + (uint64_t)(ln + 1) * sub;
     // runs
-    uint32_t n = 0, out = 0;
-    uint32_t flag = CH_IDLE;  // CH_RUN: arrived exactly at the next entry point; CH_EOB: met end-of-block; else: the chain ends before this lane
+    enum : uint32_t { R_ARRIVED = 0, R_EOB = 1, R_STOPPED = 2, R_BROKEN = 3 };
+    uint32_t n = 0, out = 0, flag = R_BROKEN;
     uint64_t pos = entry;
-    uint32_t *area = k.tok + k.ntok + (uint64_t)ln * stride;
     if (entry != ~0ull) {
         LaneBits br;
-        br.open(w.base, g.end_byte);
+        br.open(base16, g.end_byte);
         br.seek(entry);
         TokOut wr;
-        wr.open(area);
-        flag = CH_RUN;
+        wr.open(area + (uint64_t)ln * stride);
+        flag = R_ARRIVED;
         while (pos < target) {
             if (pos >= g.q2_limit || n >= stride) {
-                flag = CH_ERR;
+                flag = R_BROKEN;  // rule Q2 / no room: the ordinary decoder takes over from this run's entry point
                 break;
             }
             uint32_t nbits, len, tok;
             const uint32_t kind = lb_symbol(sm, bt, br, &nbits, &len, &tok);
             if (kind == LBK_BAD) {
-                flag = CH_ERR;
+                flag = R_BROKEN;
                 break;
             }
             pos += nbits;
             if (kind == LBK_EOB) {
-                flag = CH_EOB;
+                flag = R_EOB;
                 break;
             }
             wr.put(tok);
@@ -1062,14 +1070,18 @@ DBG_DEV uint32_t lane_decode_block(Window &w, const StreamIn &g, InflateSmem *sm
             out += len;
         }
         wr.close();
-        if (flag == CH_RUN && (pos != target || !has_target)) flag = CH_ERR;  // missed the next entry point / nothing to arrive at
+        if (flag == R_ARRIVED) {
+            if (!has_target) flag = R_STOPPED;           // a clean prefix: stands on a symbol boundary
+            else if (pos != target) flag = R_BROKEN;     // missed the next entry point (cannot happen on the real chain)
+        }
     }
-    // chain: lanes 0 .. the first one that did not simply arrive at its target
-    const uint32_t stops = simt::ballot(flag != CH_RUN);  // never empty: the last lane has no target
+    // chain: lanes 0 .. the first one that did not simply arrive at the next entry point
+    const uint32_t stops = simt::ballot(flag != R_ARRIVED);  // never empty: the last lane has no target
     const uint32_t stop_lane = (uint32_t)simt::ffs(stops) - 1;
-    const bool whole = simt::shfl(flag, (int)stop_lane) == CH_EOB;
-    const uint32_t used = whole ? stop_lane + 1 : stop_lane;  // runs that count
+    const uint32_t stop_flag = simt::shfl(flag, (int)stop_lane);
+    const uint32_t used = stop_flag == R_BROKEN ? stop_lane : stop_lane + 1;  // runs that count
     if (used == 0) return LB_UNUSED;
+    r.used = used;
     uint32_t in = ln < used ? n : 0u, io = ln < used ? out : 0u;
     const uint32_t mine = in;
     for (int d = 1; d < 32; d <<= 1) {
@@ -1079,33 +1091,89 @@ DBG_DEV uint32_t lane_decode_block(Window &w, const StreamIn &g, InflateSmem *sm
             io += yo;
         }
     }
-    const uint32_t total_n = simt::shfl(in, 31), total_out = simt::shfl(io, 31);
-    // where the caller goes on: behind end-of-block, or on the entry point of the first run that does not count
-    const uint64_t resume = whole ? pos : entry;
-    const uint32_t r_lo = simt::shfl((uint32_t)resume, (int)stop_lane), r_hi = simt::shfl((uint32_t)(resume >> 32), (int)stop_lane);
+    r.ntok = simt::shfl(in, 31);
+    r.out = simt::shfl(io, 31);
+    // where the decode goes on: behind the last run that counts, or on the entry point of the broken one
+    const uint64_t res = stop_flag == R_BROKEN ? entry : pos;
+    r.resume = ((uint64_t)simt::shfl((uint32_t)(res >> 32), (int)stop_lane) << 32) | simt::shfl((uint32_t)res, (int)stop_lane);
     // move the runs' tokens together (run 0 is in place); forward copies, the loads of a step before its stores
     simt::syncwarp();
-    uint32_t *base = k.tok + k.ntok;
     for (uint32_t j = 1; j < used; j++) {
         const uint32_t cnt = simt::shfl(mine, (int)j), dst0 = simt::shfl(in - mine, (int)j);
-        const uint32_t *src = base + (uint64_t)j * stride;
+        const uint32_t *src = area + (uint64_t)j * stride;
         for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
             const uint32_t i = i0 + ln;
             const uint32_t v = i < cnt ? src[i] : 0u;
             simt::syncwarp();
-            if (i < cnt) base[dst0 + i] = v;
+            if (i < cnt) area[dst0 + i] = v;
             simt::syncwarp();
         }
     }
-    k.ntok += total_n;
-    k.pos += total_out;
-    w.seek_bits(((uint64_t)r_hi << 32) | r_lo);
+    const bool whole = stop_flag == R_EOB;
 #ifdef DBG_SIMT_EMU
     if (ln == 0) (whole ? g_lb_done : g_lb_partial)++;
 #else
-    if (ln == 0 && k.lb_stats) atomicAdd(&k.lb_stats[whole ? 1 : 2], 1u);
+    if (ln == 0 && stats) atomicAdd(&stats[whole ? 1 : 2], 1u);
 #endif
     return whole ? LB_DONE : LB_PARTIAL;
+}
+
+// Tokens -> bytes, by the warp that decodes the stream in order (so every source byte is final): 32 tokens per step,
+// an exclusive scan of their lengths gives each its place, literals are stored at once, matches whose source lies wholly
+// before the step's output (and that are short) are copied by their own lanes side by side, the others one after the
+// other by the whole warp. Returns ST_OK or the status of the FIRST token (in stream order) that fails: a distance that
+// reaches before the output start (inflate.c:1843) or an overflow of the capacity.
+DBG_DEV uint32_t expand_tokens_bytes(const uint32_t *tok, uint32_t ntok, uint8_t *out, uint32_t &pos_io, uint32_t cap)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    uint32_t pos = pos_io;
+    uint32_t t_next = ln < ntok ? tok[ln] : 0u;
+    for (uint32_t base = 0; base < ntok; base += 32) {
+        const bool have = base + ln < ntok;
+        const uint32_t t = t_next;
+        t_next = base + 32 + ln < ntok ? tok[base + 32 + ln] : 0u;  // the next step's tokens are on their way
+        const bool is_match = have && (t & TOKEN_MATCH);
+        const uint32_t len = !have ? 0u : is_match ? (t >> 16) & 0x1ff : 1u;
+        const uint32_t dist = (t & 0x7fff) + 1;
+        uint32_t incl = len;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = simt::shfl_up(incl, d);
+            if (ln >= (uint32_t)d) incl += y;
+        }
+        const uint32_t o = pos + incl - len;
+        const uint32_t total = simt::shfl(incl, 31);
+        const bool bad_dist = is_match && dist > o;
+        const bool over = have && (uint64_t)o + len > cap;
+        const uint32_t fails = simt::ballot(bad_dist || over);
+        if (fails) {
+            const int f = simt::ffs(fails) - 1;
+            pos_io = pos;
+            return simt::shfl(over ? (uint32_t)ST_OUT_OVERFLOW : (uint32_t)ST_BAD_DISTANCE, f);
+        }
+        simt::syncwarp();  // the previous step's bytes are in place
+        if (have && !is_match) out[o] = (uint8_t)t;
+        const bool free_m = is_match && len <= 16 && o + len <= pos + dist;
+        if (free_m) {
+            const uint8_t *src = out + (o - dist);
+            uint8_t *dst = out + o;
+            uint32_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = (uint32_t)j < len ? src[j] : 0u;
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if ((uint32_t)j < len) dst[j] = (uint8_t)v[j];
+        }
+        uint32_t m = simt::ballot(is_match && !free_m);
+        while (m) {
+            const int j = simt::ffs(m) - 1;
+            m &= m - 1;
+            copy_match_slow(out, simt::shfl(o, j), simt::shfl(len, j), simt::shfl(dist, j));  // (syncs the warp first)
+        }
+        pos += total;
+    }
+    simt::syncwarp();
+    pos_io = pos;
+    return ST_OK;
 }
 
 // The block loop of inflate() (inflate.c:896-1950): decodes blocks from the window position, which
@@ -1167,9 +1235,66 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
             uint32_t st = read_huffman_tables(w, sm, btype, bt);
             if (st) return st;
             uint32_t why = END_EOB;
-            if (SINK == SINK_TOKENS && k.lanes) {
-                // whole block: next header; a prefix: decode_symbols() below goes on where the lanes stopped
-                if (lane_decode_block(w, g, sm, bt, k, stop_bit) == LB_DONE) {
+            if ((SINK == SINK_TOKENS || SINK == SINK_BYTES) && k.lanes && k.lane_skip) {
+                k.lane_skip--;  // this block is left to the symbol walk (rounds achieved nothing on the blocks before it)
+            } else if ((SINK == SINK_TOKENS || SINK == SINK_BYTES) && k.lanes) {
+                // lane-parallel rounds (lane_round above): one per presumed extent of the block. SINK_TOKENS: the extent
+                // is the caller's next boundary hint and the tokens go straight to the chunk's token area. SINK_BYTES: no
+                // hint, so the block is taken in rounds of LB_ROUND_BITS, each round's tokens go through the warp's
+                // scratch and are expanded into the output right away. Whatever a round leaves (a broken chain, the
+                // rule-Q2 limit, the last bits of the block) decode_symbols() below finishes with the same tables.
+                bool block_done = false;
+                for (;;) {
+                    const uint64_t p0 = w.abs_bits();
+                    const uint64_t in_end = 8 * g.end_byte;
+                    LaneRound lr;
+                    uint32_t got;
+                    if (SINK == SINK_TOKENS) {
+                        const bool hinted = stop_bit < in_end;
+                        uint64_t ext = (hinted ? stop_bit : in_end) > p0 ? (hinted ? stop_bit : in_end) - p0 : 0;
+                        if (!hinted && ext > LB_NOHINT_EXTENT) ext = LB_NOHINT_EXTENT;
+                        if (k.ntok >= k.tok_cap) break;
+                        got = lane_round(sm, bt, w.base, g, p0, ext, k.tok + k.ntok, k.tok_cap - k.ntok, lr, k.lb_stats);
+                        if (got == LB_UNUSED) break;
+                        k.ntok += lr.ntok;
+                        k.pos += lr.out;
+                    } else {
+                        uint64_t ext = in_end > p0 ? in_end - p0 : 0;
+                        if (ext > k.round_bits) ext = k.round_bits;
+                        got = lane_round(sm, bt, w.base, g, p0, ext, k.tok, k.tok_cap, lr, k.lb_stats);
+                        if (got == LB_UNUSED) {
+                            if (ext >= 4 * LB_MIN_SUB) {  // (not the short tail of a stream)
+                                k.lane_skip = k.lane_bad < 8 ? k.lane_bad : 8;
+                                k.lane_bad++;
+                            }
+                            break;
+                        }
+                        simt::syncwarp();
+                        flush_pending(k.pd);
+                        st = expand_tokens_bytes(k.tok, lr.ntok, k.out, k.pos, k.cap);
+                        if (st) return st;
+                    }
+                    w.seek_bits(lr.resume);
+                    if (got == LB_DONE) {
+                        block_done = true;
+                        k.lane_bad = 0;
+                        break;
+                    }
+                    if (lr.resume - p0 < (SINK == SINK_BYTES ? k.round_bits : LB_ROUND_BITS) / 2) {  // little progress: the chain broke early
+                        // Broken in the very first lanes: data whose chains do not merge (run-length trains, window-limit
+                        // periods). Back off: after the n-th such round in a row the next min(n - 1, 8) blocks are left to the
+                        // symbol walk. A chain that breaks further out (the next block's bits, a dense stretch) costs nothing
+                        // to try again.
+                        if (lr.used <= 2) {
+                            k.lane_skip = k.lane_bad < 8 ? k.lane_bad : 8;
+                            k.lane_bad++;
+                        }
+                        break;
+                    }
+                    k.lane_bad = 0;
+                    if (SINK == SINK_TOKENS) break;                 // one round per hinted extent
+                }
+                if (block_done) {
                     if (!more) return ST_OK;
                     continue;
                 }
@@ -1190,7 +1315,8 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
 // value and *final_size are uniform. `in` may have any alignment; bytes from
 // (in & ~15) up to the 16-byte boundary at or after in + in_size must be readable.
 DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap,
-                              uint64_t *final_size)
+                              uint64_t *final_size, uint32_t *tok_scratch = nullptr, uint32_t *lb_stats = nullptr,
+                              uint32_t round_bits = LB_ROUND_BITS)
 {
     *final_size = 0;
     if (cap < in_size) return ST_CAP_LT_INPUT;
@@ -1210,10 +1336,13 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     k.pd.ptr = out;
     k.pd.val = 0;
     k.pd.on = false;
-    k.tok = nullptr;
-    k.ntok = k.tok_cap = 0;
-    k.lanes = false;
-    k.lb_stats = nullptr;
+    k.tok = tok_scratch;  // LB_ROUND_TOKENS slots of this warp's own: Huffman blocks are decoded in lane-parallel rounds
+    k.ntok = 0;
+    k.tok_cap = tok_scratch ? LB_ROUND_TOKENS : 0;
+    k.lanes = tok_scratch != nullptr;
+    k.lb_stats = lb_stats;
+    k.round_bits = round_bits;
+    k.lane_bad = k.lane_skip = 0;
     uint32_t end;
     const uint32_t st = inflate_blocks<SINK_BYTES>(w, g, sm, k, ~0ull, end);
     if (st) return st;
@@ -1222,126 +1351,11 @@ DBG_DEV uint32_t inflate_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_si
     return ST_OK;
 }
 
-// ------------------------------------------------------------- split stream --
-// Intra-stream parallelism for streams that are ONE FIXED-Huffman block: what
-// stb_image_write emits for every PNG (stb_write.h:913-916), i.e. BASELINE
-// configs 3 and 4, where a handful of 150 MB streams would otherwise be decoded
-// by a handful of warps ("hard parts").
-//
-// Fixed-Huffman streams do not self-synchronise (measured: profiles/experiments),
-// so chunk boundaries are not guessed. Instead, because a fixed-code symbol is at
-// most 31 bits long (9 + 5 + 5 + 13 - 1), some symbol starts within any 31
-// consecutive bits, and the 32 lanes of a warp can carry ALL 32 possible entry
-// offsets of a chunk at once:
-//   transfer  one warp per CHUNK_BYTES of compressed data; lane j decodes
-//             (sizes only) from bit j of the chunk to the chunk end and records
-//             where it leaves the chunk, how many bytes it produced and how it
-//             ended: an exact transfer table  entry offset -> (exit offset, bytes).
-//   chain     one thread per stream walks the tables from chunk 0: exact entry
-//             bit and output offset of every chunk.
-//   decode    one warp per chunk decodes from its exact entry into 16-bit cells;
-//             a match that reaches before the chunk's own output becomes a
-//             marker (256 + 32768 - distance_before_chunk_start).
-//   resolve   one CTA per stream, chunk after chunk: cells -> bytes, markers
-//             read the already finished output.
-enum { CHUNK_BYTES = 32768 };  // smallest chunk; the host doubles it (up to 8x) for very large batches, see run_split
-
-// Lane-local fixed-Huffman size decode of the symbol at ring bit `pos`:
-// returns the symbol's bit length (0 = undecodable) and its output bytes in
-// *out_bytes (0 for end-of-block, flagged in *eob).
-DBG_DEV uint32_t lane_symbol_size(const InflateSmem *sm, uint32_t pos, uint32_t *out_bytes, bool *eob)
-{
-    const uint32_t wi = pos >> 5, sh = pos & 31;
-    const uint32_t a = sm->ring[wi & 255], b = sm->ring[(wi + 1) & 255], c = sm->ring[(wi + 2) & 255];
-    const uint32_t lo = simt::funnel_r(a, b, sh), hi = simt::funnel_r(b, c, sh);
-    const uint32_t e = sm->lit_lut[lo & ((1u << LIT_ROOT) - 1)];  // fixed code: every code fits the primary table
-    const uint32_t l1 = e & 15;
-    *eob = false;
-    *out_bytes = 1;
-    if (e & E_LIT) return l1;
-    if (e & E_BASE) {
-        const uint32_t xb = (e >> 8) & 31;
-        *out_bytes = (e >> 16) + ((lo >> l1) & ((1u << xb) - 1));
-        const uint32_t t1 = l1 + xb;
-        const uint32_t v = simt::funnel_r(lo, hi, t1);
-        const uint32_t e2 = sm->dist_lut[v & ((1u << DIST_ROOT) - 1)];
-        if (!(e2 & E_BASE)) return 0;  // distance symbols 30 / 31
-        return t1 + (e2 & 15) + ((e2 >> 8) & 31);
-    }
-    *out_bytes = 0;
-    if (e & E_EOB) {
-        *eob = true;
-        return l1;
-    }
-    return 0;  // litlen 286 / 287
-}
-
-struct TransferEntry {   // result of entering a chunk at bit (chunk start + lane)
-    uint32_t out_bytes;
-    uint8_t next;        // exit offset into the next chunk (0..30)
-    uint8_t flag;        // CH_RUN / CH_EOB / CH_Q2 / CH_ERR
-    uint16_t pad;
-};
-
-// Transfer table of chunk `chunk` (>= 1) of a single-fixed-block stream; lane j
-// writes table[j]. Chunk 0 has one known entry (bit 3) and is computed by lane 0
-// semantics: every lane starts at bit 3, so all 32 entries are identical.
-DBG_DEV void transfer_chunk_warp(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint32_t chunk, uint32_t chunk_bytes,
-                                 TransferEntry *table)
-{
-    const uint32_t ln = (uint32_t)simt::lane();
-    Window w;
-    const StreamIn g = open_stream(w, sm, in, in_size);
-    BlockTables bt;
-    bt.lit_max = bt.dist_max = 0;
-    read_huffman_tables(w, sm, 1, bt);  // the fixed code
-    const uint64_t off = 8ull * g.mis;  // stream-relative bit -> ring-coordinate bit
-    const uint64_t start = (uint64_t)chunk * chunk_bytes * 8 + off;
-    const uint64_t stop = start + (uint64_t)chunk_bytes * 8;
-    uint64_t pos = chunk == 0 ? off + 3 : start + ln;
-    uint32_t outb = 0, flag = CH_RUN;
-    // the input is walked in 512-byte ring chunks; all lanes stay within 31 bits of each other
-    const uint32_t c0 = (uint32_t)(start >> 12);                 // first 512 B ring chunk touched
-    const uint32_t c1 = (uint32_t)((stop + 31 + 95) >> 12);      // last one touched (3-word fetches)
-    simt::cp_async_wait_all();
-    simt::syncwarp();
-    w.load_chunk(c0);
-    simt::cp_async_commit();
-    for (uint32_t c = c0; c <= c1; c++) {
-        simt::syncwarp();
-        w.load_chunk(c + 1);  // the slot of ring chunk c-1, which no lane reads any more
-        simt::cp_async_commit();
-        simt::cp_async_wait_all();
-        simt::syncwarp();
-        const uint64_t seg_end = ((uint64_t)(c + 1) << 12) < stop ? ((uint64_t)(c + 1) << 12) : stop;
-        while (flag == CH_RUN && pos < seg_end) {
-            if (pos >= g.q2_limit) {  // rule Q2: no symbol may start here
-                flag = CH_Q2;
-                break;
-            }
-            uint32_t ob;
-            bool eob;
-            uint32_t bits = lane_symbol_size(sm, (uint32_t)(pos & 0xffffffffu), &ob, &eob);
-            if (bits == 0) {
-                flag = CH_ERR;
-                break;
-            }
-            pos += bits;
-            if (eob) {
-                flag = CH_EOB;
-                break;
-            }
-            outb += ob;
-        }
-    }
-    TransferEntry t;
-    t.out_bytes = outb;
-    t.next = (uint8_t)(flag == CH_RUN ? (uint32_t)(pos - stop) : 0);
-    t.flag = (uint8_t)flag;
-    t.pad = 0;
-    table[ln] = t;
-}
-
+// ------------------------------------------------------- chunk-parallel paths --
+// Streams that one warp would take too long for are cut into pieces that are decoded side by side into 16-bit cells
+// (a value >= 256 is a marker "the byte at distance 32768 - (v - 256) before this piece's output"), which the resolve
+// kernels of split_kernels.cuh turn into bytes: single fixed-Huffman blocks by fx_core.h (one LANE per chunk), long
+// multi-block streams by bsplit_core.h (one warp per stretch between two block boundaries).
 struct ChunkResult {
     uint64_t exit_bits;  // stream-relative bit where the next chunk's first symbol starts
     uint32_t out_bytes;
@@ -1349,49 +1363,8 @@ struct ChunkResult {
     uint32_t ntok;       // SINK_TOKENS: symbols seen (more than the token area holds = overflow)
 };
 
-// A stream qualifies for the split path when it is one final fixed-Huffman block.
+// What stb_image_write emits: ONE final fixed-Huffman block (fx_core.h takes such streams).
 DBG_DEV bool is_single_fixed_block(const uint8_t *in) { return (in[0] & 7) == 3; }  // BFINAL=1, BTYPE=01
 
-// Decodes chunk `chunk` from its exact entry bit (stream-relative) into cells.
-template <int SINK>
-DBG_DEV ChunkResult decode_chunk(InflateSmem *sm, const uint8_t *in, uint64_t in_size, uint32_t chunk, uint32_t chunk_bytes,
-                                 uint64_t entry_bits, uint16_t *cells, uint32_t cell_cap, uint64_t abs_base)
-{
-    ChunkResult r;
-    Window w;
-    const StreamIn g = open_stream(w, sm, in, in_size);
-    BlockTables bt;
-    bt.lit_max = bt.dist_max = 0;
-    read_huffman_tables(w, sm, 1, bt);
-    const uint64_t off = 8ull * g.mis;
-    const uint64_t chunk_end = (uint64_t)(chunk + 1) * chunk_bytes * 8 + off;
-    const bool q2_first = g.q2_limit <= chunk_end;
-    w.lim_w = (uint32_t)((q2_first ? g.q2_limit : chunk_end) >> 5);
-    w.lim_b = (uint32_t)(q2_first ? g.q2_limit : chunk_end) & 31;
-    w.seek_bits(entry_bits + off);
-    Sink k;
-    k.out = nullptr;
-    k.out16 = cells;
-    k.abs_base = abs_base;
-    k.pos = 0;
-    k.cap = cell_cap;
-    k.pd.ptr = nullptr;
-    k.pd.val = 0;
-    k.pd.on = false;
-    k.tok = nullptr;
-    k.ntok = k.tok_cap = 0;
-    k.lanes = false;
-    k.lb_stats = nullptr;
-    uint32_t why = END_EOB;
-    uint32_t st = decode_symbols<SINK>(w, sm, bt, k, why);
-    if (SINK == SINK_U16) flush_pending16(k.pd);
-    r.exit_bits = w.abs_bits() - off;
-    r.out_bytes = k.pos;
-    r.ntok = 0;
-    if (st) r.flag = CH_ERR + st;
-    else if (why == END_EOB) r.flag = CH_EOB;
-    else r.flag = q2_first ? CH_Q2 : CH_RUN;
-    return r;
-}
 
 }  // namespace dbg

@@ -27,6 +27,9 @@ struct InflateBatch {
     const uint32_t *order;       // optional scheduling permutation
     uint32_t *counter;           // work-queue head, zeroed before launch
     uint32_t n;
+    uint32_t *tok_scratch;       // optional: LB_ROUND_TOKENS slots per warp of the grid (lane-parallel rounds, inflate_core.h)
+    uint32_t *lb_stats;          // optional counters of those rounds
+    uint32_t round_bits;         // their length in bits
 };
 
 // Persistent warps pulling streams from a global queue: one warp decodes one
@@ -36,6 +39,7 @@ __global__ void __launch_bounds__(INFLATE_THREADS, INFLATE_CTAS_PER_SM) inflate_
     extern __shared__ __align__(16) uint8_t smem_raw[];
     InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
     const int ln = simt::lane();
+    uint32_t *scratch = a.tok_scratch ? a.tok_scratch + (uint64_t)(blockIdx.x * INFLATE_WARPS_PER_CTA + (threadIdx.x >> 5)) * LB_ROUND_TOKENS : nullptr;
     for (;;) {
         uint32_t idx = 0;
         if (ln == 0) idx = atomicAdd(a.counter, 1u);
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(INFLATE_THREADS, INFLATE_CTAS_PER_SM) inflate_
         uint32_t st = a.pre_status ? a.pre_status[s] : 0u;
         uint64_t fs = 0;
         if (st == 0)
-            st = inflate_warp(sm, a.in_base + a.in_off[s], a.in_size[s], a.out_base + a.out_off[s], a.out_cap[s], &fs);
+            st = inflate_warp(sm, a.in_base + a.in_off[s], a.in_size[s], a.out_base + a.out_off[s], a.out_cap[s], &fs, scratch, a.lb_stats, a.round_bits);
         if (ln == 0) {
             a.out_size[s] = fs;
             a.status[s] = st;

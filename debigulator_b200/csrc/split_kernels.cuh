@@ -1,7 +1,6 @@
-// split_kernels.cuh -- __global__ wrappers of the split-stream path (see
-// "split stream" in inflate_core.h): chunk-parallel decode of streams that are a
-// single fixed-Huffman block, used when a batch has too few streams to fill the
-// GPU with one warp per stream (BASELINE config 4: 32 images of 256 MiB per GPU).
+// split_kernels.cuh -- the resolve kernels shared by the chunk-parallel paths (fx_kernels.cuh: single fixed-Huffman
+// blocks, one lane per chunk; bsplit_kernels.cuh: long multi-block streams): 16-bit cells -> bytes. Their "chunks" are
+// the marker domains of those paths (groups of lane chunks / stretches between block boundaries).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -9,18 +8,6 @@
 #include "inflate_core.h"
 
 namespace dbg {
-
-constexpr uint64_t SPLIT_MIN_BYTES = 4 * CHUNK_BYTES;  // smaller streams stay on the warp-per-stream path
-constexpr int SPLIT_WARPS_PER_CTA = 4;
-
-struct SplitSummary {      // written by split_classify_kernel, read back by the host
-    uint32_t n_split;      // streams taking the split path
-    uint32_t total_chunks;
-    uint64_t cells_cap;    // upper bound of 16-bit cells needed (sum of output capacities)
-    uint64_t cells_used;   // running allocation cursor (split_chain_kernel)
-    uint64_t split_in;     // compressed bytes of the streams taking the split path
-    uint64_t max_in;       // the longest of them
-};
 
 struct SplitBatch {
     const uint8_t *in_base;
@@ -33,134 +20,19 @@ struct SplitBatch {
     uint32_t *status;
     const uint32_t *pre_status;  // optional
     uint32_t n;
-    uint32_t chunk_bytes;   // compressed bytes per chunk (CHUNK_BYTES << k)
     // scratch
-    SplitSummary *summary;
     uint32_t *split_flag;   // per stream: 1 = split path
     const uint32_t *redo;   // optional (block-split path): 1 = handed back, nothing to resolve
     uint32_t *chunk_base;   // per stream: first global chunk index
     uint32_t *nchunks;      // per stream: number of chunks
     uint64_t *cell_base;    // per stream: first cell
     uint32_t *chunk_stream; // per chunk
-    uint64_t *entry_bits;   // per chunk: exact entry (stream-relative bit)
     uint64_t *c_out_off;    // per chunk: output offset inside the stream
     uint32_t *c_out_len;    // per chunk
     uint32_t *c_flag;       // per chunk
-    TransferEntry *tf;      // per chunk x 32
     uint16_t *cells;
 };
 
-
-// Which streams take the split path, and how many chunks / cells that needs.
-__global__ void split_classify_kernel(SplitBatch b)
-{
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.n) return;
-    uint32_t flag = 0;
-    uint64_t size = b.in_size[s], cap = b.out_cap[s];
-    bool ok = (!b.pre_status || b.pre_status[s] == 0) && size >= SPLIT_MIN_BYTES && cap >= size && size < (1ull << 31) &&
-              cap < (1ull << 32) - 1024;
-    if (ok && is_single_fixed_block(b.in_base + b.in_off[s])) {
-        flag = 1;
-        atomicAdd(&b.summary->n_split, 1u);
-        atomicAdd((unsigned long long *)&b.summary->cells_cap, (unsigned long long)cap);
-        atomicAdd((unsigned long long *)&b.summary->split_in, (unsigned long long)size);
-        atomicMax((unsigned long long *)&b.summary->max_in, (unsigned long long)size);
-    }
-    b.split_flag[s] = flag;
-}
-
-// Chunks per stream, once the host has chosen the chunk size.
-__global__ void split_assign_kernel(SplitBatch b)
-{
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.n || !b.split_flag[s]) return;
-    const uint32_t nch = (uint32_t)((b.in_size[s] + b.chunk_bytes - 1) / b.chunk_bytes);
-    b.chunk_base[s] = atomicAdd(&b.summary->total_chunks, nch);
-    b.nchunks[s] = nch;
-}
-
-__global__ void split_fill_kernel(SplitBatch b)
-{
-    uint32_t s = blockIdx.x;
-    if (!b.split_flag[s]) return;
-    uint32_t nch = b.nchunks[s], base = b.chunk_base[s];
-    for (uint32_t c = threadIdx.x; c < nch; c += blockDim.x) b.chunk_stream[base + c] = s;
-}
-
-// Transfer tables: one warp per chunk, one lane per entry-offset hypothesis.
-__global__ void __launch_bounds__(SPLIT_WARPS_PER_CTA * 32) split_transfer_kernel(SplitBatch b)
-{
-    const uint32_t total_chunks = b.summary->total_chunks;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
-    const uint32_t warps = gridDim.x * SPLIT_WARPS_PER_CTA;
-    for (uint32_t t = blockIdx.x * SPLIT_WARPS_PER_CTA + (threadIdx.x >> 5); t < total_chunks; t += warps) {
-        const uint32_t s = b.chunk_stream[t];
-        transfer_chunk_warp(sm, b.in_base + b.in_off[s], b.in_size[s], t - b.chunk_base[s], b.chunk_bytes, b.tf + (uint64_t)t * 32);
-        simt::syncwarp();
-    }
-}
-
-// Exact entry and output offset of every chunk: one thread per stream.
-__global__ void split_chain_kernel(SplitBatch b)
-{
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.n || !b.split_flag[s]) return;
-    const uint32_t nch = b.nchunks[s], base = b.chunk_base[s];
-    uint64_t pos = 0;
-    uint32_t idx = 0, st = ST_OK;
-    bool ended = false;
-    for (uint32_t c = 0; c < nch; c++) {
-        const uint32_t t = base + c;
-        if (ended) {
-            b.c_flag[t] = CH_IDLE;
-            b.c_out_len[t] = 0;
-            b.c_out_off[t] = pos;
-            b.entry_bits[t] = 0;
-            continue;
-        }
-        const TransferEntry e = b.tf[(uint64_t)t * 32 + idx];
-        b.entry_bits[t] = c == 0 ? 3 : (uint64_t)c * b.chunk_bytes * 8 + idx;
-        b.c_out_off[t] = pos;
-        b.c_out_len[t] = e.out_bytes;
-        b.c_flag[t] = e.flag;
-        pos += e.out_bytes;
-        if (e.flag != CH_RUN) {
-            ended = true;
-            if (e.flag >= CH_ERR) st = ST_BAD_SYMBOL;
-        }
-        idx = e.next;
-    }
-    if (!ended) st = ST_TRUNCATED;
-    if (st == ST_OK && pos > b.out_cap[s]) st = ST_OUT_OVERFLOW;
-    b.status[s] = st;
-    b.out_size[s] = st == ST_OK ? pos : 0;
-    b.cell_base[s] = st == ST_OK ? atomicAdd((unsigned long long *)&b.summary->cells_used, (unsigned long long)pos) : 0;
-}
-
-// Chunk decode into 16-bit cells: one warp per chunk.
-__global__ void __launch_bounds__(SPLIT_WARPS_PER_CTA * 32) split_decode_kernel(SplitBatch b)
-{
-    const uint32_t total_chunks = b.summary->total_chunks;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
-    const uint32_t warps = gridDim.x * SPLIT_WARPS_PER_CTA;
-    for (uint32_t t = blockIdx.x * SPLIT_WARPS_PER_CTA + (threadIdx.x >> 5); t < total_chunks; t += warps) {
-        const uint32_t s = b.chunk_stream[t];
-        if (b.status[s] != ST_OK || b.c_flag[t] == CH_IDLE) continue;
-        const uint32_t c = t - b.chunk_base[s];
-        ChunkResult r = decode_chunk<SINK_U16>(sm, b.in_base + b.in_off[s], b.in_size[s], c, b.chunk_bytes, b.entry_bits[t],
-                                               b.cells + b.cell_base[s] + b.c_out_off[t], b.c_out_len[t], b.c_out_off[t]);
-        if (simt::lane() == 0) {
-            uint32_t st = ST_OK;
-            if (r.flag >= CH_ERR) st = r.flag - CH_ERR;
-            else if (r.out_bytes != b.c_out_len[t] || r.flag != b.c_flag[t]) st = ST_BAD_CODE;  // cannot happen: tables are exact
-            if (st) atomicMax(&b.status[s], st);
-        }
-        simt::syncwarp();
-    }
-}
 
 // Cells -> bytes. A marker in chunk c points into the 32 KiB of output that precede the chunk,
 // i.e. into the TAIL (last 32 KiB) of the chunks before it. Only the tails therefore form a serial

@@ -155,10 +155,11 @@ int dbg_bsplit_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *fallbacks)
  * chunk entry points that needed more than one decode run (strictly periodic symbol streams). Diagnostics only. */
 int dbg_fx_stats(const dbg_ctx *ctx, uint64_t *streams, uint64_t *handed_back, uint64_t *extra_runs);
 
-/* Diagnostics of the block-split path, counted on the device (waits for it): v[0] Huffman blocks where the lane-parallel
- * decode was attempted, v[1] blocks it decoded whole, v[2] blocks it decoded a prefix of, v[3] chunks
- * whose recorded tokens were expanded, v[4] chunks that were Huffman-decoded a second time instead. */
-int dbg_lane_stats(const dbg_ctx *ctx, uint32_t v[5]);
+/* Diagnostics of the lane-parallel block decode, counted on the device (waits for it). Block-split
+ * path: v[0] rounds, v[1] rounds that met end-of-block, v[2] rounds that stopped before it, v[3] chunks whose recorded
+ * tokens were expanded, v[4] chunks that were Huffman-decoded a second time instead. Warp-per-stream kernel: v[5]
+ * rounds, v[6] rounds that met end-of-block, v[7] rounds that did not. */
+int dbg_lane_stats(const dbg_ctx *ctx, uint32_t v[8]);
 
 /* Optional timing of the kernel groups, for roofline reports: after dbg_profile_enable(ctx, 1) every group below is
  * bracketed by CUDA events on the stream it runs on. dbg_profile_read_tag() waits for the brackets of one group and

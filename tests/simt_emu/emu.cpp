@@ -85,6 +85,7 @@ static void run_warp(void (*body)(void *), void *arg, int reverse)
 #include "../../debigulator_b200/csrc/inflate_core.h"
 
 struct InflateArgs {
+    uint32_t *scratch;  // token scratch of the lane-parallel rounds (nullptr: plain symbol walk)
     dbg::InflateSmem *sm;
     const uint8_t *in;
     uint64_t in_size;
@@ -97,7 +98,7 @@ static void inflate_body(void *p)
 {
     InflateArgs *a = (InflateArgs *)p;
     int l = simt::lane();
-    a->status[l] = dbg::inflate_warp(a->sm, a->in, a->in_size, a->out, a->cap, &a->final_size[l]);
+    a->status[l] = dbg::inflate_warp(a->sm, a->in, a->in_size, a->out, a->cap, &a->final_size[l], a->scratch);
 }
 
 // Returns the status (or 0x1000 | lane if the lanes disagree, which would be a
@@ -116,6 +117,7 @@ extern "C" uint32_t emu_inflate(const uint8_t *in, uint64_t in_size, uint8_t *ou
     dbg::InflateSmem *sm = (dbg::InflateSmem *)aligned_alloc(16, sizeof(dbg::InflateSmem));
     memset(sm, 0xCD, sizeof(*sm));
     InflateArgs a;
+    a.scratch = (misalign & 16) ? nullptr : (uint32_t *)malloc(dbg::LB_ROUND_TOKENS * 4);  // bit 4 of `misalign`: rounds off
     a.sm = sm;
     a.in = src;
     a.in_size = in_size;
@@ -126,6 +128,7 @@ extern "C" uint32_t emu_inflate(const uint8_t *in, uint64_t in_size, uint8_t *ou
     for (int i = 1; i < 32; i++)
         if (a.status[i] != st || a.final_size[i] != a.final_size[0]) st = 0x1000 | i;
     *final_size = a.final_size[0];
+    free(a.scratch);
     free(sm);
     free(arena);
     return st;

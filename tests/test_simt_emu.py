@@ -263,3 +263,60 @@ def test_lane_parallel_block_decode_kernel_source(emu, ref):
                 assert False, (k, region, st)
     emu.emu_lane_block_stats(C.byref(tried), C.byref(done), 0)
     assert done.value >= 60 and done.value >= tried.value // 2, (tried.value, done.value)
+
+
+def test_lane_parallel_rounds_in_the_warp_per_stream_decoder(emu, ref):
+    """inflate_warp (the warp-per-stream kernel's body) with its lane-parallel rounds: Huffman blocks are taken in rounds of
+    8 KiB, tokens through the warp's scratch, expanded into the output at once; the ordinary symbol walk finishes what a
+    round leaves. Whole streams, damaged streams, tight capacities -- every status and byte against the reference."""
+    import zlib
+    import numpy as np
+    from debigulator_b200 import corpus
+    emu.emu_lane_block_stats.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]
+    tried, done = C.c_uint32(0), C.c_uint32(0)
+    emu.emu_lane_block_stats(C.byref(tried), C.byref(done), 1)
+    rng = np.random.default_rng(12)
+    img = corpus.gradient_noise_rgba(200, 160, 6)
+    text = corpus.word_salad(300000, 22)
+    cases = [
+        corpus.raw_deflate(text, 6),
+        corpus.raw_deflate(text[:200000], 6, zlib.Z_FIXED),
+        corpus.fixed_block_deflate(corpus.png_filter_rows(img, 4)),
+        corpus.raw_deflate(corpus.low_entropy(200000, 3, 5), 6, zlib.Z_HUFFMAN_ONLY),
+        corpus.raw_deflate(corpus.runs(1500000, 5), 6),
+        corpus.raw_deflate(corpus.periodic(300000, 2, 31000), 9),
+        corpus.mixed_deflate(text, 4),
+        corpus.raw_deflate(bytes(rng.integers(0, 256, 100000, dtype=np.uint8)) + text[:100000], 6),
+    ]
+    variants = [(z, None) for z in cases]
+    for z in cases[:4]:
+        b = bytearray(z)
+        b[len(b) // 2 + 3] ^= 0x04
+        variants.append((bytes(b), None))
+        variants.append((z[: len(z) * 3 // 5], None))
+    want0 = ref.inflate(cases[0], 400000)[1]
+    variants.append((cases[0], len(want0)))            # exact capacity
+    variants.append((cases[0], len(want0) - 1))        # one byte short: overflow
+    variants.append((cases[0], len(want0) // 2))
+    for k, (z, cap) in enumerate(variants):
+        tight = cap is not None
+        cap = cap if tight else 1600000
+        if cap < len(z):
+            continue
+        # (the reference writes past a capacity that is too small -- undefined behaviour, it is not called there)
+        want_good, want = (1, want0) if tight else ref.inflate(z, cap)
+        for rounds_off in (0, 16):
+            st, out = emu_inflate(emu, z, cap, ((3 * k) % 16) | rounds_off, k & 1)
+            assert st < 0x1000, (k, hex(st))
+            if tight:
+                assert (st == 0 and out == want0) if cap >= len(want0) else st == 9, (k, cap, st)
+            elif k < len(cases):
+                assert st == 0 and want_good == 1 and out == want, (k, rounds_off, st)
+            elif want_good:
+                # the reference succeeded on a damaged / short stream: same bytes, unless it ran over the capacity
+                # (undefined behaviour there; this decoder reports the overflow)
+                assert (st == 0 and out == want) or (st == 9 and len(want) > cap), (k, rounds_off, st)
+            elif st == 0:
+                assert False, (k, rounds_off, "reference failed, decoder did not")
+    emu.emu_lane_block_stats(C.byref(tried), C.byref(done), 0)
+    assert done.value >= 60, (tried.value, done.value)
