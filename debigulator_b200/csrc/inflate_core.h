@@ -376,9 +376,22 @@ DBG_DEV void copy_stored(uint8_t *dst, const uint8_t *src, uint32_t len)
     const uint32_t sh = (uint32_t)((uintptr_t)src & 3) * 8;
     const uint32_t *s4 = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
     uint32_t *d4 = (uint32_t *)dst;
-    for (uint32_t i = ln; i < words; i += 32) {
+    // four words per lane and step, all loads before the stores: one memory round trip per 512 bytes instead of per 128
+    // (ncu: 57 % of the kernel's stall samples sat on the funnel shift of the one-word loop when stored members dominate)
+    uint32_t i = ln;
+    for (; i + 96 < words; i += 128) {
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            lo[j] = s4[i + 32 * j];
+            hi[j] = sh ? s4[i + 32 * j + 1] : 0u;  // s4[.. + 1] still overlaps the source when sh != 0
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) d4[i + 32 * j] = sh ? simt::funnel_r(lo[j], hi[j], sh) : lo[j];
+    }
+    for (; i < words; i += 32) {
         uint32_t lo = s4[i];
-        uint32_t v = sh ? simt::funnel_r(lo, s4[i + 1], sh) : lo;  // s4[i + 1] still overlaps the source when sh != 0
+        uint32_t v = sh ? simt::funnel_r(lo, s4[i + 1], sh) : lo;
         d4[i] = v;
     }
     const uint32_t done = words << 2;
@@ -796,7 +809,8 @@ struct LaneBits {
     uint32_t boff;      // bit offset of the stream start inside a[0]
     uint32_t last;      // index of the last word before the 16-byte boundary at or after the stream end (readable by contract,
                         // the same bytes the warp-per-stream reader sees); words past it read as zero
-    uint32_t widx;      // next word to fetch
+    uint32_t widx;      // index of the word held in `nxt`
+    uint32_t nxt;       // the next word, already on its way when the buffer runs low (its latency hides behind a symbol)
     uint32_t nb;        // valid bits in buf (>= 32 whenever a symbol is decoded)
     uint64_t buf;       // next stream bits, LSB first
 
@@ -817,13 +831,15 @@ struct LaneBits {
         buf = two >> sh;
         nb = 64 - sh;
         widx += 2;
+        nxt = word(widx);
     }
     DBG_DEVM void refill()
     {
         if (nb <= 32) {
-            buf |= (uint64_t)word(widx) << nb;
+            buf |= (uint64_t)nxt << nb;
             widx++;
             nb += 32;
+            nxt = word(widx);
         }
     }
     DBG_DEVM void drop(uint32_t n)
@@ -1235,72 +1251,98 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
             uint32_t st = read_huffman_tables(w, sm, btype, bt);
             if (st) return st;
             uint32_t why = END_EOB;
-            if ((SINK == SINK_TOKENS || SINK == SINK_BYTES) && k.lanes && k.lane_skip) {
-                k.lane_skip--;  // this block is left to the symbol walk (rounds achieved nothing on the blocks before it)
-            } else if ((SINK == SINK_TOKENS || SINK == SINK_BYTES) && k.lanes) {
-                // lane-parallel rounds (lane_round above): one per presumed extent of the block. SINK_TOKENS: the extent
-                // is the caller's next boundary hint and the tokens go straight to the chunk's token area. SINK_BYTES: no
-                // hint, so the block is taken in rounds of LB_ROUND_BITS, each round's tokens go through the warp's
-                // scratch and are expanded into the output right away. Whatever a round leaves (a broken chain, the
-                // rule-Q2 limit, the last bits of the block) decode_symbols() below finishes with the same tables.
-                bool block_done = false;
-                for (;;) {
-                    const uint64_t p0 = w.abs_bits();
-                    const uint64_t in_end = 8 * g.end_byte;
-                    LaneRound lr;
-                    uint32_t got;
-                    if (SINK == SINK_TOKENS) {
-                        const bool hinted = stop_bit < in_end;
-                        uint64_t ext = (hinted ? stop_bit : in_end) > p0 ? (hinted ? stop_bit : in_end) - p0 : 0;
-                        if (!hinted && ext > LB_NOHINT_EXTENT) ext = LB_NOHINT_EXTENT;
-                        if (k.ntok >= k.tok_cap) break;
-                        got = lane_round(sm, bt, w.base, g, p0, ext, k.tok + k.ntok, k.tok_cap - k.ntok, lr, k.lb_stats);
-                        if (got == LB_UNUSED) break;
-                        k.ntok += lr.ntok;
-                        k.pos += lr.out;
-                    } else {
-                        uint64_t ext = in_end > p0 ? in_end - p0 : 0;
-                        if (ext > k.round_bits) ext = k.round_bits;
-                        got = lane_round(sm, bt, w.base, g, p0, ext, k.tok, k.tok_cap, lr, k.lb_stats);
-                        if (got == LB_UNUSED) {
-                            if (ext >= 4 * LB_MIN_SUB) {  // (not the short tail of a stream)
+            // Lane-parallel rounds (lane_round above) alternate with the lane-cooperative symbol walk (decode_symbols) until
+            // the block has ended. SINK_TOKENS: the round's extent is the caller's next boundary hint and the tokens go
+            // straight to the chunk's token area (one round, the walk finishes the block). SINK_BYTES: no hint, so the
+            // block is taken in rounds of k.round_bits, each round's tokens go through the warp's scratch and are expanded
+            // into the output right away; where a round's chain breaks the walk decodes a stretch and the rounds go on.
+            bool block_done = false;
+            bool use_lanes = (SINK == SINK_TOKENS || SINK == SINK_BYTES) && k.lanes;
+            if (use_lanes && k.lane_skip) {
+                k.lane_skip--;  // this block is left to the walk (rounds achieved nothing on the blocks before it)
+                use_lanes = false;
+            }
+            for (;;) {
+                bool stretch = false;
+                if (use_lanes) {
+                    for (;;) {
+                        const uint64_t p0 = w.abs_bits();
+                        const uint64_t in_end = 8 * g.end_byte;
+                        LaneRound lr;
+                        uint32_t got;
+                        if (SINK == SINK_TOKENS) {
+                            const bool hinted = stop_bit < in_end;
+                            uint64_t ext = (hinted ? stop_bit : in_end) > p0 ? (hinted ? stop_bit : in_end) - p0 : 0;
+                            if (!hinted && ext > LB_NOHINT_EXTENT) ext = LB_NOHINT_EXTENT;
+                            use_lanes = false;  // one round per hinted extent
+                            if (k.ntok >= k.tok_cap) break;
+                            got = lane_round(sm, bt, w.base, g, p0, ext, k.tok + k.ntok, k.tok_cap - k.ntok, lr, k.lb_stats);
+                            if (got == LB_UNUSED) break;
+                            k.ntok += lr.ntok;
+                            k.pos += lr.out;
+                        } else {
+                            uint64_t ext = in_end > p0 ? in_end - p0 : 0;
+                            if (ext > k.round_bits) ext = k.round_bits;
+                            got = lane_round(sm, bt, w.base, g, p0, ext, k.tok, k.tok_cap, lr, k.lb_stats);
+                            if (got == LB_UNUSED) {
+                                if (ext >= 4 * LB_MIN_SUB) {  // (not the short tail of a stream)
+                                    k.lane_skip = k.lane_bad < 8 ? k.lane_bad : 8;
+                                    k.lane_bad++;
+                                    stretch = true;
+                                } else {
+                                    use_lanes = false;
+                                }
+                                break;
+                            }
+                            simt::syncwarp();
+                            flush_pending(k.pd);
+                            st = expand_tokens_bytes(k.tok, lr.ntok, k.out, k.pos, k.cap);
+                            if (st) return st;
+                        }
+                        w.seek_bits(lr.resume);
+                        if (got == LB_DONE) {
+                            block_done = true;
+                            k.lane_bad = 0;
+                            break;
+                        }
+                        if (SINK == SINK_TOKENS) break;
+                        if (lr.resume - p0 < k.round_bits / 2) {  // little progress: the chain broke early
+                            // Broken in the very first lanes: data whose chains do not merge (run-length trains, window-limit
+                            // periods). Back off: after the n-th such round in a row the next min(n - 1, 8) blocks are left to
+                            // the walk. A chain that breaks further out (a dense stretch, a lane that found no merge point)
+                            // costs nothing to try again behind the spot.
+                            if (lr.used <= 2) {
                                 k.lane_skip = k.lane_bad < 8 ? k.lane_bad : 8;
                                 k.lane_bad++;
                             }
+                            stretch = true;
                             break;
                         }
-                        simt::syncwarp();
-                        flush_pending(k.pd);
-                        st = expand_tokens_bytes(k.tok, lr.ntok, k.out, k.pos, k.cap);
-                        if (st) return st;
-                    }
-                    w.seek_bits(lr.resume);
-                    if (got == LB_DONE) {
-                        block_done = true;
                         k.lane_bad = 0;
-                        break;
                     }
-                    if (lr.resume - p0 < (SINK == SINK_BYTES ? k.round_bits : LB_ROUND_BITS) / 2) {  // little progress: the chain broke early
-                        // Broken in the very first lanes: data whose chains do not merge (run-length trains, window-limit
-                        // periods). Back off: after the n-th such round in a row the next min(n - 1, 8) blocks are left to the
-                        // symbol walk. A chain that breaks further out (the next block's bits, a dense stretch) costs nothing
-                        // to try again.
-                        if (lr.used <= 2) {
-                            k.lane_skip = k.lane_bad < 8 ? k.lane_bad : 8;
-                            k.lane_bad++;
-                        }
-                        break;
+                    if (block_done) break;
+                    if (k.lane_skip) use_lanes = false;  // backing off: the walk takes the rest of this block
+                }
+                // the walk: to the end of the block, or -- between rounds -- over a stretch of a quarter round
+                bool temp_limit = false;
+                if (SINK == SINK_BYTES && use_lanes && stretch) {
+                    const uint64_t lim = w.abs_bits() + k.round_bits / 4;
+                    if (lim < g.q2_limit) {
+                        w.set_limit(lim);
+                        temp_limit = true;
                     }
-                    k.lane_bad = 0;
-                    if (SINK == SINK_TOKENS) break;                 // one round per hinted extent
                 }
-                if (block_done) {
-                    if (!more) return ST_OK;
-                    continue;
-                }
+                why = END_EOB;
+                st = decode_symbols<SINK>(w, sm, bt, k, why);
+                if (temp_limit) w.set_limit(g.q2_limit);
+                if (st) return st;
+                if (temp_limit && why == END_LIMIT) continue;  // back to the rounds
+                break;
             }
-            st = decode_symbols<SINK>(w, sm, bt, k, why);
-            if (st) return st;
+            if (block_done) {
+                if (!more) return ST_OK;
+                continue;
+            }
             if (why == END_LIMIT) {  // rule Q2
                 end = BLK_Q2;
                 return ST_OK;
