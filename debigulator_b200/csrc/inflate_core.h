@@ -1013,6 +1013,8 @@ struct LaneRound {
     uint32_t out;      // bytes they produce
     uint64_t resume;   // ring bit where the decode goes on (LB_DONE: behind the end-of-block code)
     uint32_t used;     // runs (lanes) that counted
+    uint32_t stride;   // COMPACT = false: run j's tokens start at area + j * stride ...
+    uint32_t mine;     // ... and this lane's run has `mine` of them (0 when it does not count)
 };
 
 // One lane-parallel round over the Huffman block whose tables are built, from ring bit p0 (a symbol start):
@@ -1022,6 +1024,7 @@ struct LaneRound {
 //   LB_UNUSED   nothing was decoded.
 // `ext` = presumed bits to the end of the block (from a boundary hint, or simply a round length), `area` / `area_cap`
 // = where the tokens go. `stats` (optional): [0] rounds, [1] rounds that met end-of-block, [2] rounds that did not.
+template <bool COMPACT>
 DBG_DEV uint32_t lane_round(const InflateSmem *sm, const BlockTables &bt, const uint8_t *base16, const StreamIn &g, uint64_t p0, uint64_t ext,
                             uint32_t *area, uint32_t area_cap, LaneRound &r, uint32_t *stats)
 {
@@ -1030,6 +1033,8 @@ DBG_DEV uint32_t lane_round(const InflateSmem *sm, const BlockTables &bt, const 
     r.out = 0;
     r.resume = p0;
     r.used = 0;
+    r.stride = 0;
+    r.mine = 0;
     if (ext > LB_MAX_EXTENT) ext = LB_MAX_EXTENT;
     if (ext < 4 * LB_MIN_SUB) return LB_UNUSED;
     uint32_t sub = ((uint32_t)ext + 31) / 32;
@@ -1098,8 +1103,10 @@ DBG_DEV uint32_t lane_round(const InflateSmem *sm, const BlockTables &bt, const 
     const uint32_t used = stop_flag == R_BROKEN ? stop_lane : stop_lane + 1;  // runs that count
     if (used == 0) return LB_UNUSED;
     r.used = used;
+    r.stride = stride;
     uint32_t in = ln < used ? n : 0u, io = ln < used ? out : 0u;
     const uint32_t mine = in;
+    r.mine = mine;
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t yn = simt::shfl_up(in, d), yo = simt::shfl_up(io, d);
         if (ln >= (uint32_t)d) {
@@ -1114,7 +1121,7 @@ DBG_DEV uint32_t lane_round(const InflateSmem *sm, const BlockTables &bt, const 
     r.resume = ((uint64_t)simt::shfl((uint32_t)(res >> 32), (int)stop_lane) << 32) | simt::shfl((uint32_t)res, (int)stop_lane);
     // move the runs' tokens together (run 0 is in place); forward copies, the loads of a step before its stores
     simt::syncwarp();
-    for (uint32_t j = 1; j < used; j++) {
+    for (uint32_t j = 1; COMPACT && j < used; j++) {
         const uint32_t cnt = simt::shfl(mine, (int)j), dst0 = simt::shfl(in - mine, (int)j);
         const uint32_t *src = area + (uint64_t)j * stride;
         for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
@@ -1276,14 +1283,14 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
                             if (!hinted && ext > LB_NOHINT_EXTENT) ext = LB_NOHINT_EXTENT;
                             use_lanes = false;  // one round per hinted extent
                             if (k.ntok >= k.tok_cap) break;
-                            got = lane_round(sm, bt, w.base, g, p0, ext, k.tok + k.ntok, k.tok_cap - k.ntok, lr, k.lb_stats);
+                            got = lane_round<true>(sm, bt, w.base, g, p0, ext, k.tok + k.ntok, k.tok_cap - k.ntok, lr, k.lb_stats);
                             if (got == LB_UNUSED) break;
                             k.ntok += lr.ntok;
                             k.pos += lr.out;
                         } else {
                             uint64_t ext = in_end > p0 ? in_end - p0 : 0;
                             if (ext > k.round_bits) ext = k.round_bits;
-                            got = lane_round(sm, bt, w.base, g, p0, ext, k.tok, k.tok_cap, lr, k.lb_stats);
+                            got = lane_round<false>(sm, bt, w.base, g, p0, ext, k.tok, k.tok_cap, lr, k.lb_stats);
                             if (got == LB_UNUSED) {
                                 if (ext >= 4 * LB_MIN_SUB) {  // (not the short tail of a stream)
                                     k.lane_skip = k.lane_bad < 8 ? k.lane_bad : 8;
@@ -1296,8 +1303,11 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
                             }
                             simt::syncwarp();
                             flush_pending(k.pd);
-                            st = expand_tokens_bytes(k.tok, lr.ntok, k.out, k.pos, k.cap);
-                            if (st) return st;
+                            // the runs that count, one after the other, each from its own stretch of the scratch
+                            for (uint32_t j = 0; j < lr.used; j++) {
+                                st = expand_tokens_bytes(k.tok + (uint64_t)j * lr.stride, simt::shfl(lr.mine, (int)j), k.out, k.pos, k.cap);
+                                if (st) return st;
+                            }
                         }
                         w.seek_bits(lr.resume);
                         if (got == LB_DONE) {

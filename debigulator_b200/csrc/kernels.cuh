@@ -9,7 +9,10 @@ namespace dbg {
 
 constexpr int INFLATE_WARPS_PER_CTA = 4;
 constexpr int INFLATE_THREADS = INFLATE_WARPS_PER_CTA * 32;
-constexpr int INFLATE_CTAS_PER_SM = 6;  // 24 resident streams per SM: their 32 KiB windows (3,552 x 32 KiB = 116 MB) still fit the 126 MB L2; measured 46.5 GB/s vs 43.0 at 8
+#ifndef DBG_BUILD_INFLATE_CTAS
+#define DBG_BUILD_INFLATE_CTAS 6
+#endif
+constexpr int INFLATE_CTAS_PER_SM = DBG_BUILD_INFLATE_CTAS;  // resident CTAs per SM = the register budget (80 at 6). Round 1 (symbol walk only): 6 beat 8 (L2 footprint of the 32 KiB windows). Round 2 (lane-parallel rounds): cfg2 4 -> 50.2 ms, 5 -> 37.2 ms, 6 -> 38.8 ms, but the config-5 shape 5 -> 180 ms, 6 -> 112 ms (the block-split kernels size their grids and their threshold by this number)
 
 struct InflateBatch {
     const uint8_t *in_base;
