@@ -598,13 +598,22 @@ def run_ours(args):
 
     if rank == 0:
         alg_bytes = comp_bytes + out_total  # C + U per launch
-        traffic = None  # dram read + write of one inflate launch from the committed `ncu --set full` capture
+        # dram read + write of one inflate launch from the committed `ncu --set full` capture; reported only while the
+        # kernel's sources still hash to what was captured (scripts/make_traffic_json.py)
+        traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_inflate_traffic.json")))
-            if n == N_MEMBERS and int(tj["algorithmic_bytes_per_launch"]) == int(alg_bytes):
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            from make_traffic_json import kernel_hash
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02", "inflate_traffic.json")))
+            if n != N_MEMBERS or int(tj["algorithmic_bytes_per_launch"]) != int(alg_bytes):
+                traffic_src = "no capture of this workload"
+            elif tj["kernel_sources_sha256_16"] != kernel_hash():
+                traffic_src = "stale: kernel sources changed since profiles/r02/inflate_traffic.json was captured"
+            else:
                 traffic = float(tj["traffic_bytes_per_launch"])
-        except Exception:
-            pass
+                traffic_src = "profiles/r02/inflate_traffic.json (ncu --set full; kernel source hash %s matches)" % tj["kernel_sources_sha256_16"]
+        except Exception as e:
+            traffic_src = "unavailable: %r" % (e,)
         avg_kern_ms = kern_ms / max(kern_n, 1)
         achieved = alg_bytes / (avg_kern_ms / 1e3) / 1e9
         line = {
@@ -620,7 +629,7 @@ def run_ours(args):
                     "link_ceiling": pcie},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": "profiles/r01_inflate_traffic.json (ncu --set full; kernel unchanged since)" if traffic else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "inflate_batch_kernel", "avg_launch_ms": avg_kern_ms, "launches": kern_n,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
