@@ -229,7 +229,7 @@ def _paeth(a, b, c):
 
 
 def png_filter_rows(img, filt):
-    """img: (h, w, bpp) uint8. filt 0..4 forced, -1 = per-row minimum-sum choice."""
+    """img: (h, w, bpp) uint8. filt 0..4 forced, -1 = per-row minimum-sum choice, a sequence = one filter type per row."""
     h, w, bpp = img.shape
     raw = img.reshape(h, w * bpp)
     left = np.zeros_like(raw); left[:, bpp:] = raw[:, :-bpp]
@@ -239,7 +239,11 @@ def png_filter_rows(img, filt):
              raw - ((left.astype(np.uint16) + up.astype(np.uint16)) >> 1).astype(np.uint8),
              raw - _paeth(left, up, ul)]
     out = np.empty((h, w * bpp + 1), dtype=np.uint8)
-    if filt >= 0:
+    if not np.isscalar(filt):
+        best = np.asarray(filt, dtype=np.int64)
+        out[:, 0] = best
+        out[:, 1:] = np.stack(cands)[best, np.arange(h)]
+    elif filt >= 0:
         out[:, 0] = filt
         out[:, 1:] = cands[filt]
     else:

@@ -367,8 +367,14 @@ DBG_DEV uint32_t png_scan_warp(const CrcTables *T, uint32_t lane_k, const uint8_
 }
 
 // ---------------------------------------------------------------- un-filter ----
+constexpr int UNF_RS = 68;  // ring row stride in words: (UNF_RS - 1) odd keeps the skewed accesses of the wavefront conflict-free
 struct UnfilterSmem {
-    uint32_t tile[32][33];
+    union {
+        uint32_t tile[32][33];      // palette / RGB images (png_unfilter_band)
+        uint32_t ring[33][UNF_RS];  // RGBA8 images (png_unfilter_band4): row 0 = last row of the band above, rows 1..32 = the
+                                    // band, column = pixel x & 63 (two 32-pixel blocks: the one being staged / computed and the
+                                    // one the skewed lanes are still finishing)
+    };
 };
 
 DBG_DEV uint32_t swar_add4(uint32_t a, uint32_t b)
@@ -392,6 +398,47 @@ DBG_DEV uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c)  // decode_png.c:441
         r |= (uint32_t)pr << k;
     }
     return r;
+}
+
+// Four bytes at once. absdiff4 is one VABSDIFF4 on sm_100a; ge4_hi leaves x >= y in bit 7 of every byte (the other bits
+// are garbage): bit 7 of the per-byte rounded-up average of x and 255 - y; sign_mask4 spreads bit 7 over its byte (PRMT).
+#ifndef DBG_SIMT_EMU
+DBG_DEV uint32_t absdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+DBG_DEV uint32_t sign_mask4(uint32_t v)  // __byte_perm() drops the selector's replicate-sign bit, the instruction does not
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(v));
+    return r;
+}
+#else
+DBG_DEV uint32_t absdiff4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int k = 0; k < 32; k += 8) {
+        int x = (int)((a >> k) & 255) - (int)((b >> k) & 255);
+        r |= (uint32_t)(x < 0 ? -x : x) << k;
+    }
+    return r;
+}
+DBG_DEV uint32_t sign_mask4(uint32_t v) { return ((v >> 7) & 0x01010101u) * 255u; }
+#endif
+DBG_DEV uint32_t ge4_hi(uint32_t x, uint32_t y)
+{
+    const uint32_t ny = ~y;
+    return (x | ny) - (((x ^ ny) >> 1) & 0x7f7f7f7fu);
+}
+// Paeth predictor of four channels without leaving the 32-bit word (decode_png.c:441-487: pa = |b - c|, pb = |a - c|,
+// pc = |a + b - 2c|, ties a -> b -> c). pc does not fit a byte, but it is never needed as a number: with x = b - c and
+// y = a - c it is |x + y|, i.e. pa + pb (>= both, so c loses every comparison) when x and y have the same sign, and
+// |pa - pb| when they do not; both forms agree when either is zero.
+DBG_DEV uint32_t paeth4_swar(uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t pa = absdiff4(b, c), pb = absdiff4(a, c), pcd = absdiff4(pa, pb);
+    const uint32_t same = ~(ge4_hi(b, c) ^ ge4_hi(a, c));
+    const uint32_t sel_a = ge4_hi(pb, pa) & (same | ge4_hi(pcd, pa));
+    const uint32_t sel_b = ~sel_a & (same | ge4_hi(pcd, pb));
+    const uint32_t ma = sign_mask4(sel_a), mb = sign_mask4(sel_b);
+    return (a & ma) | (~ma & ((b & mb) | (c & ~mb)));
 }
 
 template <int BPP>
@@ -422,6 +469,7 @@ DBG_DEV uint32_t load_px_l2(const uint8_t *p)
 }
 
 enum { BAND_ROWS = 32, BAND_SLOTS = 128 };
+constexpr uint32_t UNF4_MAX_W = 1u << 30;  // png_unfilter_band4 counts pixels in 32-bit signed integers
 
 // Reconstructs band `band` (rows 32*band .. 32*band+31) of one image. `scan`
 // holds h rows of (1 filter byte + w*BPP bytes); it is overwritten in place
@@ -543,13 +591,210 @@ DBG_DEV void png_unfilter_band(UnfilterSmem *sm, uint8_t *scan, uint32_t w, uint
     }
 }
 
+// ------------------------------------------------ un-filter of RGBA8 bands by row class ----
+// (decode_png.c:497-541; BASELINE configs 3 and 4.) A band's 32 filter bytes decide how it is reconstructed:
+//   * None / Up rows only: every column is independent -- one lane per pixel column walks down the rows straight from the
+//     scanlines to the RGBA output (elementwise, no shared memory, coalesced both ways);
+//   * None / Sub rows only: every row is independent of the rows above -- one lane per row, running per-channel sum along the
+//     row, and the band neither waits for the band above nor reads its last row;
+//   * anything with Average or Paeth rows (or a mix of Sub and Up): the skewed wavefront -- lane j = row j, j pixels behind
+//     lane j-1, `b` by shuffle, `c` = the previous `b`; all four channels of a pixel in one 32-bit word (paeth4_swar), the row's
+//     filter applied through per-lane masks so that a band of mixed rows does not diverge. The Paeth arithmetic is compiled
+//     in only for bands that have a Paeth row.
+// The row-per-lane forms work on a shared-memory ring of two 32-pixel blocks per row: block k is staged (coalesced reads,
+// the scanline's odd byte offset removed by a funnel shift), the lanes run their 32 steps, and block k-1 -- finished by every
+// lane by then -- is written out with coalesced stores. Progress towards the band below is published in the same units
+// as png_unfilter_band: t tiles done = pixels [0, 32 (t-1)) of every row are in `out`.
+DBG_DEV void unf4_publish(uint64_t *prog, uint32_t band, uint32_t tiles)
+{
+    simt::syncwarp();  // orders the other lanes' stores before lane 0's release (which is a fence of its own: no __threadfence())
+    if (prog && simt::lane() == 0) simt::st_release_u64(prog + (band & (BAND_SLOTS - 1)), ((uint64_t)(band + 1) << 32) | tiles);
+}
+DBG_DEV void unf4_wait_above(const uint64_t *prog, uint32_t band, uint32_t tiles)
+{
+    if (prog) {
+        const uint64_t need = ((uint64_t)band << 32) | tiles;
+        const uint64_t *slot = prog + ((band - 1) & (BAND_SLOTS - 1));
+        while (simt::ld_acquire_u64(slot) < need) simt::backoff();
+        simt::syncwarp();
+    }
+}
+
+// Pixels [32k, 32k + 32) of the band's rows into registers, one row per register: one aligned word per lane, the next word
+// from the lane above it (lane 31 loads its own), the scanline's byte offset (1 filter byte + 4 * pixels: any alignment)
+// removed by a funnel shift. All loads are issued before the first is used.
+DBG_DEV void unf4_load_block(const uint8_t *scan, uint64_t stride, uint32_t r0, uint32_t rows, uint32_t x_blk, uint32_t w,
+                             uint32_t (&v)[32])
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    uint32_t hi31[32];
+#pragma unroll
+    for (uint32_t jj = 0; jj < 32; jj++) {
+        v[jj] = 0;
+        hi31[jj] = 0;
+        if (jj < rows) {
+            const uintptr_t p = (uintptr_t)(scan + (uint64_t)(r0 + jj) * stride + 1 + (uint64_t)x_blk * 4);
+            const uint32_t *q = (const uint32_t *)(p & ~(uintptr_t)3);
+            if (x_blk <= w) v[jj] = q[0];  // the word after the last pixel's holds its last 1..3 bytes
+            if (ln == 31 && x_blk < w && (p & 3)) hi31[jj] = q[1];
+        }
+    }
+#pragma unroll
+    for (uint32_t jj = 0; jj < 32; jj++) {
+        if (jj < rows) {
+            const uint32_t sh = (uint32_t)((uintptr_t)(scan + (uint64_t)(r0 + jj) * stride + 1) & 3) * 8;
+            uint32_t hi = simt::shfl_down(v[jj], 1);
+            if (ln == 31) hi = hi31[jj];
+            v[jj] = simt::funnel_r(v[jj], hi, sh);
+        }
+    }
+}
+
+// MODE 0: None / Sub rows; 1: general without Paeth rows; 2: general
+template <int MODE>
+DBG_DEV void unf4_rows(UnfilterSmem *sm, const uint8_t *scan, uint32_t w, uint32_t h, uint32_t *out32, uint32_t band, uint64_t *prog,
+                       uint32_t ft, bool needs_up)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint64_t stride = (uint64_t)w * 4 + 1;
+    const uint32_t r0 = band * BAND_ROWS;
+    const uint32_t rows = h - r0 < BAND_ROWS ? h - r0 : BAND_ROWS;
+    const bool row_ok = ln < rows;
+    const uint32_t nblk = (w + 31) / 32, ntiles = nblk + 1;
+    const uint32_t m_sub = ft == 1 ? ~0u : 0u, m_up = ft == 2 ? ~0u : 0u, m_avg = ft == 3 ? ~0u : 0u, m_paeth = ft == 4 ? ~0u : 0u;
+    const uint32_t keep = ft <= 4 ? ~0u : 0u;  // :528-540 unknown filter -> 0 in the no-assert build
+    const uint32_t w_eff = row_ok ? w : 0;
+    uint32_t *my = sm->ring[1 + ln];
+    uint32_t prev_out = 0, prev_b = 0;
+    // Lanes j > 0 begin j pixels left of the image: there the ring (the half block 0 does not use), hence every input and
+    // every result, is zero, which is what the first pixel's `a` and `c` have to be.
+    for (uint32_t jj = 0; jj < 33; jj++) sm->ring[jj][32 + ln] = 0;
+    uint32_t v[32], up = 0;
+    unf4_load_block(scan, stride, r0, rows, ln, w, v);
+    if (MODE != 0 && needs_up) {
+        unf4_wait_above(prog, band, 2 < ntiles ? 2 : ntiles);
+        if (ln < w) up = simt::ldcg_u32(out32 + (uint64_t)(r0 - 1) * w + ln);
+    }
+    for (uint32_t k = 0; k < ntiles; k++) {
+        if (k < nblk) {
+            const uint32_t col = (32 * k + ln) & 63;
+#pragma unroll
+            for (uint32_t jj = 0; jj < 32; jj++)
+                if (jj < rows) sm->ring[1 + jj][col] = v[jj];
+            if (MODE != 0) sm->ring[0][col] = up;
+        }
+        simt::syncwarp();
+#pragma unroll 4
+        for (uint32_t i = 0; i < 32; i++) {
+            const uint32_t x = 32 * k + i - ln;  // "negative" left of the image
+            const uint32_t cx = x & 63;
+            uint32_t b = 0;
+            if (MODE != 0) {
+                b = simt::shfl_up(prev_out, 1);
+                if (ln == 0) b = sm->ring[0][cx];
+            }
+            const uint32_t cur = my[cx];
+            const uint32_t a = prev_out;
+            uint32_t pred = a & m_sub;
+            if (MODE != 0) {
+                pred |= (b & m_up) | (swar_havg4(a, b) & m_avg);
+                if (MODE == 2) pred |= paeth4_swar(a, b, prev_b) & m_paeth;
+            }
+            const uint32_t o = swar_add4(cur, pred) & keep;
+            if (x < w_eff) my[cx] = o;
+            prev_out = o;  // past the end of the row it is read by no one
+            prev_b = b;
+        }
+        simt::syncwarp();
+        // the next block's loads are in flight while the finished block is written out and published
+        if (k + 1 < nblk) unf4_load_block(scan, stride, r0, rows, 32 * (k + 1) + ln, w, v);
+        if (k >= 1) {
+            const uint32_t x_out = 32 * (k - 1) + ln, oc = x_out & 63;
+            if (x_out < w) {
+#pragma unroll 8
+                for (uint32_t jj = 0; jj < rows; jj++) out32[(uint64_t)(r0 + jj) * w + x_out] = sm->ring[1 + jj][oc];
+            }
+        }
+        unf4_publish(prog, band, k + 1);
+        if (MODE != 0 && needs_up && k + 1 < nblk) {
+            unf4_wait_above(prog, band, k + 3 < ntiles ? k + 3 : ntiles);
+            const uint32_t xn = 32 * (k + 1) + ln;
+            up = xn < w ? simt::ldcg_u32(out32 + (uint64_t)(r0 - 1) * w + xn) : 0;
+        }
+    }
+}
+
+// None / Up rows only: lane = pixel column
+DBG_DEV void unf4_columns(const uint8_t *scan, uint32_t w, uint32_t h, uint32_t *out32, uint32_t band, uint64_t *prog, uint32_t ft,
+                          bool needs_up)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint64_t stride = (uint64_t)w * 4 + 1;
+    const uint32_t r0 = band * BAND_ROWS;
+    const uint32_t rows = h - r0 < BAND_ROWS ? h - r0 : BAND_ROWS;
+    const uint32_t nblk = (w + 31) / 32, ntiles = nblk + 1;
+    const uint32_t up_rows = simt::ballot(ft == 2);
+    uint32_t v[32];
+    for (uint32_t k = 0; k < nblk; k++) {
+        const uint32_t x = 32 * k + ln;
+        unf4_load_block(scan, stride, r0, rows, x, w, v);
+        uint32_t acc = 0;
+        if (needs_up) {
+            unf4_wait_above(prog, band, k + 2 < ntiles ? k + 2 : ntiles);
+            if (x < w) acc = simt::ldcg_u32(out32 + (uint64_t)(r0 - 1) * w + x);
+        }
+#pragma unroll
+        for (uint32_t jj = 0; jj < 32; jj++) {
+            if (jj < rows) {
+                acc = (up_rows >> jj) & 1 ? swar_add4(v[jj], acc) : v[jj];
+                if (x < w) out32[(uint64_t)(r0 + jj) * w + x] = acc;
+            }
+        }
+        unf4_publish(prog, band, k + 2 < ntiles ? k + 2 : ntiles);
+    }
+    if (nblk == 0) unf4_publish(prog, band, ntiles);
+}
+
+DBG_DEV void png_unfilter_band4(UnfilterSmem *sm, const uint8_t *scan, uint32_t w, uint32_t h, uint8_t *out, uint32_t band,
+                                uint64_t *prog)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    const uint64_t stride = (uint64_t)w * 4 + 1;
+    const uint32_t r0 = band * BAND_ROWS;
+    const uint32_t r = r0 + ln;
+    const uint32_t ft = r < h ? scan[(uint64_t)r * stride] : 0;
+    const uint32_t ntiles = (w + 31) / 32 + 1;
+    // This band publishes in the slot band - BAND_SLOTS used: that band must have finished (a band whose first row is None or
+    // Sub does not wait for the band above, so "the band BAND_SLOTS - 1 above is done" would not imply it, and a late
+    // publication of the old band would take the slot backwards under this band's readers). Its only reader, one band further
+    // down, then finds a larger value than it waits for, which is right: everything it wants is there.
+    if (prog && band >= BAND_SLOTS) {
+        const uint64_t done = ((uint64_t)(band - BAND_SLOTS + 1) << 32) | ntiles;
+        const uint64_t *slot = prog + (band & (BAND_SLOTS - 1));
+        while (simt::ld_acquire_u64(slot) < done) simt::backoff();
+        simt::syncwarp();
+    }
+    const bool has_sub = simt::any(ft == 1), has_up = simt::any(ft == 2), has_avg = simt::any(ft == 3), has_paeth = simt::any(ft == 4),
+               has_bad = simt::any(ft > 4);
+    const uint32_t ft0 = simt::shfl(ft, 0);
+    const bool needs_up = r0 > 0 && ft0 >= 2 && ft0 <= 4;  // only the band's first row looks at the band above
+    uint32_t *out32 = (uint32_t *)out;
+    if (!has_avg && !has_paeth && !has_bad && !has_up) unf4_rows<0>(sm, scan, w, h, out32, band, prog, ft, false);
+    else if (!has_avg && !has_paeth && !has_bad && !has_sub) unf4_columns(scan, w, h, out32, band, prog, ft, needs_up);
+    else if (!has_paeth) unf4_rows<1>(sm, scan, w, h, out32, band, prog, ft, needs_up);
+    else unf4_rows<2>(sm, scan, w, h, out32, band, prog, ft, needs_up);
+}
+
 // Whole image by one warp (bands in order, no hand-off needed).
 template <int BPP>
 DBG_DEV void png_unfilter_warp(UnfilterSmem *sm, uint8_t *scan, uint32_t w, uint32_t h, uint8_t *out, const uint8_t *plte,
                                uint32_t plte_size)
 {
-    for (uint32_t band = 0; band * BAND_ROWS < h; band++)
-        png_unfilter_band<BPP>(sm, scan, w, h, out, plte, plte_size, band, nullptr);
+    for (uint32_t band = 0; band * BAND_ROWS < h; band++) {
+        if (BPP == 4 && w <= UNF4_MAX_W) png_unfilter_band4(sm, scan, w, h, out, band, nullptr);
+        else png_unfilter_band<BPP>(sm, scan, w, h, out, plte, plte_size, band, nullptr);
+        simt::syncwarp();
+    }
 }
 
 }  // namespace dbg

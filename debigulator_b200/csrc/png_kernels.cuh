@@ -15,7 +15,7 @@ struct PngLayout {
     PngInfo *info;
     uint32_t *band_base;  // n + 1: first un-filter work item (32-row band) of every image
     uint64_t *band_prog;  // BAND_SLOTS per image: band pipeline hand-off
-    uint32_t *band_counter;
+    uint32_t *band_counter;  // [0] work-queue head, [1] number of fetches, [2] band levels (0: items in image order)
     ScanQueues queues;     // deferred CRC / copy segments of large chunks
     uint32_t *task_counter;
     uint8_t *idat;  // compacted IDAT payloads
@@ -230,10 +230,11 @@ __global__ void png_verify_kernel(PngBatch b)
 __global__ void __launch_bounds__(PLAN_THREADS) png_bands_kernel(PngBatch b)
 {
     __shared__ uint32_t sh[PLAN_THREADS];
-    __shared__ uint32_t carry;
+    __shared__ uint32_t carry, max_nb;
     const int t = threadIdx.x;
     if (t == 0) {
         carry = 0;
+        max_nb = 0;
         *b.lay.band_counter = 0;
     }
     __syncthreads();
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) png_bands_kernel(PngBatch b)
                 for (int j = 0; j < 8; j++) b.lay.band_prog[(uint64_t)i * BAND_SLOTS + k + j] = 0;
         }
         sh[t] = nb;
+        if (nb) atomicMax(&max_nb, nb);
         __syncthreads();
         for (int d = 1; d < PLAN_THREADS; d <<= 1) {
             uint32_t v = t >= d ? sh[t - d] : 0;
@@ -258,11 +260,22 @@ __global__ void __launch_bounds__(PLAN_THREADS) png_bands_kernel(PngBatch b)
         if (t == PLAN_THREADS - 1) carry += sh[t];
         __syncthreads();
     }
-    if (t == 0) b.lay.band_base[b.n] = carry;
+    if (t == 0) {
+        b.lay.band_base[b.n] = carry;
+        // Order of the work items. Band-major -- band 0 of every image, then band 1 of every image, ... (fetch f = band f / n of
+        // image f % n, skipped when the image is not that tall) -- keeps the resident warps busy: by the time a warp takes band
+        // k of an image, band k-1 is well ahead. In image order the 32-row bands of one image start two tiles apart, so with
+        // a few thousand warps resident most of them would sit waiting for the band above. When the heights differ so much that
+        // most fetches would be skips, items go in image order.
+        const uint64_t fetches = (uint64_t)b.n * max_nb;
+        const bool by_band = fetches <= 8ull * carry + 4096 && fetches < (1ull << 31);
+        b.lay.band_counter[1] = by_band ? (uint32_t)fetches : carry;
+        b.lay.band_counter[2] = by_band ? max_nb : 0;
+    }
 }
 
-// Pass D: scanline reconstruction into RGBA. Persistent warps take (image, band) items in order from a
-// global counter; the bands of one image form a pipeline (png_unfilter_band), so a single large image
+// Pass D: scanline reconstruction into RGBA. Persistent warps take (image, band) items in order (see
+// png_bands_kernel) from a global counter; the bands of one image form a pipeline (png_unfilter_band), so a single large image
 // keeps hundreds of warps busy instead of one.
 constexpr int UNF_WARPS = 4;
 __global__ void __launch_bounds__(UNF_WARPS * 32, 6) png_unfilter_kernel(PngBatch b, uint8_t *out_base, const uint64_t *out_off,
@@ -271,20 +284,27 @@ __global__ void __launch_bounds__(UNF_WARPS * 32, 6) png_unfilter_kernel(PngBatc
     __shared__ UnfilterSmem sm_all[UNF_WARPS];
     UnfilterSmem *sm = &sm_all[threadIdx.x >> 5];
     const uint32_t ln = (uint32_t)simt::lane();
-    const uint32_t total = b.lay.band_base[b.n];
+    const uint32_t total = b.lay.band_counter[1], levels = b.lay.band_counter[2];
     for (;;) {
         uint32_t t = 0;
         if (ln == 0) t = atomicAdd(b.lay.band_counter, 1u);
         t = simt::shfl(t, 0);
         if (t >= total) break;
-        // image of work item t: last i with band_base[i] <= t
-        uint32_t lo = 0, hi = b.n;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (b.lay.band_base[mid] <= t) lo = mid;
-            else hi = mid;
+        uint32_t i, band;
+        if (levels) {  // band-major order
+            band = t / b.n;
+            i = t - band * b.n;
+            if (band >= b.lay.band_base[i + 1] - b.lay.band_base[i]) continue;
+        } else {  // image of work item t: last i with band_base[i] <= t
+            uint32_t lo = 0, hi = b.n;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (b.lay.band_base[mid] <= t) lo = mid;
+                else hi = mid;
+            }
+            i = lo;
+            band = t - b.lay.band_base[i];
         }
-        const uint32_t i = lo, band = t - b.lay.band_base[i];
         uint32_t st = b.lay.pre_status[i];
         if (st == ST_OK) st = b.lay.inf_status[i];
         if (st == ST_OK) {
@@ -299,7 +319,8 @@ __global__ void __launch_bounds__(UNF_WARPS * 32, 6) png_unfilter_kernel(PngBatc
                 uint8_t *out = out_base + out_off[i];
                 const uint8_t *file = b.in_base + b.in_off[i];
                 uint64_t *prog = b.lay.band_prog + (uint64_t)i * BAND_SLOTS;
-                if (info.bpp == 4) png_unfilter_band<4>(sm, scan, info.w, info.h, out, nullptr, 0, band, prog);
+                if (info.bpp == 4 && info.w <= UNF4_MAX_W) png_unfilter_band4(sm, scan, info.w, info.h, out, band, prog);
+                else if (info.bpp == 4) png_unfilter_band<4>(sm, scan, info.w, info.h, out, nullptr, 0, band, prog);
                 else if (info.bpp == 3) png_unfilter_band<3>(sm, scan, info.w, info.h, out, nullptr, 0, band, prog);
                 else png_unfilter_band<1>(sm, scan, info.w, info.h, out, file + info.plte_off, info.plte_size, band, prog);
             }

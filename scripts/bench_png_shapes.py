@@ -7,7 +7,8 @@ from bench import make_unique, pack
 W=int(sys.argv[1]); H=int(sys.argv[2]); N=int(sys.argv[3]); U=int(sys.argv[4])
 def gen(i):
     from debigulator_b200 import corpus
-    return corpus.png_cfg3(i*6+5, W, H)   # forced Paeth
+    f = os.environ.get('PNG_FILT', '4')   # forced Paeth by default; 'mix' = config 3's i % 6 - 1
+    return corpus.png_cfg3(i if f == 'mix' else i*6+int(f)+1, W, H)
 import bench
 bench._gen=gen
 def _g(i): return gen(i)
@@ -34,4 +35,7 @@ e0.record();
 for _ in range(2): step()
 e1.record(); torch.cuda.synchronize()
 ms=e0.elapsed_time(e1)/2
-print(json.dumps({'W':W,'H':H,'N':N,'split_max':os.environ.get('DBG_SPLIT_MAX_STREAMS','default'),'ms':ms,'Mpix_s':N*W*H/ms/1e3,'GBps':N*rgba/ms/1e6}))
+ctx.profile_enable(True); step(); torch.cuda.synchronize()
+groups={k:round(ctx.profile_read_tag(t)[0],3) for k,t in (('fx_sizes',ctx.PROF_FX_SIZES),('fx_expand',ctx.PROF_FX_EXPAND),('png_scan',ctx.PROF_PNG_SCAN),('png_unfilter',ctx.PROF_PNG_UNFILTER),('inflate',ctx.PROF_INFLATE))}
+ctx.profile_enable(False)
+print(json.dumps({'W':W,'H':H,'N':N,'filt':os.environ.get('PNG_FILT','4'),'groups_ms':groups,'split_max':os.environ.get('DBG_SPLIT_MAX_STREAMS','default'),'ms':ms,'Mpix_s':N*W*H/ms/1e3,'GBps':N*rgba/ms/1e6}))

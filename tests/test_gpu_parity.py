@@ -153,6 +153,36 @@ def test_png_variants(ctx, ref):
     assert good == 1 and rgba == exp.tobytes()
 
 
+def test_png_unfilter_row_classes_vs_reference(ctx, ref):
+    """RGBA8 un-filter by row class (png_unfilter_band4): bands of None/Up rows (columns), None/Sub rows (rows), wavefront
+    bands with and without Paeth rows, every mix per band; widths around the 32-pixel block, heights around the 32-row band,
+    and images tall enough (> 128 bands) for the hand-off ring between the bands' warps to wrap."""
+    rng = np.random.default_rng(11)
+    sets = [(0,), (1,), (2,), (3,), (4,), (0, 1), (0, 2), (1, 2), (0, 1, 2, 3), (0, 1, 2, 3, 4)]
+    files, want = [], []
+    k = 0
+    for w, h in ((5, 40), (31, 33), (32, 32), (33, 31), (64, 65), (97, 40), (130, 70), (1024, 96), (40, 5000), (300, 4200)):
+        for fs in sets:
+            img = corpus.gradient_noise_rgba(w, h, 300 + k, amp=3)  # noisier images trip rule Q12 (compressed > raw)
+            if h >= 4000:  # a class per band, so that neighbouring bands of different classes hand rows to each other
+                rows = np.repeat([rng.choice(sets[(k + j) % len(sets)]) for j in range((h + 31) // 32)], 32)[:h]
+                rows = np.where(rng.random(h) < 0.9, rows, rng.choice(fs, size=h))
+            else:
+                rows = rng.choice(fs, size=h)
+            files.append(corpus.write_png(img, filt=rows, level=1, strategy=zlib.Z_FIXED, single_block=(k % 3 == 0)))
+            want.append(img.tobytes())
+            k += 1
+    res = ctx.decode_png_batch(files)
+    for i, (f, (good, w, h, rgba)) in enumerate(zip(files, res)):
+        rgood, _, _, rrgba = ref.decode_png(f)
+        assert good == rgood, i
+        if not good:
+            continue
+        assert rgba == want[i], i
+        if i % 3 == 0:  # single-block streams: the reference's own pixels are right as well (defect D1 needs a late block)
+            assert rrgba == want[i], i
+
+
 def test_empty_and_ragged_batches(ctx):
     assert ctx.inflate_batch([], []) == []
     d = corpus.word_salad(1000, 1)
