@@ -351,10 +351,18 @@ def bench_png(ctx, dbg, dev, torch, name, n, w, h, uniq, peak, steps=3, e2e=True
         for _ in range(reps):
             osz, st = ctx.decode_packed(dbg.api.KIND_PNG, h_in, a4[0], a4[1], h_out, a4[2], a4[3])
         torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0) / reps
+        dt1 = max_over_ranks(time.perf_counter() - t0) / reps
         assert int(st.sum()) == 0 and int(osz.sum()) == ne * rgba, f"{name}: e2e failures"
         for k in (0, 1, ne // 2, ne - 1):
             assert h_out[k * rgba:(k + 1) * rgba].tobytes() == uniq[k % n_unique][1], f"{name}: e2e pixel mismatch"
+        # two calls in flight (dbg_pipe_*): the batch as two sub-batches, one's ramp under the other's downloads
+        ctx.trim()
+        h_out[:] = 0
+        dt, osz, st, pipe_launches = e2e_pipelined(dbg, dev.index, dbg.api.KIND_PNG, h_in, a4[0], a4[1], h_out, a4[2], a4[3], reps,
+                                                   barrier, max_over_ranks)
+        assert int(st.sum()) == 0 and int(osz.sum()) == ne * rgba, f"{name}: pipelined e2e failures"
+        for k in (0, 1, ne // 2 - 1, ne // 2, ne - 1):
+            assert h_out[k * rgba:(k + 1) * rgba].tobytes() == uniq[k % n_unique][1], f"{name}: pipelined e2e pixel mismatch"
         # link ceiling: the same arenas copied up and down at once, nothing else running (all ranks together)
         s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         barrier()
@@ -367,7 +375,12 @@ def bench_png(ctx, dbg, dev, torch, name, n, w, h, uniq, peak, steps=3, e2e=True
         ct = max_over_ranks(time.perf_counter() - t0)
         out["e2e"] = {"value": world * ne * w * h / dt / 1e6, "unit": "Mpix/s", "rgba_GBps": world * ne * rgba / dt / 1e9,
                       "ms_per_step": dt * 1e3, "images_per_gpu": ne, "h2d_bytes_per_step": int(e_in), "d2h_bytes_per_step": int(ne * rgba),
-                      "steps": reps, "api": "dbg_decode_batch_packed(kind=PNG), pinned host arenas, overlapped waves",
+                      "steps": reps, "calls_in_flight": 2,
+                      "api": "dbg_pipe_submit / dbg_pipe_wait (kind=PNG): every step's batch as two packed sub-batches of the same "
+                             "pinned host arenas, two in flight",
+                      "single_call": {"value": world * ne * w * h / dt1 / 1e6, "unit": "Mpix/s", "ms_per_step": dt1 * 1e3,
+                                      "api": "dbg_decode_batch_packed(kind=PNG), one blocking call per step", "frac_of_ceiling": ct / dt1},
+                      "kernel_launches_per_step": pipe_launches,
                       "link_ceiling": {"h2d_plus_d2h_s": ct, "Mpix_s_if_copies_only": world * ne * w * h / ct / 1e6,
                                        "ranks_copying_at_once": world, "per_rank_h2d_GBps": e_in / ct / 1e9,
                                        "per_rank_d2h_GBps": ne * rgba / ct / 1e9, "frac_of_ceiling": ct / dt}}
@@ -386,6 +399,37 @@ def bench_png(ctx, dbg, dev, torch, name, n, w, h, uniq, peak, steps=3, e2e=True
                                "sample": f"{m} of {n} images, one process per core (reference decode_png, decode_png.c:683)",
                                "single_thread": {"value": b1 / 4 / s1[0] / 1e6, "unit": "Mpix/s", "sample": "1 image"}}
     return out
+
+
+def e2e_pipelined(dbg, dev_index, kind, h_in_np, in_off, in_size, h_out_np, out_off, out_cap, steps, barrier, max_over_ranks,
+                  parts=2, depth=2):
+    """The packed host API with `depth` calls in flight (dbg_pipe_*): every step's batch goes through the pipe as `parts`
+    consecutive sub-batches of the same pinned arenas, so one sub-batch's ramp (first upload, first kernels) runs under the
+    previous one's downloads. Every step still uploads all of its inputs and downloads all of its outputs.
+    Returns (seconds per step, out_size, status, kernel launches per step)."""
+    n = len(in_off)
+    cuts = [n * k // parts for k in range(parts + 1)]
+    pipe = dbg.Pipe(dev_index, depth)
+
+    def submit_step():
+        return [pipe.submit(kind, h_in_np, in_off[a:b], in_size[a:b], h_out_np, out_off[a:b], out_cap[a:b])
+                for a, b in zip(cuts, cuts[1:])]
+
+    for t in submit_step():  # warm-up: the contexts size their arenas and scratch
+        pipe.wait(t)
+    l0 = pipe.kernel_launches()
+    barrier()
+    t0 = time.perf_counter()
+    tickets = []
+    for _ in range(steps):
+        tickets += submit_step()  # blocks while `depth` sub-batches are in flight
+    res = [pipe.wait(t) for t in tickets]
+    dt = max_over_ranks(time.perf_counter() - t0) / steps
+    osz = np.concatenate([r[0] for r in res[-parts:]])
+    st = np.concatenate([r[1] for r in res[-parts:]])
+    launches = (pipe.kernel_launches() - l0) / steps
+    pipe.close()
+    return dt, osz, st, launches
 
 
 # ----------------------------------------------------------------------- ours ---
@@ -521,7 +565,16 @@ def run_ours(args):
     assert int(st.sum()) == 0 and int(osz.sum()) == out_total
     for k in (0, 1, 2, 3, n - 1):
         assert hout_np[k * stride:k * stride + size].tobytes() == uniq[k % N_UNIQUE][1], "e2e payload mismatch"
-    e2e_val = world * out_total * e2e_steps / e2e_s / 1e9
+    e2e_single = world * out_total * e2e_steps / e2e_s / 1e9
+    # the same with two calls in flight (dbg_pipe_*: the batch as two sub-batches, one's ramp under the other's downloads)
+    ctx.trim()
+    hout_np[:] = 0
+    pdt, osz, st, pipe_launches = e2e_pipelined(dbg, local, dbg.api.KIND_GZ, hin_np, in_off, in_size, hout_np, out_off, out_cap,
+                                                max(2, e2e_steps), barrier, max_over_ranks)
+    assert int(st.sum()) == 0 and int(osz.sum()) == out_total
+    for k in (0, 1, 2, 3, n // 2 - 1, n // 2, n - 1):
+        assert hout_np[k * stride:k * stride + size].tobytes() == uniq[k % N_UNIQUE][1], "pipelined e2e payload mismatch"
+    e2e_val = world * out_total / pdt / 1e9
     # the link ceiling of that path: the same pinned arenas copied H2D and D2H at once, nothing else running -- on
     # every rank at the same time, so that at N > 1 it is the box's ceiling (host memory / PCIe fabric), not one link's
     s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -537,7 +590,8 @@ def run_ours(args):
     dt = max_over_ranks(own_dt)
     pcie = {"h2d_plus_d2h_s": dt, "output_GBps_if_copies_only": world * out_total / dt / 1e9, "ranks_copying_at_once": world,
             "per_rank_h2d_GBps": in_total / dt / 1e9, "per_rank_d2h_GBps": out_span / dt / 1e9,
-            "e2e_frac_of_ceiling": (e2e_val / (world * out_total / dt / 1e9))}
+            "e2e_frac_of_ceiling": (e2e_val / (world * out_total / dt / 1e9)),
+            "single_call_frac_of_ceiling": (e2e_single / (world * out_total / dt / 1e9))}
     del h_out, hout_np
     torch.cuda.empty_cache()
 
@@ -625,7 +679,12 @@ def run_ours(args):
                        "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % ((comp_bytes + out_total) / 1e9),
                        "parallelism": f"{world} independent shard(s), no collective"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(in_total + 64), "d2h_bytes_per_step": int(out_span),
-                    "steps": e2e_steps, "api": "dbg_decode_batch_packed(kind=gzip), pinned host arenas",
+                    "steps": max(2, e2e_steps), "ms_per_step": pdt * 1e3, "calls_in_flight": 2,
+                    "api": "dbg_pipe_submit / dbg_pipe_wait (kind=gzip): every step's batch as two packed sub-batches of the same "
+                           "pinned host arenas, two in flight",
+                    "single_call": {"value": e2e_single, "unit": UNIT, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+                                    "api": "dbg_decode_batch_packed(kind=gzip), one blocking call per step"},
+                    "kernel_launches_per_step": pipe_launches,
                     "link_ceiling": pcie},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -6,9 +6,9 @@ a ctypes binding for tests, benchmarks and scripting; it has no decode logic of
 its own and no CPU fallback: loading fails loudly if the library is missing and
 `Context()` raises if no CUDA device is usable.
 """
-from .api import (Context, MultiContext, DebigulatorError, STATUS_NAMES, load_library, library_path,
+from .api import (Context, MultiContext, Pipe, DebigulatorError, STATUS_NAMES, load_library, library_path,
                   png_get_width_height, bmp_get_width_height)
 from . import api
 
-__all__ = ["Context", "MultiContext", "DebigulatorError", "STATUS_NAMES", "load_library", "library_path",
+__all__ = ["Context", "MultiContext", "Pipe", "DebigulatorError", "STATUS_NAMES", "load_library", "library_path",
            "png_get_width_height", "bmp_get_width_height", "api"]

@@ -71,6 +71,18 @@ def load_library():
     L.dbg_decode_batch_packed_multi.restype = i32
     L.dbg_multi_partition.argtypes = [i32, i32, u64] + [vp] * 7
     L.dbg_multi_partition.restype = i32
+    L.dbg_pipe_create.argtypes = [i32, i32]
+    L.dbg_pipe_create.restype = vp
+    L.dbg_pipe_destroy.argtypes = [vp]
+    L.dbg_pipe_destroy.restype = None
+    L.dbg_pipe_depth.argtypes = [vp]
+    L.dbg_pipe_depth.restype = i32
+    L.dbg_pipe_ctx.argtypes = [vp, i32]
+    L.dbg_pipe_ctx.restype = vp
+    L.dbg_pipe_submit.argtypes = [vp, i32, u64] + [vp] * 8
+    L.dbg_pipe_submit.restype = C.c_int64
+    L.dbg_pipe_wait.argtypes = [vp, C.c_int64]
+    L.dbg_pipe_wait.restype = i32
     L.dbg_bsplit_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.dbg_bsplit_stats.restype = i32
     L.dbg_fx_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -368,3 +380,49 @@ class MultiContext:
         if rc != 0:
             raise DebigulatorError("dbg_decode_batch_packed_multi failed (%d): %s" % (rc, (self.L.dbg_multi_last_error(self.h) or b"").decode()))
         return out_size, status, dev
+
+
+class Pipe:
+    """Several packed batches in flight on one GPU (dbg_pipe_*): submit() returns a ticket at once, wait() the batch's
+    (out_size, status). The arrays handed to submit() must stay alive and untouched until wait() has returned."""
+
+    def __init__(self, device=0, depth=2):
+        self.L = load_library()
+        self.h = self.L.dbg_pipe_create(int(device), int(depth))
+        if not self.h:
+            raise DebigulatorError("dbg_pipe_create failed: " + (self.L.dbg_last_error(None) or b"").decode())
+        self.depth = self.L.dbg_pipe_depth(self.h)
+        self._jobs = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dbg_pipe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def kernel_launches(self):
+        return sum(int(self.L.dbg_kernel_launches(self.L.dbg_pipe_ctx(self.h, k))) for k in range(self.depth))
+
+    def submit(self, kind, h_in, in_off, in_size, h_out, out_off, out_cap):
+        n = len(in_off)
+        a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (in_off, in_size, out_off, out_cap)]
+        out_size = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.uint32)
+        t = int(self.L.dbg_pipe_submit(self.h, int(kind), n, _ptr(h_in), _ptr(a[0]), _ptr(a[1]), _ptr(h_out), _ptr(a[2]), _ptr(a[3]),
+                                       _ptr(out_size), _ptr(status)))
+        if t < 0:
+            raise DebigulatorError("dbg_pipe_submit failed (%d)" % t)
+        self._jobs[t] = (a, out_size, status, h_in, h_out)
+        return t
+
+    def wait(self, ticket):
+        rc = self.L.dbg_pipe_wait(self.h, int(ticket))
+        a, out_size, status, _, _ = self._jobs.pop(ticket)
+        if rc != 0:
+            raise DebigulatorError("packed batch of ticket %d failed (%d)" % (ticket, rc))
+        return out_size, status

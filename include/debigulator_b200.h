@@ -208,6 +208,26 @@ int dbg_multi_partition(int n_devices, int kind, uint64_t n, const uint8_t *h_in
                         const uint64_t *in_size, const uint64_t *out_off, const uint64_t *out_cap, uint32_t *device_of_item,
                         uint64_t *device_cost);
 
+/* ---- several packed batches in flight on one GPU ---------------------------------------------------------------
+ * dbg_decode_batch_packed() returns when its batch is done, so back-to-back calls pay the ramp of every batch in full:
+ * the download engine idles until the first wave's kernels have finished, the upload engine after the last wave's
+ * upload. A pipe keeps `depth` batches in flight, each on a context, stream set and host thread of its own, so that one
+ * batch's ramp runs under the previous batch's downloads (a caller that streams batches through the decoder: the
+ * reference's counterpart is a loop over decode_gz() / decode_png(), decode_gz.c:123, decode_png.c:683).
+ * dbg_pipe_submit() takes the arguments of dbg_decode_batch_packed(), returns a ticket >= 0 (or a negative DBG_ERR_*)
+ * and blocks only while `depth` batches are already in flight; every buffer passed to it belongs to the pipe until
+ * dbg_pipe_wait() has returned that ticket's result (the batch call's return code). Tickets may be waited for in any
+ * order, once each. Submit and wait may be called from one thread or several. */
+typedef struct dbg_pipe dbg_pipe;
+dbg_pipe *dbg_pipe_create(int device, int depth); /* depth 1..4 */
+void dbg_pipe_destroy(dbg_pipe *p);               /* waits for the batches in flight */
+int dbg_pipe_depth(const dbg_pipe *p);
+dbg_ctx *dbg_pipe_ctx(dbg_pipe *p, int k);        /* the k-th context (counters, tunables) */
+int64_t dbg_pipe_submit(dbg_pipe *p, int kind, uint64_t n, const uint8_t *h_in, const uint64_t *in_off,
+                        const uint64_t *in_size, uint8_t *h_out, const uint64_t *out_off, const uint64_t *out_cap,
+                        uint64_t *out_size, uint32_t *status);
+int dbg_pipe_wait(dbg_pipe *p, int64_t ticket);
+
 /* ---- BMP (decode_bmp.h:14-36; decode_bmp.c:105-372) --------------------------
  * 32-bit BGRA BMP <-> RGBA8, the reference's decode_BMP / encode_BMP batched. Decode accepts what the
  * reference accepts ('BM', 40- or 108-byte DIB header, 1 plane, 32 bpp, either row order) and writes

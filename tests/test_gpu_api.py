@@ -366,6 +366,40 @@ def test_packed_multi_two_contexts_one_gpu(ref):
     m.close()
 
 
+def test_pipe_keeps_batches_in_flight(ref):
+    """dbg_pipe_*: five packed batches (gzip, PNG, gzip, ...) through a pipe of depth 2, tickets waited for out of order,
+    every item against what the members / images were made from; one member against the reference."""
+    p = dbg.Pipe(0, 2)
+    assert p.depth == 2
+    jobs = []
+    for b in range(5):
+        if b % 2 == 0:
+            members = [corpus.gz_member_cfg2(7 * b + i, 1 << 16) for i in range(300 + 50 * b)]
+            caps = [len(d) + len(g) + 64 for g, d in members]
+            packed = _pack([g for g, _ in members], caps)
+            want = [d for _, d in members]
+            kind = dbg.api.KIND_GZ
+            if b == 0:
+                rg, rout = ref.decode_gz(members[5][0], caps[5])
+                assert rg == 1 and rout == members[5][1]
+        else:
+            files, want = _png_batch(24, 640, 480, 8)
+            caps = [640 * 480 * 4] * len(files)
+            packed = _pack(files, caps)
+            kind = dbg.api.KIND_PNG
+        h_in, in_off, in_size, h_out, out_off, out_cap = packed
+        jobs.append((p.submit(kind, h_in, in_off, in_size, h_out, out_off, out_cap), packed, want, kind))
+    for k in (1, 0, 2, 4, 3):
+        ticket, (h_in, in_off, in_size, h_out, out_off, out_cap), want, kind = jobs[k]
+        osz, st = p.wait(ticket)
+        for i, d in enumerate(want):
+            assert st[i] == 0 and osz[i] == len(d), (k, i)
+            o = int(out_off[i])
+            assert h_out[o:o + len(d)].tobytes() == d, (k, i)
+    assert p.kernel_launches() > 0
+    p.close()
+
+
 def test_device_calls_on_two_streams_share_scratch_safely(ctx):
     """Two device-resident calls issued back to back on DIFFERENT streams, neither synchronised in between: the
     second must not disturb the first one's work queue and descriptors (per-context scratch)."""
