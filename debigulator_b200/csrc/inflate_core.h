@@ -647,6 +647,10 @@ DBG_DEV uint32_t decode_symbols(Window &w, InflateSmem *sm, const BlockTables &b
 {
     const uint32_t ln = (uint32_t)simt::lane();
     uint32_t flip = 0;
+    // A call that follows another one directly (a stretch between two rounds ends at its limit, the next round finds too
+    // little left and hands back to the walk) starts on candidate buffer 0 again: no lane may fill it while a slower lane
+    // is still walking the previous call's last pass in it.
+    simt::syncwarp();
     for (;;) {
         // Two words (64 start offsets) per pass when the limit is not in sight, otherwise one word
         // with the limit applied. Candidate k of the second word carries offsets relative to the first.
@@ -914,6 +918,7 @@ enum : uint32_t { CH_RUN = 0, CH_EOB = 1, CH_Q2 = 2, CH_IDLE = 3, CH_ERR = 16 };
 // function with the block's own tables (LUTs + slow_decode for codes longer than the LUT index, rule Q5 included).
 constexpr uint32_t LB_MIN_SUB = 2048;         // smallest sub-chunk, bits
 constexpr uint32_t LB_MAX_EXTENT = 1u << 20;  // largest presumed extent, bits (128 KiB of compressed data)
+constexpr uint32_t LB_TOKENS_STRETCH = 4096;     // count pass of the block-split path: bits the walk decodes between two rounds of one block
 constexpr uint32_t LB_NOHINT_EXTENT = 3u << 17;  // presumed extent when the caller has no hint, bits (48 KiB)
 constexpr uint32_t LB_ROUND_BITS = 3u << 15;   // round length of the byte sink (12 KiB of compressed data, 3,072 bits per lane; measured: cfg2 57.3 ms at 8 KiB, 54.1 at 12, 63.6 at 16)
 constexpr uint32_t LB_ROUND_TOKENS = 16384;   // its token scratch per warp (a round of the densest sensible code: 4 bits per symbol)
@@ -1260,7 +1265,8 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
             uint32_t why = END_EOB;
             // Lane-parallel rounds (lane_round above) alternate with the lane-cooperative symbol walk (decode_symbols) until
             // the block has ended. SINK_TOKENS: the round's extent is the caller's next boundary hint and the tokens go
-            // straight to the chunk's token area (one round, the walk finishes the block). SINK_BYTES: no hint, so the
+            // straight to the chunk's token area; where a round ends short of the block's end the walk decodes a stretch and another
+            // round follows. SINK_BYTES: no hint, so the
             // block is taken in rounds of k.round_bits, each round's tokens go through the warp's scratch and are expanded
             // into the output right away; where a round's chain breaks the walk decodes a stretch and the rounds go on.
             bool block_done = false;
@@ -1281,10 +1287,15 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
                             const bool hinted = stop_bit < in_end;
                             uint64_t ext = (hinted ? stop_bit : in_end) > p0 ? (hinted ? stop_bit : in_end) - p0 : 0;
                             if (!hinted && ext > LB_NOHINT_EXTENT) ext = LB_NOHINT_EXTENT;
-                            use_lanes = false;  // one round per hinted extent
-                            if (k.ntok >= k.tok_cap) break;
+                            if (k.ntok >= k.tok_cap) {
+                                use_lanes = false;
+                                break;
+                            }
                             got = lane_round<true>(sm, bt, w.base, g, p0, ext, k.tok + k.ntok, k.tok_cap - k.ntok, lr, k.lb_stats);
-                            if (got == LB_UNUSED) break;
+                            if (got == LB_UNUSED) {
+                                use_lanes = false;  // (too little left of the extent, or no room for tokens)
+                                break;
+                            }
                             k.ntok += lr.ntok;
                             k.pos += lr.out;
                         } else {
@@ -1315,7 +1326,15 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
                             k.lane_bad = 0;
                             break;
                         }
-                        if (SINK == SINK_TOKENS) break;
+                        if (SINK == SINK_TOKENS) {
+                            // The chain broke before the end of the block (a lane without a merge point, a dense stretch), or the
+                            // block is longer than the extent. The walk decodes a stretch and another round takes what is left
+                            // -- leaving the rest of the block to the walk costs a lone stream milliseconds (gzipsample.gz: one
+                            // of its five blocks). A chain that breaks in the first lanes is not tried again.
+                            if (lr.used > 2) stretch = true;
+                            else use_lanes = false;
+                            break;
+                        }
                         if (lr.resume - p0 < k.round_bits / 2) {  // little progress: the chain broke early
                             // Broken in the very first lanes: data whose chains do not merge (run-length trains, window-limit
                             // periods). Back off: after the n-th such round in a row the next min(n - 1, 8) blocks are left to
@@ -1335,8 +1354,8 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
                 }
                 // the walk: to the end of the block, or -- between rounds -- over a stretch of a quarter round
                 bool temp_limit = false;
-                if (SINK == SINK_BYTES && use_lanes && stretch) {
-                    const uint64_t lim = w.abs_bits() + k.round_bits / 4;
+                if ((SINK == SINK_BYTES || SINK == SINK_TOKENS) && use_lanes && stretch) {
+                    const uint64_t lim = w.abs_bits() + (SINK == SINK_BYTES ? k.round_bits / 4 : LB_TOKENS_STRETCH);
                     if (lim < g.q2_limit) {
                         w.set_limit(lim);
                         temp_limit = true;
@@ -1344,6 +1363,7 @@ DBG_DEV uint32_t inflate_blocks(Window &w, const StreamIn &g, InflateSmem *sm, S
                 }
                 why = END_EOB;
                 st = decode_symbols<SINK>(w, sm, bt, k, why);
+
                 if (temp_limit) w.set_limit(g.q2_limit);
                 if (st) return st;
                 if (temp_limit && why == END_LIMIT) continue;  // back to the rounds

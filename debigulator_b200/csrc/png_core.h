@@ -196,7 +196,10 @@ DBG_DEV bool scan_enqueue(ScanQueues *q, const uint8_t *p, uint64_t n, uint8_t *
     uint32_t base = 0;
     if (ln == 0) base = atomicAdd(q->ntasks, nseg);
     base = simt::shfl(base, 0);
-    if (base + nseg > q->task_cap) return false;  // the slots stay unused (len 0)
+    if (base + nseg > q->task_cap) {  // no room: the caller does the work itself; the slots that exist are marked empty
+        for (uint32_t k = base + ln; k < q->task_cap; k += 32) q->tasks[k].len = 0;  // (the scratch is reused: no stale records)
+        return false;
+    }
     for (uint32_t k = ln; k < nseg; k += 32) {
         ScanTask t;
         uint64_t o = (uint64_t)k * SCAN_SEG;

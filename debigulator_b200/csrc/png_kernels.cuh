@@ -132,9 +132,13 @@ __global__ void __launch_bounds__(PLAN_THREADS) png_plan_kernel(PngBatch b)
             __syncthreads();
         }
         if (i < b.n) {
-            b.lay.z_off[i] = (uint64_t)(uintptr_t)(b.lay.idat + (carry_z + sh_z[t] - zc));  // absolute address
-            b.lay.s_off[i] = carry_s + sh_s[t] - sc;
-            b.lay.s_cap[i] = est;  // inflate's recipient_size, decode_png.c:803-804
+            // The scratch was sized from the caller's totals (device API: total_in_bytes / total_rgba_bytes). An item that
+            // would reach past it gets no room: a null stream address fails it in png_scan_kernel, a scanline buffer of
+            // capacity 0 fails its inflate.
+            const bool z_fits = carry_z + sh_z[t] <= b.lay.idat_bytes, s_fits = carry_s + sh_s[t] <= b.lay.scan_bytes;
+            b.lay.z_off[i] = z_fits ? (uint64_t)(uintptr_t)(b.lay.idat + (carry_z + sh_z[t] - zc)) : 0ull;  // absolute address
+            b.lay.s_off[i] = s_fits ? carry_s + sh_s[t] - sc : 0ull;
+            b.lay.s_cap[i] = s_fits ? est : 0ull;  // inflate's recipient_size, decode_png.c:803-804
             b.lay.z_size[i] = 0;
             b.lay.s_size[i] = 0;
             b.lay.inf_status[i] = 0;
@@ -166,8 +170,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) png_scan_kernel(PngBatch b)
         PngInfo info;
         info.w = info.h = info.bpp = 0;
         ScanQueues q = b.lay.queues;
-        uint32_t st = png_scan_warp(&tables, lane_k, b.in_base + b.in_off[i], b.in_size[i], b.rgba_size[i], zdst, zcap, &info,
-                                    &zs, &zp, &q, i);
+        uint32_t st = ST_TOO_LARGE;  // no room in the scratch (under-reported totals, see png_plan_kernel)
+        if (zdst)
+            st = png_scan_warp(&tables, lane_k, b.in_base + b.in_off[i], b.in_size[i], b.rgba_size[i], zdst, zcap, &info, &zs, &zp,
+                               &q, i);
         if (ln == 0) {
             b.lay.z_off[i] = (uint64_t)(uintptr_t)zp;
             b.lay.z_size[i] = zs;

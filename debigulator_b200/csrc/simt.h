@@ -60,6 +60,11 @@ DBG_DEV void st_release_u64(uint64_t *p, uint64_t v)
 DBG_DEV void threadfence() { __threadfence(); }
 DBG_DEV void backoff() { __nanosleep(64); }
 DBG_DEV uint32_t ldg_u32(const uint32_t *p) { return __ldg(p); }
+DBG_DEV void ldg_u32x4(const uint32_t *p, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d)  // p 16-byte aligned
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    a = v.x, b = v.y, c = v.z, d = v.w;
+}
 DBG_DEV uint32_t atomic_inc_shared(uint32_t *p) { return atomicAdd(p, 1u); }
 DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return __ldcg(p); }
 DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return __ldcg(p); }
@@ -180,6 +185,7 @@ DBG_DEV void st_release_u64(uint64_t *p, uint64_t v) { *p = v; }
 DBG_DEV void threadfence() {}
 DBG_DEV void backoff() {}
 DBG_DEV uint32_t ldg_u32(const uint32_t *p) { return *p; }
+DBG_DEV void ldg_u32x4(const uint32_t *p, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) { a = p[0], b = p[1], c = p[2], d = p[3]; }
 DBG_DEV uint32_t atomic_inc_shared(uint32_t *p) { return (*p)++; }
 DBG_DEV uint32_t ldcg_u32(const uint32_t *p) { return *p; }
 DBG_DEV uint32_t ldcg_u8(const uint8_t *p) { return *p; }
