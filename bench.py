@@ -886,14 +886,14 @@ def run_strong(args):
     ngpu = args.gpus
     m = dbg.MultiContext(ngpu)
     if args.strong == "cfg4":
-        n = args.images or 256
+        n = args.images or 32 * ngpu  # 256 at N = 8, as BASELINE config 4 states it
         uniq = pool_map(_gen_png, [(i, PNG4_W, PNG4_H, 4) for i in range(min(PNG4_UNIQUE, n))])
         kind, w, h = dbg.api.KIND_PNG, PNG4_W, PNG4_H
         caps = [w * h * 4] * n
         unit, per_item = "Mpix/s", w * h / 1e6
         name = f"cfg4: {n} x {w}x{h} RGBA8 PNGs (stb_write, forced Paeth), one batch"
     else:
-        n = args.images or 16384
+        n = args.images or 2048 * ngpu  # 16,384 at N = 8
         uniq = [(g, None) for g, _, _ in pool_map(_gen_cfg5, list(range(64)))]
         sizes_out = [int(65536 * (256.0 ** (((i * 2654435761) % 1000) / 999.0))) for i in range(64)]
         kind = dbg.api.KIND_GZ

@@ -111,6 +111,7 @@ struct dbg_ctx {
     std::vector<int> prof_tag;  // DBG_PROF_* of every bracket
     size_t prof_used = 0;
     // tunables (environment)
+    uint32_t fx_expand_ctas = 12;   // CTAs per SM of the lane-serial path's token expansion (DBG_FX_EXPAND_CTAS)
     uint32_t fx_chunk_forced = 0, fx_group_forced = 0;  // DBG_FX_CHUNK / DBG_FX_GROUP: fixed chunk / group size (experiments)
     bool fx = true;                 // lane-serial path for single fixed-Huffman-block streams
     uint32_t bsplit_tok_per_byte = 4;             // token slots per compressed byte (0 = no tokens: decode twice)
@@ -239,6 +240,7 @@ static dbg_ctx *ctx_create(int device, const cudaStream_t *pre_wave, int n_pre, 
     if (const char *v = getenv("DBG_FX_CHUNK")) ctx->fx_chunk_forced = (uint32_t)std::min(1 << 20, std::max((int)dbg::FX_MIN_CHUNK, atoi(v))) & ~15u;
     if (const char *v = getenv("DBG_FX_GROUP")) ctx->fx_group_forced = (uint32_t)std::min(1 << 22, std::max(4096, atoi(v))) & ~15u;
     if (const char *v = getenv("DBG_FX")) ctx->fx = atoi(v) != 0;
+    if (const char *v = getenv("DBG_FX_EXPAND_CTAS")) ctx->fx_expand_ctas = (uint32_t)std::min(16, std::max(1, atoi(v)));
     if (const char *v = getenv("DBG_WAVES")) ctx->waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(v)));
     if (const char *v = getenv("DBG_PNG_WAVES")) ctx->png_waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(v)));
     if (const char *v = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(v) != 0;
@@ -578,7 +580,7 @@ static int run_fx(dbg_ctx *ctx, Slot &sl, const dbg::InflateBatch &a, cudaStream
         b.tok = (uint32_t *)sl.fx_tok.p;
         ProfScope prof(ctx, s, DBG_PROF_FX_EXPAND);
         dbg::fx_tokens_kernel<<<lane_grid, dbg::FX_LANE_THREADS, 0, s>>>(b);
-        dbg::fx_expand_kernel<<<std::min<uint32_t>((NG + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * 12),
+        dbg::fx_expand_kernel<<<std::min<uint32_t>((NG + dbg::FX_WARPS_PER_CTA - 1) / dbg::FX_WARPS_PER_CTA, (uint32_t)ctx->sm_count * ctx->fx_expand_ctas),
                                 dbg::FX_WARPS_PER_CTA * 32, 0, s>>>(b);
         // cells -> bytes: the resolve kernels see the groups as their chunks
         dbg::SplitBatch r{};

@@ -936,7 +936,9 @@ constexpr uint32_t LB_MIN_SUB = 2048;         // smallest sub-chunk, bits
 constexpr uint32_t LB_MAX_EXTENT = 1u << 20;  // largest presumed extent, bits (128 KiB of compressed data)
 constexpr uint32_t LB_TOKENS_STRETCH = 4096;     // count pass of the block-split path: bits the walk decodes between two rounds of one block
 constexpr uint32_t LB_NOHINT_EXTENT = 3u << 17;  // presumed extent when the caller has no hint, bits (48 KiB)
-constexpr uint32_t LB_ROUND_BITS = 3u << 15;   // round length of the byte sink (12 KiB of compressed data, 3,072 bits per lane; measured: cfg2 57.3 ms at 8 KiB, 54.1 at 12, 63.6 at 16)
+constexpr uint32_t LB_ROUND_BITS = 86016;     // round length of the byte sink (10.5 KiB of compressed data, 2,688 bits per lane; measured on cfg2 with the final
+                                              // kernel: 41.9 ms at 6 KiB, 40.8 at 8, 36.5 at 9, 34.7 at 10, 33.5 at 10.5, 36.7 at 11, 38.6 at 12 -- the warps' token
+                                              // scratch in flight competes with the output for the 126 MB L2)
 constexpr uint32_t LB_ROUND_TOKENS = 16384;   // its token scratch per warp (a round of the densest sensible code: 4 bits per symbol)
 constexpr uint32_t LB_MERGE_BITS = 1024;      // chains that have not merged after this many bits are given up
 constexpr uint32_t LB_STARTS = 48;            // candidate entry offsets per sub-chunk = longest possible symbol
