@@ -629,6 +629,7 @@ def run_ours(args):
     bmp = cfg5 = cfg1 = None
     if args.bmp and rank == 0 and world == 1:
         bmp = bench_bmp(ctx, dev, torch, args.bmp)
+        bmp["sprite_sheet"] = bench_sprites(ctx, dev, torch)
     if args.cfg5 and rank == 0 and world == 1:
         cfg5 = bench_cfg5(ctx, dev, torch, args.cfg5)
     if args.cfg1 and rank == 0 and world == 1:
@@ -705,6 +706,8 @@ def run_ours(args):
         if bmp:
             bmp["roofline"]["peak"] = peak
             bmp["roofline"]["frac"] = bmp["roofline"]["achieved"] / peak
+            bmp["sprite_sheet"]["roofline"]["peak"] = peak
+            bmp["sprite_sheet"]["roofline"]["frac"] = bmp["sprite_sheet"]["roofline"]["achieved"] / peak
             line["bmp"] = bmp
         print(json.dumps(line))
     if world > 1:
@@ -871,6 +874,40 @@ def bench_bmp(ctx, dev, torch, n, w=2048, h=2048):
             "config": {"workload": f"{n} x {w}x{h} 32-bit bottom-up BMP files (rows flipped), then re-encoded", "unique_images": 1},
             "roofline": {"bound": "hbm", "achieved": ach, "unit": "GB/s", "kernel": "bmp_swizzle_kernel",
                          "algorithmic_bytes_per_launch": alg, "encode_achieved": alg / (res["encode"] / 1e3) / 1e9}}
+
+
+def bench_sprites(ctx, dev, torch, n=1000, w=512, h=512):
+    """Sprite-sheet tiling (intent of concat_pngs.c:81-100): n decoded w x h RGBA8 images into one
+    sheet of ceil(sqrt(n)) columns; plain HBM traffic (every image pixel read once, every sheet pixel written once)."""
+    rgba = w * h * 4
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    d_img = torch.randint(0, 256, (n * rgba,), dtype=torch.uint8, device=dev, generator=g)
+    off = torch.arange(n, dtype=torch.int64, device=dev) * rgba
+    cols = next(c for c in range(1, n + 2) if c * c >= n)
+    rows = (n + cols - 1) // cols
+    d_sheet = torch.zeros(cols * w * rows * h * 4, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        r, c = ctx.tile_sprites_device(d_img, off, n, w, h, 0, True, d_sheet, stream=stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ctx.tile_sprites_device(d_img, off, n, w, h, 0, True, d_sheet, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    sheet = d_sheet.view(rows * h, cols * w * 4)
+    for i in (0, 1, cols, n - 1):  # spot check: tile i against its image
+        rr, cc = divmod(i, cols)
+        tile = sheet[rr * h:(rr + 1) * h, cc * w * 4:(cc + 1) * w * 4]
+        assert torch.equal(tile.reshape(-1), d_img[i * rgba:(i + 1) * rgba]), "sprite sheet mismatch"
+    assert (r, c) == (rows, cols)
+    alg = n * rgba + d_sheet.numel()
+    return {"metric": "sprite_sheet_Mpixels_per_s", "value": n * w * h / (ms / 1e3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms,
+            "config": {"workload": f"{n} x {w}x{h} RGBA8 images into one {cols} x {rows} sheet, device-resident"},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "unit": "GB/s", "kernel": "sprite_tile_kernel",
+                         "algorithmic_bytes_per_launch": alg}}
 
 
 # -------------------------------------------------------------------- strong ----

@@ -71,6 +71,11 @@ def load_library():
     L.dbg_decode_batch_packed_multi.restype = i32
     L.dbg_multi_partition.argtypes = [i32, i32, u64] + [vp] * 7
     L.dbg_multi_partition.restype = i32
+    L.dbg_tile_sprites_device.argtypes = [vp, u64, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, i32, vp, u64, C.POINTER(C.c_uint32),
+                                          C.POINTER(C.c_uint32), vp]
+    L.dbg_tile_sprites_device.restype = i32
+    L.dbg_tile_sprites.argtypes = [vp, u64, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, u64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.dbg_tile_sprites.restype = i32
     L.dbg_pipe_create.argtypes = [i32, i32]
     L.dbg_pipe_create.restype = vp
     L.dbg_pipe_destroy.argtypes = [vp]
@@ -200,6 +205,26 @@ class Context:
         ms, n = C.c_double(0), C.c_uint64(0)
         self._check(self.L.dbg_profile_read_tag(self.h, tag, C.byref(ms), C.byref(n)), "dbg_profile_read_tag")
         return float(ms.value), int(n.value)
+
+    def tile_sprites(self, images, w, h, columns=0):
+        """Sprite sheet of n decoded RGBA8 images (bytes, w * h * 4 each): (sheet bytes, rows, columns) (dbg_tile_sprites)."""
+        n = len(images)
+        cols = columns or next(c for c in range(1, n + 2) if c * c >= n)
+        cols = min(cols, n)
+        rows = (n + cols - 1) // cols
+        bufs = [C.create_string_buffer(bytes(im), len(im)) for im in images]
+        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        sheet = C.create_string_buffer(cols * w * rows * h * 4)
+        r, c = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.L.dbg_tile_sprites(self.h, n, ptrs, w, h, columns, sheet, len(sheet.raw), C.byref(r), C.byref(c)), "dbg_tile_sprites")
+        return sheet.raw, int(r.value), int(c.value)
+
+    def tile_sprites_device(self, d_rgba, d_off, n, w, h, columns, aligned16, d_sheet, stream=None):
+        """Device form (torch CUDA tensors; offsets as int64): returns (rows, columns)."""
+        r, c = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.L.dbg_tile_sprites_device(self.h, n, _ptr(d_rgba), _ptr(d_off), w, h, columns, 1 if aligned16 else 0, _ptr(d_sheet),
+                                                   d_sheet.numel(), C.byref(r), C.byref(c), stream), "dbg_tile_sprites_device")
+        return int(r.value), int(c.value)
 
     def trim(self):
         """Releases the grow-only scratch of the context (dbg_trim)."""

@@ -26,6 +26,7 @@
 #include "kernels.cuh"
 #include "png_kernels.cuh"
 #include "split_kernels.cuh"
+#include "sprite_kernels.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -1454,6 +1455,89 @@ extern "C" dbg_multi *dbg_multi_create(int n_devices, const int *device_ids)
 extern "C" int dbg_multi_device_count(const dbg_multi *m) { return m ? (int)m->ctx.size() : 0; }
 extern "C" dbg_ctx *dbg_multi_ctx(dbg_multi *m, int k) { return (m && k >= 0 && k < (int)m->ctx.size()) ? m->ctx[k] : nullptr; }
 extern "C" const char *dbg_multi_last_error(const dbg_multi *m) { return m ? m->err : g_err; }
+
+// ---------------------------------------------------------------- sprite sheets --
+static int sprite_grid(dbg_ctx *ctx, uint64_t n, uint32_t w, uint32_t h, uint32_t columns, uint64_t sheet_cap, uint32_t *rows_out,
+                       uint32_t *cols_out)
+{
+    if (n == 0 || w == 0 || h == 0 || n > 0x7fffffffull) {
+        set_err(ctx, "sprite sheet: no images, or a zero tile size");
+        return DBG_ERR_ARG;
+    }
+    uint64_t cols = columns;
+    if (cols == 0)
+        for (cols = 1; cols * cols < n; cols++) {}
+    if (cols > n) cols = n;
+    const uint64_t rows = (n + cols - 1) / cols;
+    const uint64_t sheet_w = cols * w, sheet_h = rows * h;
+    if (sheet_w > 0xffffffffull || sheet_h > 0xffffffffull || sheet_w * sheet_h > sheet_cap / 4) {
+        set_err(ctx, "sprite sheet: %llu x %llu pixels do not fit %llu bytes", (unsigned long long)sheet_w, (unsigned long long)sheet_h,
+                (unsigned long long)sheet_cap);
+        return DBG_ERR_ARG;
+    }
+    *rows_out = (uint32_t)rows;
+    *cols_out = (uint32_t)cols;
+    return DBG_OK;
+}
+
+extern "C" int dbg_tile_sprites_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_rgba, const uint64_t *d_rgba_off, uint32_t w, uint32_t h,
+                                       uint32_t columns, int offsets_16_aligned, uint8_t *d_sheet, uint64_t sheet_cap, uint32_t *out_rows,
+                                       uint32_t *out_columns, void *stream)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (!d_rgba || !d_rgba_off || !d_sheet) {
+        set_err(ctx, "dbg_tile_sprites_device: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    uint32_t rows = 0, cols = 0;
+    const int rc = sprite_grid(ctx, n, w, h, columns, sheet_cap, &rows, &cols);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const dbg::SpriteBatch b{d_rgba, d_rgba_off, d_sheet, (uint32_t)n, w, h, cols, rows};
+    const bool a16 = offsets_16_aligned && (((uintptr_t)d_rgba | (uintptr_t)d_sheet) & 15) == 0;
+    CU((cudaError_t)dbg::sprite_launch(b, a16, ctx->sm_count, stream ? (cudaStream_t)stream : ctx->stream));
+    ctx->launches += 1;
+    if (out_rows) *out_rows = rows;
+    if (out_columns) *out_columns = cols;
+    return DBG_OK;
+}
+
+extern "C" int dbg_tile_sprites(dbg_ctx *ctx, uint64_t n, const uint8_t *const *rgba, uint32_t w, uint32_t h, uint32_t columns,
+                                uint8_t *sheet, uint64_t sheet_cap, uint32_t *out_rows, uint32_t *out_columns)
+{
+    if (!ctx) return DBG_ERR_NO_DEVICE;
+    if (!rgba || !sheet) {
+        set_err(ctx, "dbg_tile_sprites: bad arguments");
+        return DBG_ERR_ARG;
+    }
+    uint32_t rows = 0, cols = 0;
+    int rc = sprite_grid(ctx, n, w, h, columns, sheet_cap, &rows, &cols);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; i++)
+        if (!rgba[i]) {
+            set_err(ctx, "dbg_tile_sprites: image %llu is NULL", (unsigned long long)i);
+            return DBG_ERR_ARG;
+        }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint64_t tile = (uint64_t)w * h * 4, tile_al = (tile + 15) & ~15ull, sheet_bytes = (uint64_t)cols * w * rows * h * 4;
+    CU(ctx->d_in.reserve(n * tile_al + 64));
+    CU(ctx->d_out.reserve(sheet_bytes + 64));
+    CU(ctx->h_desc.reserve(n * 8));
+    CU(ctx->d_desc.reserve(n * 8));
+    uint64_t *h_off = (uint64_t *)ctx->h_desc.p;
+    for (uint64_t i = 0; i < n; i++) {
+        h_off[i] = i * tile_al;
+        CU(cudaMemcpyAsync((uint8_t *)ctx->d_in.p + h_off[i], rgba[i], tile, cudaMemcpyHostToDevice, s));
+    }
+    CU(cudaMemcpyAsync(ctx->d_desc.p, h_off, n * 8, cudaMemcpyHostToDevice, s));
+    rc = dbg_tile_sprites_device(ctx, n, (const uint8_t *)ctx->d_in.p, (const uint64_t *)ctx->d_desc.p, w, h, cols, 1, (uint8_t *)ctx->d_out.p,
+                                 sheet_bytes, out_rows, out_columns, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(sheet, ctx->d_out.p, sheet_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return DBG_OK;
+}
 
 // ------------------------------------------------------------------- pipe -----
 // Several packed batches in flight on one GPU (see the header): `depth` workers, each a host thread with a context of

@@ -208,6 +208,22 @@ int dbg_multi_partition(int n_devices, int kind, uint64_t n, const uint8_t *h_in
                         const uint64_t *in_size, const uint64_t *out_off, const uint64_t *out_cap, uint32_t *device_of_item,
                         uint64_t *device_cost);
 
+/* ---- sprite sheets (intent of concat_pngs.c:81-100) -----------------------------------------------
+ * The reference's concat_pngs.c decodes a few PNGs and calls concatenate_images(to_concat, n, &sprite_rows,
+ * &sprite_columns), which its tree does not define; this is that step for a decoded batch: n RGBA8 images of w x h
+ * pixels each become the cells of one sheet of `columns` cells per row (0: ceil(sqrt(n))), image i in cell
+ * (i / columns, i % columns), cells without an image transparent black. The sheet is (columns * w) x (rows * h) pixels,
+ * rows = ceil(n / columns); sheet_cap must hold it. *out_rows / *out_columns (may be NULL) receive the grid.
+ * Device form: d_rgba_off is a device array of byte offsets into d_rgba (any 4-byte alignment; 16-byte aligned images
+ * and sheet with w % 4 == 0 take 16-byte accesses -- pass offsets_16_aligned = 1 when that holds). Returns DBG_ERR_ARG
+ * when the sheet does not fit or a size is zero. */
+int dbg_tile_sprites_device(dbg_ctx *ctx, uint64_t n, const uint8_t *d_rgba, const uint64_t *d_rgba_off, uint32_t w, uint32_t h,
+                            uint32_t columns, int offsets_16_aligned, uint8_t *d_sheet, uint64_t sheet_cap, uint32_t *out_rows,
+                            uint32_t *out_columns, void *stream);
+/* Host form: n pointers to decoded images (w * h * 4 bytes each), sheet in host memory. */
+int dbg_tile_sprites(dbg_ctx *ctx, uint64_t n, const uint8_t *const *rgba, uint32_t w, uint32_t h, uint32_t columns,
+                     uint8_t *sheet, uint64_t sheet_cap, uint32_t *out_rows, uint32_t *out_columns);
+
 /* ---- several packed batches in flight on one GPU ---------------------------------------------------------------
  * dbg_decode_batch_packed() returns when its batch is done, so back-to-back calls pay the ramp of every batch in full:
  * the download engine idles until the first wave's kernels have finished, the upload engine after the last wave's

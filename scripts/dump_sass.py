@@ -26,11 +26,11 @@ for line in txt.split("\n"):
         funcs[cur].append(f"/*{m.group(1)}*/  {m.group(2).strip()} ;")
 os.makedirs(OUT, exist_ok=True)
 for f in os.listdir(OUT):
-    if f.endswith(".sass"):
+    if f.endswith(".sass") and f.startswith(tag + "_"):  # listings of other rounds stay
         os.remove(os.path.join(OUT, f))
 rows = []
 for mangled, ins in funcs.items():
-    name = subprocess.run(["c++filt", mangled], capture_output=True, text=True).stdout.strip().split("(")[0].replace("dbg::", "")
+    name = subprocess.run(["c++filt", mangled], capture_output=True, text=True).stdout.strip().split("(")[0].replace("dbg::", "").replace("void ", "").replace("<", "_").replace(">", "")
     if not ins:
         continue
     with open(os.path.join(OUT, f"{tag}_{name}.sass"), "w") as fh:
@@ -38,7 +38,7 @@ for mangled, ins in funcs.items():
     cnt = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", i.split("  ", 1)[1]).split()[0].split(".")[0] for i in ins)
     keys = ["LDGSTS", "LDG", "STG", "LDS", "STS", "SHFL", "MATCH", "VOTE", "REDUX", "ATOMG", "ATOMS", "RED", "BAR", "WARPSYNC", "PRMT", "BRA", "LDL", "STL"]
     rows.append((name, len(ins), ", ".join(f"{k} {cnt[k]}" for k in keys if cnt[k])))
-with open(os.path.join(OUT, "README.md"), "w") as fh:
+with open(os.path.join(OUT, "README.md" if tag == "r01" else f"README_{tag}.md"), "w") as fh:
     fh.write(f"# SASS listings (round {tag[1:]}, sm_100a)\n\nOne file per kernel, from `cuobjdump -sass debigulator_b200/libdebigulator_b200.so` via\n"
              "`scripts/dump_sass.py` (instruction encodings stripped; `scripts/sass_ctrl.py` decodes the scheduling\n"
              "control fields when they are needed). `LDGSTS` is the cp.async global->shared staging of compressed input;\n"

@@ -194,3 +194,54 @@ def test_gpu_device_api_misaligned(ctx):
         size, want = checker.encode_bmp(it[0], it[1], it[2])
         assert esz[k].item() == size
         assert enc[e_off[k]:e_off[k] + size - 1].tobytes() == want, k
+
+
+def _sheet(images, w, h, cols):
+    n = len(images)
+    rows = (n + cols - 1) // cols
+    sheet = np.zeros((rows * h, cols * w, 4), np.uint8)
+    for i, im in enumerate(images):
+        r, c = divmod(i, cols)
+        sheet[r * h:(r + 1) * h, c * w:(c + 1) * w] = np.frombuffer(im, np.uint8).reshape(h, w, 4)
+    return sheet.tobytes(), rows
+
+
+@pytest.mark.gpu
+def test_sprite_sheet_tiling(ctx):
+    """dbg_tile_sprites / dbg_tile_sprites_device (the intent of the reference's concat_pngs.c:81-100, whose
+    concatenate_images() is not defined anywhere in the reference tree): decoded images become the cells of a row-major
+    grid, empty cells transparent black. Host and device forms, tile widths that do and do not allow 16-byte accesses,
+    the default square-ish grid and a caller-given number of columns -- against a numpy tiling; the device form on the
+    output of the PNG decoder."""
+    import torch
+    from debigulator_b200 import corpus
+    for n, w, h, cols in ((7, 96, 64, 0), (3, 33, 17, 0), (10, 64, 8, 4), (1, 5, 5, 0), (5, 40, 30, 5)):
+        images = [corpus.gradient_noise_rgba(w, h, 40 + i).tobytes() for i in range(n)]
+        got, r, c = ctx.tile_sprites(images, w, h, cols)
+        want_c = cols or next(k for k in range(1, n + 2) if k * k >= n)
+        want, want_r = _sheet(images, w, h, min(want_c, n))
+        assert (r, c) == (want_r, min(want_c, n)), (n, w, h, cols, r, c)
+        assert got == want, (n, w, h, cols)
+    # device form, fed by the PNG decoder's output arena
+    n, w, h = 6, 128, 96
+    files, pix = zip(*[corpus.png_cfg3(6 * i + 5, w, h) for i in range(n)])  # forced Paeth (a None-filtered tile this small trips rule Q12)
+    dev = torch.device("cuda", 0)
+    in_off = np.concatenate([[0], np.cumsum([(len(f) + 31) // 16 * 16 for f in files[:-1]])]).astype(np.int64)
+    h_in = np.zeros(int(in_off[-1]) + len(files[-1]) + 64, np.uint8)
+    for f, o in zip(files, in_off):
+        h_in[o:o + len(f)] = np.frombuffer(f, np.uint8)
+    rgba = w * h * 4
+    d_in = torch.from_numpy(h_in).to(dev)
+    d_out = torch.zeros(n * rgba, dtype=torch.uint8, device=dev)
+    t64 = lambda a: torch.from_numpy(np.asarray(a, np.int64)).to(dev)
+    o_off = t64(np.arange(n) * rgba)
+    st = torch.zeros(n, dtype=torch.int32, device=dev)
+    ctx.png_device(d_in, t64(in_off), t64([len(f) for f in files]), d_out, o_off, t64([rgba] * n), st, int(sum(len(f) for f in files)), n * rgba)
+    d_sheet = torch.zeros(3 * w * 2 * h * 4, dtype=torch.uint8, device=dev)
+    r, c = ctx.tile_sprites_device(d_out, o_off, n, w, h, 0, True, d_sheet)
+    torch.cuda.synchronize()
+    assert int(st.abs().sum()) == 0, st.tolist()
+    assert (r, c) == (2, 3)
+    assert d_sheet.cpu().numpy().tobytes() == _sheet(pix, w, h, 3)[0]
+    with pytest.raises(Exception):
+        ctx.tile_sprites_device(d_out, o_off, n, w, h, 0, True, d_sheet[:100])
