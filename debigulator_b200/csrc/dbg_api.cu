@@ -1561,6 +1561,7 @@ struct dbg_pipe {
     std::condition_variable cv_job, cv_done;
     std::deque<Job> queue;
     std::vector<std::pair<int64_t, int>> done;  // finished tickets not yet waited for
+    std::vector<int64_t> open_tickets;           // submitted, not yet waited for
     int64_t next_ticket = 0;
     int64_t upload_turn = 0;  // the ticket whose uploads may be enqueued: batches upload in ticket order, one after the other
     int in_flight = 0;        // submitted, not yet finished
@@ -1690,6 +1691,7 @@ extern "C" int64_t dbg_pipe_submit(dbg_pipe *p, int kind, uint64_t n, const uint
         p->cv_done.wait(lk, [&] { return p->in_flight < (int)p->ctx.size(); });
         ticket = p->next_ticket++;
         p->in_flight++;
+        p->open_tickets.push_back(ticket);
         p->queue.push_back(dbg_pipe::Job{ticket, kind, n, h_in, in_off, in_size, h_out, out_off, out_cap, out_size, status});
     }
     p->cv_job.notify_one();
@@ -1700,7 +1702,9 @@ extern "C" int dbg_pipe_wait(dbg_pipe *p, int64_t ticket)
 {
     if (!p) return DBG_ERR_NO_DEVICE;
     std::unique_lock<std::mutex> lk(p->mu);
-    if (ticket < 0 || ticket >= p->next_ticket) return DBG_ERR_ARG;
+    auto it = std::find(p->open_tickets.begin(), p->open_tickets.end(), ticket);
+    if (it == p->open_tickets.end()) return DBG_ERR_ARG;  // never handed out, or waited for already
+    p->open_tickets.erase(it);
     for (;;) {
         for (size_t k = 0; k < p->done.size(); k++)
             if (p->done[k].first == ticket) {

@@ -397,6 +397,7 @@ def test_pipe_keeps_batches_in_flight(ref):
             o = int(out_off[i])
             assert h_out[o:o + len(d)].tobytes() == d, (k, i)
     assert p.kernel_launches() > 0
+    assert p.L.dbg_pipe_wait(p.h, jobs[0][0]) == -3 and p.L.dbg_pipe_wait(p.h, 99) == -3  # waited for already / never handed out: DBG_ERR_ARG
     p.close()
 
 
