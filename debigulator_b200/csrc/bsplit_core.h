@@ -334,4 +334,39 @@ DBG_DEV uint32_t expand_tokens_warp(const uint32_t *tok, uint32_t ntok, uint16_t
     return err;
 }
 
+// A lone long stream has few chunks (one per block boundary the search found), and the expansion of a chunk is one warp's
+// latency chain (32 tokens per step, one L2 round trip each): gzipsample.gz spends 2.3 of its 3.9 ms there. A chunk's token
+// run can be cut anywhere: piece j starts at token j * piece_tok and at the output offset of everything before it, which is
+// a prefix sum of the token lengths. Every piece is then a marker domain of its own (a match that reaches before the piece
+// becomes a marker, resolved against the finished bytes of the pieces before it), expanded by a warp of its own.
+// Writes p_off[j] (output offset inside the stream) and p_len[j] for j < ceil(ntok / piece_tok); piece_tok must be a
+// multiple of 128 (the walk takes four tokens per lane and step, all four loads in flight at once). Warp-wide, uniform
+// result = the number of pieces.
+DBG_DEV uint32_t cut_token_pieces(const uint32_t *tok, uint32_t ntok, uint32_t piece_tok, uint64_t out0, uint64_t *p_off, uint32_t *p_len)
+{
+    const uint32_t ln = (uint32_t)simt::lane();
+    uint32_t run = 0, start = 0, j = 0;
+    for (uint32_t base = 0; base < ntok; base += 128) {
+        if (base % piece_tok == 0) {
+            if (ln == 0) {
+                p_off[j] = out0 + run;
+                if (j) p_len[j - 1] = run - start;
+            }
+            start = run;
+            j++;
+        }
+        uint32_t t[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] = base + 32 * k + ln < ntok ? simt::ldg_u32(tok + base + 32 * k + ln) : 0u;
+        uint32_t len = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) len += base + 32 * k + ln >= ntok ? 0u : (t[k] & TOKEN_MATCH) ? (t[k] >> 16) & 0x1ff : 1u;
+        for (int d = 16; d; d >>= 1) len += simt::shfl_xor(len, d);
+        run += len;
+    }
+    if (j && ln == 0) p_len[j - 1] = run - start;
+    simt::syncwarp();
+    return j;
+}
+
 }  // namespace dbg

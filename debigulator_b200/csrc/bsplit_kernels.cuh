@@ -322,4 +322,100 @@ __global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_decode_kernel(BsBatc
     }
 }
 
+// ---- pieces: a chunk's token run expanded by several warps (lone long streams; cut_token_pieces, bsplit_core.h) ----
+// Slot u = region * max_pieces + j. A chunk whose tokens are usable fills up to max_pieces slots of its region with pieces of
+// equal token count; a chunk that has to be Huffman-decoded again is one "piece" (p_ntok = BS_PIECE_DECODE); every other slot
+// is idle. The resolve kernels then take the slots as their marker domains.
+constexpr uint32_t BS_PIECE_DECODE = 0xffffffffu;
+constexpr uint32_t BS_PIECE_MIN_TOK = 1024;
+struct BsPieces {
+    uint32_t max_pieces;
+    uint32_t *p_stream;   // per slot
+    uint64_t *p_out_off;  // per slot: output offset inside the stream
+    uint32_t *p_out_len;  // per slot
+    uint32_t *p_flag;     // per slot: CH_IDLE = unused
+    uint32_t *p_ntok;     // per slot: tokens of the piece, or BS_PIECE_DECODE
+    uint32_t *p_base;     // per stream: first slot
+    uint32_t *p_count;    // per stream: slots
+};
+__device__ __forceinline__ uint32_t bs_piece_tok(uint32_t ntok, uint32_t max_pieces)
+{
+    uint32_t pt = ((ntok + max_pieces - 1) / max_pieces + 127) & ~127u;
+    return pt < BS_PIECE_MIN_TOK ? BS_PIECE_MIN_TOK : pt;
+}
+
+__global__ void bs_piece_ranges_kernel(BsBatch b, BsPieces q)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n) return;
+    q.p_base[s] = b.chunk_base[s] * q.max_pieces;
+    q.p_count[s] = (b.flag[s] && !b.redo[s]) ? b.nchunks[s] * q.max_pieces : 0u;
+}
+
+__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_pieces_kernel(BsBatch b, BsPieces q)
+{
+    const uint32_t total_regions = b.summary->total_regions;
+    const uint32_t ln = (uint32_t)simt::lane(), M = q.max_pieces;
+    const uint32_t warps = gridDim.x * BS_WARPS_PER_CTA;
+    for (uint32_t t = blockIdx.x * BS_WARPS_PER_CTA + (threadIdx.x >> 5); t < total_regions; t += warps) {
+        const uint32_t s = b.chunk_stream[t], u0 = t * M;
+        for (uint32_t j = ln; j < M; j += 32) {
+            q.p_stream[u0 + j] = s;
+            q.p_out_off[u0 + j] = 0;
+            q.p_out_len[u0 + j] = 0;
+            q.p_flag[u0 + j] = CH_IDLE;
+            q.p_ntok[u0 + j] = 0;
+        }
+        simt::syncwarp();
+        if (!b.flag[s] || b.redo[s] || b.status[s] != ST_OK || b.c_flag[t] == CH_IDLE) continue;
+        const uint32_t ntok = b.tok ? b.c_ntok[t] : 0u;
+        if (b.tok && ntok && ntok <= bs_tok_cap(b, s, b.cand[t], bs_next_hint(b, s, t))) {
+            const uint32_t pt = bs_piece_tok(ntok, M);
+            const uint32_t np = cut_token_pieces(b.tok + bs_tok_base(b, s, b.cand[t]), ntok, pt, b.c_out_off[t], q.p_out_off + u0, q.p_out_len + u0);
+            for (uint32_t j = ln; j < np; j += 32) {
+                q.p_flag[u0 + j] = j + 1 < np ? (uint32_t)CH_RUN : b.c_flag[t];
+                q.p_ntok[u0 + j] = j + 1 < np ? pt : ntok - j * pt;
+            }
+        } else if (ln == 0) {
+            q.p_out_off[u0] = b.c_out_off[t];
+            q.p_out_len[u0] = b.c_out_len[t];
+            q.p_flag[u0] = b.c_flag[t];
+            q.p_ntok[u0] = BS_PIECE_DECODE;
+        }
+        simt::syncwarp();
+    }
+}
+
+// One warp per slot: tokens -> 16-bit cells of the piece, or the chunk's second Huffman decode.
+__global__ void __launch_bounds__(BS_WARPS_PER_CTA * 32) bs_decode_pieces_kernel(BsBatch b, BsPieces q)
+{
+    const uint32_t M = q.max_pieces, total_slots = b.summary->total_regions * M;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    InflateSmem *sm = reinterpret_cast<InflateSmem *>(smem_raw) + (threadIdx.x >> 5);
+    const uint32_t warps = gridDim.x * BS_WARPS_PER_CTA;
+    for (uint32_t u = blockIdx.x * BS_WARPS_PER_CTA + (threadIdx.x >> 5); u < total_slots; u += warps) {
+        if (q.p_flag[u] == CH_IDLE) continue;
+        const uint32_t t = u / M, j = u - t * M, s = b.chunk_stream[t];
+        if (b.status[s] != ST_OK && q.p_ntok[u] != BS_PIECE_DECODE) continue;  // (another piece of the stream failed already)
+        uint16_t *cells = b.cells + b.cell_base[s] + q.p_out_off[u];
+        uint32_t st = ST_OK;
+        if (q.p_ntok[u] == BS_PIECE_DECODE) {
+            const uint64_t stop = b.c_flag[t] == CH_RUN ? b.exit_bits[t] : BS_NONE;
+            const ChunkResult r = decode_block_chunk<SINK_U16>(sm, b.in_base + b.in_off[s], b.in_size[s], b.cand[t], stop, cells,
+                                                               b.c_out_len[t], b.c_out_off[t]);
+            if (simt::lane() == 0 && b.lb_stats) atomicAdd(&b.lb_stats[4], 1u);
+            if (r.flag >= CH_ERR) st = r.flag - CH_ERR;
+            else if (r.out_bytes != b.c_out_len[t] || r.flag != b.c_flag[t]) st = ST_BAD_CODE;  // cannot happen: same decode twice
+        } else {
+            const uint32_t pt = bs_piece_tok(b.c_ntok[t], M);
+            uint32_t ob = 0;
+            st = expand_tokens_warp(b.tok + bs_tok_base(b, s, b.cand[t]) + (uint64_t)j * pt, q.p_ntok[u], cells, q.p_out_off[u], &ob);
+            if (simt::lane() == 0 && b.lb_stats && j == 0) atomicAdd(&b.lb_stats[3], 1u);
+            if (!st && ob != q.p_out_len[u]) st = ST_BAD_CODE;  // cannot happen: the cut summed the same lengths
+        }
+        if (simt::lane() == 0 && st) atomicMax(&b.status[s], st);
+        simt::syncwarp();
+    }
+}
+
 }  // namespace dbg

@@ -76,12 +76,12 @@ struct Slot {
     Buf sched;                       // work-queue order computed on the device when the caller brings none
     Buf round_tok;                   // token scratch of the warp-per-stream kernel's lane-parallel rounds (64 KiB per resident warp)
     Buf fx_stream, fx_chunks, fx_tok, cells, h_fx;            // lane-serial fixed-block path (fx_kernels.cuh)
-    Buf bs_stream, bs_region, bs_cells, bs_tok, h_bs;         // block-split path (bsplit_kernels.cuh)
+    Buf bs_stream, bs_region, bs_cells, bs_tok, bs_pieces, h_bs;  // block-split path (bsplit_kernels.cuh)
     Slot() { h_fx.pinned_host = h_bs.pinned_host = true; }
     void release()
     {
         Buf *all[] = {&counter, &meta, &png_scratch, &sched, &round_tok, &fx_stream, &fx_chunks, &fx_tok, &cells, &h_fx,
-                      &bs_stream, &bs_region, &bs_cells, &bs_tok, &h_bs};
+                      &bs_stream, &bs_region, &bs_cells, &bs_tok, &bs_pieces, &h_bs};
         for (Buf *b : all) b->release();
     }
 };
@@ -117,6 +117,8 @@ struct dbg_ctx {
     bool fx = true;                 // lane-serial path for single fixed-Huffman-block streams
     uint32_t bsplit_tok_per_byte = 4;             // token slots per compressed byte (0 = no tokens: decode twice)
     uint64_t bsplit_tok_max_bytes = 24ull << 30;  // the token area never grows beyond this
+    bool bs_pieces = true;                // DBG_BS_PIECES: chunks of a handful of long streams are expanded in pieces (cut_token_pieces)
+    uint32_t bs_pieces_max_slots = 512;   // ... into at most this many marker domains per call (16 per region when the regions are few)
     bool bsplit = true;
     bool rounds = true;             // the warp-per-stream kernel decodes Huffman blocks in lane-parallel rounds (DBG_ROUNDS)
     uint32_t round_bits = dbg::LB_ROUND_BITS;  // their length (DBG_ROUND_BITS)
@@ -246,6 +248,7 @@ static dbg_ctx *ctx_create(int device, const cudaStream_t *pre_wave, int n_pre, 
     if (const char *v = getenv("DBG_PNG_WAVES")) ctx->png_waves = std::min((int)dbg_ctx::MAX_WAVES, std::max(1, atoi(v)));
     if (const char *v = getenv("DBG_BSPLIT")) ctx->bsplit = atoi(v) != 0;
     if (const char *v = getenv("DBG_BSPLIT_LANES")) ctx->bsplit_lanes = atoi(v) != 0;
+    if (const char *v = getenv("DBG_BS_PIECES")) ctx->bs_pieces = atoi(v) != 0;
     if (const char *v = getenv("DBG_ROUNDS")) ctx->rounds = atoi(v) != 0;
     if (const char *v = getenv("DBG_ROUND_BITS")) ctx->round_bits = (uint32_t)std::min(1 << 20, std::max(8192, atoi(v)));
     if (const char *v = getenv("DBG_BSPLIT_ALL")) ctx->bsplit_all = atoi(v);
@@ -716,15 +719,45 @@ static int run_bsplit(dbg_ctx *ctx, Slot &sl, dbg::InflateBatch a, cudaStream_t 
     if (hs->cells_used) {
         CU(sl.bs_cells.reserve((size_t)hs->cells_used * 2 + 256));
         b.cells = (uint16_t *)sl.bs_cells.p;
-        dbg::bs_decode_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b);
-        // cells -> bytes with the resolve kernels
         dbg::SplitBatch r{};
         r.out_base = a.out_base; r.out_off = a.out_off; r.out_size = a.out_size; r.status = a.status; r.n = n;
-        r.split_flag = b.flag; r.redo = b.redo; r.chunk_base = b.chunk_base; r.nchunks = b.nchunks; r.cell_base = b.cell_base;
-        r.chunk_stream = b.chunk_stream; r.c_out_off = b.c_out_off; r.c_out_len = b.c_out_len; r.c_flag = b.c_flag;
-        r.cells = b.cells;
+        r.split_flag = b.flag; r.redo = b.redo; r.cell_base = b.cell_base; r.cells = b.cells;
+        // A handful of long streams (few regions): the expansion of a chunk is one warp's latency chain, so every chunk's token
+        // run is cut into up to 16 pieces, each expanded by a warp of its own and resolved as a marker domain of its own
+        // (gzipsample.gz as a batch of one: 2.3 of its 3.9 ms were that chain). Large batches have chunks enough.
+        // (at most bs_pieces_max_slots domains in all: the tails of a stream's domains are resolved one after the other)
+        const uint32_t M = (ctx->bs_pieces && b.tok) ? std::min<uint32_t>(16u, std::max<uint32_t>(1u, ctx->bs_pieces_max_slots / std::max<uint32_t>(T, 1u))) : 1u;
+        uint32_t domains = T;
+        if (M > 1) {
+            const size_t slots = (size_t)T * M;
+            CU(sl.bs_pieces.reserve(slots * (8 + 4 * 4) + (size_t)n * 8 + 256));
+            CU(cudaMemsetAsync(sl.bs_pieces.p, 0, slots * (8 + 4 * 4) + (size_t)n * 8, s));
+            dbg::BsPieces q{};
+            q.max_pieces = M;
+            q.p_out_off = (uint64_t *)sl.bs_pieces.p;
+            q.p_stream = (uint32_t *)(q.p_out_off + slots);
+            q.p_out_len = q.p_stream + slots;
+            q.p_flag = q.p_out_len + slots;
+            q.p_ntok = q.p_flag + slots;
+            q.p_base = q.p_ntok + slots;
+            q.p_count = q.p_base + n;
+            dbg::bs_piece_ranges_kernel<<<sb, 128, 0, s>>>(b, q);
+            dbg::bs_pieces_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, 0, s>>>(b, q);
+            const uint32_t pgrid = std::min<uint32_t>((uint32_t)((slots + dbg::BS_WARPS_PER_CTA - 1) / dbg::BS_WARPS_PER_CTA),
+                                                      (uint32_t)ctx->sm_count * dbg::INFLATE_CTAS_PER_SM);
+            dbg::bs_decode_pieces_kernel<<<pgrid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b, q);
+            ctx->launches += 2;
+            r.chunk_base = q.p_base; r.nchunks = q.p_count; r.chunk_stream = q.p_stream; r.c_out_off = q.p_out_off;
+            r.c_out_len = q.p_out_len; r.c_flag = q.p_flag;
+            domains = (uint32_t)slots;
+        } else {
+            dbg::bs_decode_kernel<<<grid, dbg::BS_WARPS_PER_CTA * 32, smem, s>>>(b);
+            r.chunk_base = b.chunk_base; r.nchunks = b.nchunks; r.chunk_stream = b.chunk_stream; r.c_out_off = b.c_out_off;
+            r.c_out_len = b.c_out_len; r.c_flag = b.c_flag;
+        }
+        // cells -> bytes with the resolve kernels
         dbg::split_resolve_tails_kernel<<<n, dbg::RESOLVE_THREADS, 0, s>>>(r);
-        dbg::split_resolve_body_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(r, T);
+        dbg::split_resolve_body_kernel<<<std::min<uint32_t>(domains, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(r, domains);
         ctx->launches += 3;
         CU(cudaGetLastError());
     }

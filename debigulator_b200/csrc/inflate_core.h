@@ -1147,11 +1147,23 @@ DBG_DEV uint32_t lane_round(const InflateSmem *sm, const BlockTables &bt, const 
     for (uint32_t j = 1; COMPACT && j < used; j++) {
         const uint32_t cnt = simt::shfl(mine, (int)j), dst0 = simt::shfl(in - mine, (int)j);
         const uint32_t *src = area + (uint64_t)j * stride;
-        for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
-            const uint32_t i = i0 + ln;
-            const uint32_t v = i < cnt ? src[i] : 0u;
+        // 128 tokens per step, the four loads of a lane before its stores: a run moves DOWN (dst0 + i < j * stride + i), so a
+        // store can only land on a source that was read in this step or an earlier one, never on a later one -- and one
+        // memory round trip now moves 128 tokens instead of 32 (the loop is a pure latency chain: tokens written a moment
+        // ago by other lanes come back through L2)
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = i0 + 32 * k + ln;
+                v[k] = i < cnt ? src[i] : 0u;
+            }
             simt::syncwarp();
-            if (i < cnt) area[dst0 + i] = v;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = i0 + 32 * k + ln;
+                if (i < cnt) area[dst0 + i] = v[k];
+            }
             simt::syncwarp();
         }
     }

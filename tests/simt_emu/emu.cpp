@@ -13,6 +13,7 @@
 #define DBG_SIMT_EMU 1
 #include <stdint.h>
 #include <stdlib.h>
+#include <vector>
 #include <string.h>
 #include <ucontext.h>
 
@@ -257,7 +258,10 @@ struct BsArgs {
     const uint16_t *kraft;
     const uint8_t *in;
     uint64_t in_size;
-    int mode;  // 0 search, 1 count, 2 decode, 3 expand tokens
+    int mode;  // 0 search, 1 count, 2 decode, 3 expand tokens, 4 cut the token run into pieces
+    uint32_t piece_tok, npieces[32];
+    uint64_t out0, *p_off;
+    uint32_t *p_len;
     uint32_t *tok;
     uint32_t tok_cap, ntok, exp_bytes[32], exp_st[32];
     int lanes;
@@ -277,15 +281,17 @@ static void bs_body(void *p)
         a->res[l] = dbg::decode_block_chunk<dbg::SINK_TOKENS>(a->sm, a->in, a->in_size, a->start, a->stop, nullptr, 0, 0, a->tok, a->tok_cap, a->lanes != 0);
     else if (a->mode == 1) a->res[l] = dbg::decode_block_chunk<dbg::SINK_COUNT>(a->sm, a->in, a->in_size, a->start, a->stop, nullptr, 0, 0);
     else if (a->mode == 3) a->exp_st[l] = dbg::expand_tokens_warp(a->tok, a->ntok, a->cells, a->abs_base, &a->exp_bytes[l]);
+    else if (a->mode == 4) a->npieces[l] = dbg::cut_token_pieces(a->tok, a->ntok, a->piece_tok, a->out0, a->p_off, a->p_len);
     else a->res[l] = dbg::decode_block_chunk<dbg::SINK_U16>(a->sm, a->in, a->in_size, a->start, a->stop, a->cells, a->cell_cap, a->abs_base);
 }
 
 // The block-split pipeline (search, count, chain, 16-bit decode, resolve) of bsplit_kernels.cuh run
 // region by region through the emulator. Returns the status; 0x4000 = the chain did not close (the
 // product would hand the stream back to the warp-per-stream kernel). *n_chunks = hinted regions used.
-extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
-                                       int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks, uint32_t tok_per_byte,
-                                       int lanes)
+// max_pieces > 1: a chunk's tokens are expanded as up to that many pieces, each a marker domain of its own (cut_token_pieces)
+static uint32_t bsplit_inflate_impl(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
+                                    int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks, uint32_t tok_per_byte,
+                                    int lanes, uint32_t max_pieces)
 {
     size_t arena_sz = ((size_t)in_size + 64 + 32 + 15) & ~(size_t)15;
     uint8_t *arena = (uint8_t *)aligned_alloc(16, arena_sz);
@@ -349,17 +355,54 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
             a.cells = cells + ooff[c]; a.cell_cap = olen[c]; a.abs_base = ooff[c];
             uint64_t nh = next_hint(c);
             uint32_t cap_c = tokens ? (uint32_t)(tok_per_byte * ((nh == dbg::BS_NONE ? in_size : nh >> 3) - (cand[c] >> 3))) : 0;
+            if (tokens && ntok[c] <= cap_c && max_pieces > 1 && ntok[c]) {
+                // the product's piece scheme: cut, expand every piece on its own, resolve the pieces in order
+                uint32_t *ctok = tokens + (size_t)tok_per_byte * (cand[c] >> 3);
+                uint32_t pt = (ntok[c] + max_pieces - 1) / max_pieces;
+                pt = (pt + 127) & ~127u;
+                std::vector<uint64_t> poff(max_pieces + 1);
+                std::vector<uint32_t> plen(max_pieces + 1);
+                a.mode = 4; a.tok = ctok; a.ntok = ntok[c]; a.piece_tok = pt; a.out0 = ooff[c]; a.p_off = poff.data(); a.p_len = plen.data();
+                simt::run_warp(bs_body, &a, reverse);
+                const uint32_t np = a.npieces[0];
+                if (np == 0 || np > max_pieces) { status = 0x3001; continue; }
+                uint64_t sum = 0;
+                for (uint32_t j = 0; j < np && !status; j++) {
+                    if (poff[j] != ooff[c] + sum) status = 0x3002;
+                    sum += plen[j];
+                    a.mode = 3; a.tok = ctok + (size_t)j * pt; a.ntok = j + 1 < np ? pt : ntok[c] - j * pt;
+                    a.cells = cells + poff[j]; a.abs_base = poff[j];
+                    simt::run_warp(bs_body, &a, reverse);
+                    if (a.exp_st[0]) status = a.exp_st[0];
+                    else if (a.exp_bytes[0] != plen[j]) status = 0x3000;
+                    for (uint32_t i = 0; i < plen[j] && !status; i++) {  // resolve this piece (its markers point before it)
+                        uint32_t v = cells[poff[j] + i];
+                        out[poff[j] + i] = v < 256 ? (uint8_t)v : out[poff[j] + (int64_t)v - 33024];
+                    }
+                }
+                if (!status && sum != olen[c]) status = 0x3003;
+                flag[c] = dbg::CH_IDLE;  // resolved already
+                (*n_chunks) += 0x10000;
+                continue;
+            }
             if (tokens && ntok[c] <= cap_c) {
                 a.mode = 3; a.tok = tokens + (size_t)tok_per_byte * (cand[c] >> 3); a.ntok = ntok[c];
                 simt::run_warp(bs_body, &a, reverse);
                 if (a.exp_st[0]) status = a.exp_st[0];
                 else if (a.exp_bytes[0] != olen[c]) status = 0x3000;
                 (*n_chunks) += 0x10000;  // high half: chunks expanded from tokens
-                continue;
+            } else {
+                simt::run_warp(bs_body, &a, reverse);
+                if (a.res[0].flag >= dbg::CH_ERR) status = a.res[0].flag - dbg::CH_ERR;
+                else if (a.res[0].out_bytes != olen[c] || a.res[0].flag != flag[c]) status = 0x3000;
             }
-            simt::run_warp(bs_body, &a, reverse);
-            if (a.res[0].flag >= dbg::CH_ERR) status = a.res[0].flag - dbg::CH_ERR;
-            else if (a.res[0].out_bytes != olen[c] || a.res[0].flag != flag[c]) status = 0x3000;
+            if (max_pieces > 1 && !status) {  // pieces are resolved as they come, so everything before them must be bytes already
+                for (uint32_t i = 0; i < olen[c]; i++) {
+                    uint32_t v = cells[ooff[c] + i];
+                    out[ooff[c] + i] = v < 256 ? (uint8_t)v : out[ooff[c] + (int64_t)v - 33024];
+                }
+                flag[c] = dbg::CH_IDLE;
+            }
         }
         for (uint32_t c = 0; c < nreg && !status; c++) {
             if (flag[c] == dbg::CH_IDLE) continue;
@@ -373,6 +416,19 @@ extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint
     }
     free(cand); free(exitb); free(ooff); free(olen); free(flag); free(ntok); free(tokens); free(sm); free(arena);
     return status;
+}
+
+extern "C" uint32_t emu_bsplit_inflate(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
+                                       int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks, uint32_t tok_per_byte,
+                                       int lanes)
+{
+    return bsplit_inflate_impl(in, in_size, out, cap, final_size, misalign, reverse, region_bytes, n_chunks, tok_per_byte, lanes, 1);
+}
+extern "C" uint32_t emu_bsplit_inflate_pieces(const uint8_t *in, uint64_t in_size, uint8_t *out, uint64_t cap, uint64_t *final_size,
+                                              int misalign, int reverse, uint32_t region_bytes, uint32_t *n_chunks,
+                                              uint32_t tok_per_byte, int lanes, uint32_t max_pieces)
+{
+    return bsplit_inflate_impl(in, in_size, out, cap, final_size, misalign, reverse, region_bytes, n_chunks, tok_per_byte, lanes, max_pieces);
 }
 
 extern "C" void emu_lane_block_stats(uint32_t *tried, uint32_t *done, int reset)

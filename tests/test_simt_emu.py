@@ -99,6 +99,36 @@ def test_png_fixture_small(emu, manifest, golden_dir):
         assert sha(ob.raw[: f["w"] * f["h"] * 4]) == f["ref_sha256"], name
 
 
+def test_block_split_token_pieces(emu, ref):
+    """cut_token_pieces (bsplit_core.h): a chunk's token run expanded as several pieces, each a marker domain of its own --
+    what a lone long stream gets so that its expansion is not one warp's latency chain. Same streams as the lane-parallel
+    test, several piece counts, against the reference's inflate()."""
+    import zlib
+    from debigulator_b200 import corpus
+    emu.emu_bsplit_inflate_pieces.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int,
+                                              C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.c_uint32]
+    emu.emu_bsplit_inflate_pieces.restype = C.c_uint32
+    text = corpus.word_salad(300000, 33)
+    img = corpus.gradient_noise_rgba(200, 150, 6)
+    cases = [corpus.raw_deflate(text, 6), corpus.raw_deflate(text, 1), corpus.raw_deflate(corpus.png_filter_rows(img, 4), 6),
+             corpus.raw_deflate(corpus.runs(600000, 7), 6), corpus.raw_deflate(corpus.periodic(500000, 3, 31000), 6)]
+    pieced = 0
+    for k, z in enumerate(cases):
+        cap = 700000
+        want_good, want = ref.inflate(z, cap)
+        for region, pieces in ((32768, 16), (16384, 4), (65536, 7)):
+            ib = C.create_string_buffer(z, len(z))
+            ob = C.create_string_buffer(cap + 64)
+            n, nch = C.c_uint64(0), C.c_uint32(0)
+            st = emu.emu_bsplit_inflate_pieces(ib, len(z), ob, cap, C.byref(n), (5 * k) % 16, k & 1, region, C.byref(nch), 4, 1, pieces)
+            if st == 0x4000:
+                continue
+            assert st == 0 and want_good == 1, (k, region, pieces, hex(st))
+            assert ob.raw[: n.value] == want, (k, region, pieces)
+            pieced += nch.value >> 16
+    assert pieced >= 10
+
+
 def test_png_unfilter_row_classes(emu, ref):
     """RGBA8 bands by row class (png_unfilter_band4): None/Up bands by columns, None/Sub bands by rows, the wavefront with and
     without Paeth rows, mixed bands, widths around the 32-pixel block and heights around the 32-row band."""
