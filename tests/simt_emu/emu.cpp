@@ -532,3 +532,26 @@ extern "C" uint32_t emu_crc32(const uint8_t *p, uint64_t n, int reverse)
     free(a.tables);
     return c;
 }
+
+// paeth4_swar (png_core.h) against the scalar definition (decode_png.c:441-487) for every byte triple, four different
+// triples per word so that the byte lanes are seen not to leak into each other. Returns the number of mismatches.
+extern "C" uint64_t emu_paeth4_mismatches()
+{
+    auto paeth = [](int a, int b, int c) {
+        int pa = b - c, pb = a - c, pc = a + b - 2 * c;
+        pa = pa < 0 ? -pa : pa; pb = pb < 0 ? -pb : pb; pc = pc < 0 ? -pc : pc;
+        return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+    };
+    uint64_t bad = 0;
+    for (int a = 0; a < 256; a++)
+        for (int b = 0; b < 256; b++)
+            for (int c = 0; c < 256; c++) {
+                const uint32_t A = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)(255 - a) << 24);
+                const uint32_t B = (uint32_t)b | ((uint32_t)c << 8) | ((uint32_t)a << 16) | ((uint32_t)b << 24);
+                const uint32_t Cw = (uint32_t)c | ((uint32_t)a << 8) | ((uint32_t)b << 16) | ((uint32_t)(c ^ 0x55) << 24);
+                const uint32_t want = (uint32_t)paeth(a, b, c) | ((uint32_t)paeth(b, c, a) << 8) | ((uint32_t)paeth(c, a, b) << 16) |
+                                      ((uint32_t)paeth(255 - a, b, c ^ 0x55) << 24);
+                if (dbg::paeth4_swar(A, B, Cw) != want) bad++;
+            }
+    return bad;
+}

@@ -129,6 +129,13 @@ def test_block_split_token_pieces(emu, ref):
     assert pieced >= 10
 
 
+def test_paeth_swar_exhaustive(emu):
+    """paeth4_swar (four channels per 32-bit word, png_core.h) equals the scalar Paeth predictor (decode_png.c:441-487) for
+    all 2^24 byte triples. (The device build replaces two helpers by VABSDIFF4 / PRMT; the GPU parity suite covers those.)"""
+    emu.emu_paeth4_mismatches.restype = C.c_uint64
+    assert emu.emu_paeth4_mismatches() == 0
+
+
 def test_png_unfilter_row_classes(emu, ref):
     """RGBA8 bands by row class (png_unfilter_band4): None/Up bands by columns, None/Sub bands by rows, the wavefront with and
     without Paeth rows, mixed bands, widths around the 32-pixel block and heights around the 32-row band."""
